@@ -1,0 +1,403 @@
+/*
+ * mc33_api.c -- the marching_cubes_33.h API in plain C on top of the CUDA C-ABI
+ * (include/mc33cu.h).  Compiled once per element-type variant, exactly like the
+ * reference library is (reference source/libMC33.c:17-34 and
+ * include/marching_cubes_33.h:57-88):
+ *
+ *   default                                   float grid,   MC33_real float
+ *   -DGRD_TYPE_SIZE=8                         double grid,  MC33_real double
+ *   -DINTEGER_GRD -DGRD_TYPE_SIZE={1,2,4}     u8/u16/u32,   MC33_real float
+ *   -DGRD_ORTHOGONAL                          no inclined-grid members
+ *   -DMC33_NORMAL_NEG=1  -DDEFAULT_SURFACE_COLOR=0x..   as in the reference
+ *
+ * What each function replaces is cited at its definition.  Nothing here does
+ * marching cubes arithmetic: the host side wraps grids, snapshots geometry,
+ * moves bytes and owns the malloc'ed result arrays.
+ */
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/marching_cubes_33.h"
+#include "../../include/mc33cu.h"
+
+#ifndef DEFAULT_SURFACE_COLOR
+#define DEFAULT_SURFACE_COLOR 0xff5c5c5c
+#endif
+#ifndef MC33_NORMAL_NEG
+#define MC33_NORMAL_NEG 0
+#endif
+
+#if defined(INTEGER_GRD)
+#  if GRD_TYPE_SIZE == 1
+#    define MC33_DTYPE MC33CU_U8
+#  elif GRD_TYPE_SIZE == 2
+#    define MC33_DTYPE MC33CU_U16
+#  else
+#    define MC33_DTYPE MC33CU_U32
+#  endif
+#elif GRD_TYPE_SIZE == 8
+#  define MC33_DTYPE MC33CU_F64
+#else
+#  define MC33_DTYPE MC33CU_F32
+#endif
+
+/* reference marching_cubes_33.c:76-80 */
+int DefaultColorMC = (int)DEFAULT_SURFACE_COLOR;
+
+/* The MC33 handed to the caller is the head of this private record. */
+typedef struct {
+	MC33 pub;
+	mc33cu_ctx *ctx;
+	int grid_uploaded;
+} mc33_private;
+
+/* ------------------------------------------------------------------------- */
+/* 3x3 helpers: reference MC33_util_grd.c:86-121                              */
+/* ------------------------------------------------------------------------- */
+#ifndef GRD_ORTHOGONAL
+void _multTSA_bf(const double (*A)[3], MC33_real *b, MC33_real *c, int t)
+{
+	if (t) {
+		c[2] = (MC33_real)(A[0][2] * b[0] + A[1][2] * b[1] + A[2][2] * b[2]);
+		c[1] = (MC33_real)(A[0][1] * b[0] + A[1][1] * b[1]);
+		c[0] = (MC33_real)(A[0][0] * b[0]);
+	} else {
+		c[0] = (MC33_real)(A[0][0] * b[0] + A[0][1] * b[1] + A[0][2] * b[2]);
+		c[1] = (MC33_real)(A[1][1] * b[1] + A[1][2] * b[2]);
+		c[2] = (MC33_real)(A[2][2] * b[2]);
+	}
+}
+
+void _multA_bf(const double (*A)[3], MC33_real *b, MC33_real *c, int t)
+{
+	double r[3];
+	for (int i = 0; i < 3; i++)
+		r[i] = t ? A[0][i] * b[0] + A[1][i] * b[1] + A[2][i] * b[2]
+		         : A[i][0] * b[0] + A[i][1] * b[1] + A[i][2] * b[2];
+	for (int i = 0; i < 3; i++) c[i] = (MC33_real)r[i];
+}
+
+void (*mult_Abf)(const double (*)[3], MC33_real *, MC33_real *, int) = _multA_bf;
+
+void setIdentMat3x3d(double (*A)[3])
+{
+	for (int j = 0; j < 3; j++)
+		for (int i = 0; i < 3; i++) A[j][i] = (i == j) ? 1.0 : 0.0;
+}
+#endif
+
+/* Markers for MC33.store.  In the reference these are the four vertex store
+ * routines (marching_cubes_33.c:485-621); here the store runs on the GPU and the
+ * pointer only records which variant create_MC33 selected. */
+unsigned int MC33_spn0(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
+unsigned int MC33_spnA(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
+unsigned int MC33_spnB(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
+#ifndef GRD_ORTHOGONAL
+unsigned int MC33_spnC(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* grids: reference MC33_util_grd.c:125-169, :585-686                         */
+/* ------------------------------------------------------------------------- */
+void free_memory_grd(_GRD *Z)
+{
+	if (!Z) return;
+	if (Z->F) {
+		for (unsigned int k = 0; k <= Z->N[2]; k++) {
+			if (Z->internal_data) {
+				if (!Z->F[k]) break;
+				for (unsigned int j = 0; j <= Z->N[1]; j++) free(Z->F[k][j]);
+			}
+			free(Z->F[k]);
+		}
+		free(Z->F);
+	}
+	free(Z);
+}
+
+/* one malloc per x-row, like the reference: callers may free rows themselves */
+int alloc_F(_GRD *Z)
+{
+	const unsigned int ny1 = Z->N[1] + 1, nz1 = Z->N[2] + 1;
+	const size_t rowb = ((size_t)Z->N[0] + 1) * sizeof(GRD_data_type);
+	Z->F = (GRD_data_type ***)malloc(nz1 * sizeof(void *));
+	if (!Z->F) return -1;
+	for (unsigned int k = 0; k < nz1; k++) {
+		Z->F[k] = (GRD_data_type **)malloc(ny1 * sizeof(void *));
+		if (!Z->F[k]) return -1;
+		for (unsigned int j = 0; j < ny1; j++) {
+			Z->F[k][j] = (GRD_data_type *)malloc(rowb);
+			if (!Z->F[k][j]) {
+				while (j) free(Z->F[k][--j]);
+				free(Z->F[k]);
+				Z->F[k] = 0;
+				return -1;
+			}
+		}
+	}
+	Z->internal_data = 1;
+	return 0;
+}
+
+static void grd_defaults(_GRD *Z)
+{
+#ifndef GRD_ORTHOGONAL
+	for (int i = 0; i < 3; i++) Z->Ang[i] = 90.0f;
+	Z->nonortho = 0;
+	setIdentMat3x3d(Z->_A);
+	setIdentMat3x3d(Z->A_);
+#else
+	(void)Z;
+#endif
+}
+
+_GRD *grid_from_data_pointer(unsigned int Nx, unsigned int Ny, unsigned int Nz, GRD_data_type *data)
+{
+	if (!data || !Nx || !Ny || !Nz) return 0;
+	_GRD *Z = (_GRD *)malloc(sizeof(_GRD));
+	if (!Z) return 0;
+	Z->internal_data = 0;
+	Z->F = (GRD_data_type ***)malloc(Nz * sizeof(void *));
+	if (!Z->F) { free(Z); return 0; }
+	for (unsigned int k = 0; k < Nz; k++) {
+		GRD_data_type **rows = (GRD_data_type **)malloc(Ny * sizeof(void *));
+		if (!rows) {
+			while (k) free(Z->F[--k]);
+			free(Z->F); free(Z);
+			return 0;
+		}
+		for (unsigned int j = 0; j < Ny; j++) rows[j] = data + ((size_t)k * Ny + j) * Nx;
+		Z->F[k] = rows;
+	}
+	Z->N[0] = Nx - 1; Z->N[1] = Ny - 1; Z->N[2] = Nz - 1;
+	for (int i = 0; i < 3; i++) {
+		Z->L[i] = (float)Z->N[i];
+		Z->d[i] = 1.0;
+		Z->r0[i] = 0.0;
+	}
+	grd_defaults(Z);
+	return Z;
+}
+
+_GRD *generate_grid_from_fn(double xi, double yi, double zi, double xf, double yf, double zf,
+                            double dx, double dy, double dz, double (*fn)(double x, double y, double z))
+{
+	double lo[3] = {xi, yi, zi}, hi[3] = {xf, yf, zf}, st[3] = {dx, dy, dz};
+	for (int i = 0; i < 3; i++) {
+		if (st[i] <= 0 || lo[i] == hi[i]) return 0;
+		if (lo[i] > hi[i]) { double t = lo[i]; lo[i] = hi[i]; hi[i] = t; }
+		if (hi[i] - lo[i] < st[i]) st[i] = hi[i] - lo[i];
+	}
+	_GRD *Z = (_GRD *)malloc(sizeof(_GRD));
+	if (!Z) return 0;
+	for (int i = 0; i < 3; i++) Z->N[i] = (unsigned int)(int)((hi[i] - lo[i]) / st[i] + 0.5);
+	if (alloc_F(Z)) { free_memory_grd(Z); return 0; }
+	for (int i = 0; i < 3; i++) { Z->d[i] = st[i]; Z->r0[i] = lo[i]; }
+	if (fn) {
+		/* coordinates are accumulated (x += dx) in double, as the reference does
+		 * (MC33_util_grd.c:661-672): this decides the last bits of the samples */
+		double z = lo[2];
+		for (unsigned int k = 0; k <= Z->N[2]; k++, z += st[2]) {
+			double y = lo[1];
+			for (unsigned int j = 0; j <= Z->N[1]; j++, y += st[1]) {
+				GRD_data_type *row = Z->F[k][j];
+				double x = lo[0];
+				for (unsigned int i = 0; i <= Z->N[0]; i++, x += st[0]) row[i] = (GRD_data_type)fn(x, y, z);
+			}
+		}
+	}
+	for (int i = 0; i < 3; i++) Z->L[i] = (float)(Z->N[i] * Z->d[i]);
+	grd_defaults(Z);
+	return Z;
+}
+
+/* ------------------------------------------------------------------------- */
+/* surfaces: reference marching_cubes_33.c:84-127                             */
+/* ------------------------------------------------------------------------- */
+void free_surface_memory(surface *S)
+{
+	if (!S) return;
+	free(S->T); free(S->V); free(S->N); free(S->color);
+	free(S);
+}
+
+static int shrink(void **p, size_t bytes)
+{
+	void *q = malloc(bytes ? bytes : 1);
+	if (!q) return -1;
+	memcpy(q, *p, bytes);
+	free(*p);
+	*p = q;
+	return 0;
+}
+
+void adjustvectorlenght_s(surface *S)
+{
+	if (!S) return;
+	if (S->capv > S->nV) {
+		if (shrink((void **)&S->color, sizeof(int) * S->nV)) return;
+		if (shrink((void **)&S->N, 3 * sizeof(float) * S->nV)) return;
+		if (shrink((void **)&S->V, 3 * sizeof(MC33_real) * S->nV)) return;
+		S->capv = S->nV;
+	}
+	if (S->capt > S->nT) {
+		if (shrink((void **)&S->T, 3 * sizeof(int) * S->nT)) return;
+		S->capt = S->nT;
+	}
+}
+
+/* ------------------------------------------------------------------------- */
+/* extractor: reference marching_cubes_33.c:1727-1940                         */
+/* ------------------------------------------------------------------------- */
+void free_MC33(MC33 *M)
+{
+	if (!M) return;
+	mc33_private *p = (mc33_private *)M;
+	mc33cu_destroy(p->ctx);
+	free(p);
+}
+
+static void describe(const MC33 *M, mc33cu_desc *d)
+{
+	memset(d, 0, sizeof *d);
+	d->dtype = MC33_DTYPE;
+	d->nx = M->nx; d->ny = M->ny; d->nz = M->nz;
+	d->z_lo = 0; d->z_hi = M->nz + 1;
+	d->cell_z0 = 0; d->cell_z1 = M->nz;
+	d->is_last = 1;
+	d->normal_neg = MC33_NORMAL_NEG;
+	d->store = M->store == MC33_spn0 ? MC33CU_SPN0 : M->store == MC33_spnA ? MC33CU_SPNA
+	         : M->store == MC33_spnB ? MC33CU_SPNB : -1;
+	for (int i = 0; i < 3; i++) { d->O[i] = M->O[i]; d->D[i] = M->D[i]; }
+	d->ca = M->ca; d->cb = M->cb;
+	d->A[0] = d->A[4] = d->A[8] = 1.0;
+	d->Ai[0] = d->Ai[4] = d->Ai[8] = 1.0;
+#ifndef GRD_ORTHOGONAL
+	if (M->store == MC33_spnC) {
+		d->store = MC33CU_SPNC;
+		for (int j = 0; j < 3; j++)
+			for (int i = 0; i < 3; i++) { d->A[3 * j + i] = M->_A[j][i]; d->Ai[3 * j + i] = M->A_[j][i]; }
+		/* a user-supplied mult_Abf cannot run on the GPU: only the two library
+		 * routines are recognised */
+		d->tsa = mult_Abf == _multTSA_bf ? 1 : (mult_Abf == _multA_bf ? 0 : -1);
+	}
+#endif
+}
+
+MC33 *create_MC33(_GRD *G)
+{
+	if (!G || !G->F) return 0;
+	mc33_private *p = (mc33_private *)calloc(1, sizeof(mc33_private));
+	if (!p) return 0;
+	MC33 *M = &p->pub;
+	M->nx = G->N[0]; M->ny = G->N[1]; M->nz = G->N[2];
+	M->ca = M->cb = 1;   /* the reference leaves these unset unless spnB is chosen */
+	/* choice of store variant and geometry snapshot: reference c:1762-1782 */
+#ifndef GRD_ORTHOGONAL
+	if (G->nonortho) {
+		M->store = MC33_spnC;
+		for (int j = 0; j < 3; j++)
+			for (int i = 0; i < 3; i++) {
+				M->_A[j][i] = G->_A[j][i] * G->d[i];
+				M->A_[j][i] = G->A_[j][i] / G->d[j];
+			}
+	} else
+#endif
+	if (G->d[0] != G->d[1] || G->d[1] != G->d[2]) {
+		M->ca = (MC33_real)(G->d[2] / G->d[0]);
+		M->cb = (MC33_real)(G->d[2] / G->d[1]);
+		M->store = MC33_spnB;
+	} else {
+		M->store = (G->d[0] == 1 && G->r0[0] == 0 && G->r0[1] == 0 && G->r0[2] == 0) ? MC33_spn0 : MC33_spnA;
+	}
+	for (int j = 0; j < 3; j++) {
+		M->O[j] = (MC33_real)G->r0[j];
+		M->D[j] = (MC33_real)G->d[j];
+	}
+	M->F = (const GRD_data_type ***)G->F;
+	if (!M->nx || !M->ny || !M->nz) { free(p); return 0; }
+	mc33cu_desc d;
+	describe(M, &d);
+	if (d.tsa < 0) d.tsa = 0;
+	if (mc33cu_create(&d, 0, &p->ctx) != MC33CU_OK) {
+		if (getenv("MC33_B200_VERBOSE")) fprintf(stderr, "create_MC33: %s\n", mc33cu_last_error());
+		free(p);
+		return 0;
+	}
+	return M;
+}
+
+/* shared front half of calculate_isosurface / size_of_isosurface: bring the
+ * samples to the device and count */
+static int count_on_device(MC33 *M, MC33_real iso, mc33cu_counts *k)
+{
+	mc33_private *p = (mc33_private *)M;
+	mc33cu_desc d;
+	describe(M, &d);
+	if (d.store < 0 || d.tsa < 0) return MC33CU_ERR_ARG;
+	int rc = mc33cu_set_geometry(p->ctx, &d);
+	if (rc) return rc;
+	/* The reference reads the samples at calculate time (c:1792, c:1820), so they
+	 * are uploaded on every call; MC33_B200_CACHE_GRID=1 promises they do not
+	 * change between calls on the same MC33 and uploads them once. */
+	const char *cache = getenv("MC33_B200_CACHE_GRID");
+	if (!(p->grid_uploaded && cache && cache[0] == '1')) {
+		rc = mc33cu_grid_upload_rows(p->ctx, (const void *const *const *)M->F);
+		if (rc) return rc;
+		p->grid_uploaded = 1;
+	}
+	M->iso = iso;
+	return mc33cu_count(p->ctx, (double)iso, k);
+}
+
+unsigned long long size_of_isosurface(MC33 *M, MC33_real iso, unsigned int *nV, unsigned int *nT)
+{
+	mc33cu_counts k;
+	if (!M || count_on_device(M, iso, &k) != MC33CU_OK) {
+		if (nV) *nV = 0;
+		if (nT) *nT = 0;
+		return 0;
+	}
+	M->nV = (unsigned int)k.nV; M->nT = (unsigned int)k.nT;
+	if (nV) *nV = (unsigned int)k.nV;
+	if (nT) *nT = (unsigned int)k.nT;
+	/* same formula as the reference, including its 6*sizeof(MC33_real) (c:1939) */
+	return k.nV * (6 * sizeof(MC33_real) + sizeof(int)) + k.nT * (3 * sizeof(int)) + sizeof(surface);
+}
+
+surface *calculate_isosurface(MC33 *M, MC33_real iso)
+{
+	if (!M) return 0;
+	mc33_private *p = (mc33_private *)M;
+	surface *S = (surface *)calloc(1, sizeof(surface));
+	if (!S) return 0;
+	mc33cu_counts k;
+	M->memoryfault = 0;
+	int rc = count_on_device(M, iso, &k);
+	if (rc != MC33CU_OK) goto fail;
+	if (k.nV == 0) {
+		/* empty isosurface: zero-filled struct, iso included (reference c:1880-1883) */
+		M->nV = M->nT = 0;
+		return S;
+	}
+	S->nV = (unsigned int)k.nV; S->nT = (unsigned int)k.nT;
+	S->capv = S->nV; S->capt = S->nT ? S->nT : 1;
+	S->iso = iso;
+	S->T = (unsigned int (*)[3])malloc((size_t)S->capt * 3 * sizeof(int));
+	S->V = (MC33_real (*)[3])malloc((size_t)S->capv * 3 * sizeof(MC33_real));
+	S->N = (float (*)[3])malloc((size_t)S->capv * 3 * sizeof(float));
+	S->color = (int *)malloc((size_t)S->capv * sizeof(int));
+	if (!S->T || !S->V || !S->N || !S->color) goto fail;
+	rc = mc33cu_emit_host(p->ctx, S->V, (float *)S->N, S->color, (unsigned int *)S->T, DefaultColorMC);
+	if (rc != MC33CU_OK) goto fail;
+	/* the MC33 mirrors the surface head, as in the reference (c:1873) */
+	memcpy(M, S, offsetof(MC33, memoryfault));
+	return S;
+fail:
+	if (getenv("MC33_B200_VERBOSE")) fprintf(stderr, "calculate_isosurface: %s\n", mc33cu_last_error());
+	M->memoryfault = 1;
+	free_surface_memory(S);
+	return 0;
+}

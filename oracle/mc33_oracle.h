@@ -14,10 +14,10 @@
  * BASELINE.md (K1..K7) committed under tests/golden/.
  *
  * Canonical order produced here (and by the CUDA path):
- *   vertices : first all SHARED vertices, by owning grid point in (z,y,x)
- *              order; a point owns, in this slot order,
- *                 POINT  (sample exactly on the isovalue)           or
- *                 X edge (p -> p+ex), Y edge (p -> p+ey), Z edge (p -> p+ez);
+ *   vertices : first all SHARED vertices, by point row in (z,y) order; within
+ *              a row first the X plane by x (X edge p -> p+ex, or the POINT
+ *              vertex of a sample exactly on the isovalue), then the Y plane
+ *              (edges p -> p+ey), then the Z plane (p -> p+ez);
  *              then all CENTRE vertices by owning cell in (z,y,x) order.
  *   triangles: by cell in (z,y,x) order -- the reference's sweep order
  *              (marching_cubes_33.c:1832-1865) -- then in table order, with the

@@ -372,29 +372,34 @@ static int FN(extract)(const SAMPLE *data, uint32_t nx, uint32_t ny, uint32_t nz
 	if (!pat_out) {
 		vid = (uint32_t *)malloc(NP * 3 * sizeof(uint32_t));
 		if (!vid) goto done;
-		/* shared vertices: SURVEY.md A.6 */
+		/* shared vertices: SURVEY.md A.6.  Canonical numbering: per point row all
+		 * X-plane vertices (X edges and POINT vertices) by x, then Y, then Z. */
+		for (uint64_t k = 0; k < NP * 3; k++) vid[k] = 0xFFFFFFFFu;
 		for (uint32_t z = 0; z <= nz; z++)
 			for (uint32_t y = 0; y <= ny; y++)
-				for (uint32_t x = 0; x <= nx; x++) {
-					uint64_t p = (uint64_t)z * NXY + (uint64_t)y * NX + x;
-					unsigned s = S[p];
-					uint32_t *id = vid + 3 * p;
-					id[0] = id[1] = id[2] = 0xFFFFFFFFu;
-					if (s & 2) {
-						unsigned any = 0;
-						if (x > 0) any |= S[p - 1];
-						if (x < nx) any |= S[p + 1];
-						if (y > 0) any |= S[p - NX];
-						if (y < ny) any |= S[p + NX];
-						if (z > 0) any |= S[p - NXY];
-						if (z < nz) any |= S[p + NXY];
-						if (any & 1) { id[0] = (uint32_t)nShared++; nPoint++; }
-					} else {
-						if (x < nx && !(S[p + 1] & 2) && ((S[p + 1] ^ s) & 1)) id[0] = (uint32_t)nShared++;
-						if (y < ny && !(S[p + NX] & 2) && ((S[p + NX] ^ s) & 1)) id[1] = (uint32_t)nShared++;
-						if (z < nz && !(S[p + NXY] & 2) && ((S[p + NXY] ^ s) & 1)) id[2] = (uint32_t)nShared++;
+				for (int pl = 0; pl < 3; pl++)
+					for (uint32_t x = 0; x <= nx; x++) {
+						uint64_t p = (uint64_t)z * NXY + (uint64_t)y * NX + x;
+						unsigned s = S[p];
+						uint32_t *id = vid + 3 * p;
+						if (s & 2) {
+							unsigned any = 0;
+							if (pl != 0) continue;
+							if (x > 0) any |= S[p - 1];
+							if (x < nx) any |= S[p + 1];
+							if (y > 0) any |= S[p - NX];
+							if (y < ny) any |= S[p + NX];
+							if (z > 0) any |= S[p - NXY];
+							if (z < nz) any |= S[p + NXY];
+							if (any & 1) { id[0] = (uint32_t)nShared++; nPoint++; }
+						} else if (pl == 0) {
+							if (x < nx && !(S[p + 1] & 2) && ((S[p + 1] ^ s) & 1)) id[0] = (uint32_t)nShared++;
+						} else if (pl == 1) {
+							if (y < ny && !(S[p + NX] & 2) && ((S[p + NX] ^ s) & 1)) id[1] = (uint32_t)nShared++;
+						} else {
+							if (z < nz && !(S[p + NXY] & 2) && ((S[p + NXY] ^ s) & 1)) id[2] = (uint32_t)nShared++;
+						}
 					}
-				}
 	}
 	/* cells, in the reference's sweep order */
 	for (uint32_t z = 0; z < nz; z++)

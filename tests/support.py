@@ -432,3 +432,96 @@ def compare_exact(a, b, nrm_atol=2e-6):
         assert np.array_equal(fa, fb)
         d = np.abs(np.where(fa, a.N, 0).astype(np.float64) - np.where(fb, b.N, 0).astype(np.float64))
         assert d.max() <= nrm_atol, d.max()
+
+
+# --------------------------------------------------------------------------
+# C-ABI descriptions + the test-only host emulation of the device code
+# --------------------------------------------------------------------------
+HOSTEMU_SO = ROOT / "tests" / "hostemu" / "_build" / "libmc33_hostemu.so"
+DEFAULT_COLOR = -10724260  # 0xff5c5c5c as int
+
+
+def make_desc(shape, variant="f32", geom=None, slab=None):
+    from mc33_c_library_b200 import _cabi as cabi
+    code, _, real = DTYPES[variant]
+    NZ, NY, NX = shape
+    geom = geom or Geometry()
+    store, O, D, ca, cb, A, Ai = geom.derived(real)
+    kw = {}
+    if slab is not None:
+        kw = dict(z_lo=slab.z_lo, z_hi=slab.z_hi, cell_z0=slab.cell_z0, cell_z1=slab.cell_z1, is_last=slab.is_last)
+    return cabi.make_desc(code, NX - 1, NY - 1, NZ - 1, store, O, D, ca, cb, A.flat, Ai.flat, geom.tsa,
+                          geom.normal_neg, **kw)
+
+
+_emu = None
+
+
+def hostemu_lib():
+    global _emu
+    if _emu is None:
+        from mc33_c_library_b200 import _cabi as cabi
+        if not HOSTEMU_SO.exists():
+            from mc33_c_library_b200 import build
+            build.build_oracle()
+        _emu = C.CDLL(str(HOSTEMU_SO))
+        _emu.mc33emu_run.argtypes = [C.POINTER(cabi.Desc), C.c_void_p, C.c_double, C.POINTER(cabi.Out),
+                                     C.POINTER(cabi.Counts)]
+    return _emu
+
+
+def emu_count(data_slab, iso, desc):
+    from mc33_c_library_b200 import _cabi as cabi
+    k = cabi.Counts()
+    rc = hostemu_lib().mc33emu_run(C.byref(desc), data_slab.ctypes.data, float(iso), None, C.byref(k))
+    assert rc == 0
+    return k
+
+
+def emu_emit(data_slab, iso, desc, k, real, vbase=0, vbase_next=0):
+    from mc33_c_library_b200 import _cabi as cabi
+    nV, nT = int(k.nV), int(k.nT)
+    V = np.zeros((nV, 3), real); N = np.zeros((nV, 3), np.float32); col = np.zeros(nV, np.int32)
+    T = np.zeros((nT, 3), np.uint32); vkey = np.zeros(nV, np.uint64); tcell = np.zeros(nT, np.uint64)
+    o = cabi.Out()
+    o.V, o.N, o.color, o.T = V.ctypes.data, N.ctypes.data, col.ctypes.data, T.ctypes.data
+    o.vkey, o.tcell = vkey.ctypes.data, tcell.ctypes.data
+    o.capV, o.capT, o.color_value = nV, nT, DEFAULT_COLOR
+    o.vbase, o.vbase_next = vbase, vbase_next
+    k2 = cabi.Counts()
+    rc = hostemu_lib().mc33emu_run(C.byref(desc), data_slab.ctypes.data, float(iso), C.byref(o), C.byref(k2))
+    assert rc == 0, rc
+    return Mesh(V, N, T, color=col, vkey=vkey, tcell=tcell, nShared=int(k.nShared), nCentre=int(k.nCentre))
+
+
+def emu_extract(data, iso, variant="f32", geom=None):
+    code, sdt, real = DTYPES[variant]
+    data = np.ascontiguousarray(data, dtype=sdt)
+    d = make_desc(data.shape, variant, geom)
+    k = emu_count(data, iso, d)
+    return emu_emit(data, iso, d, k, real)
+
+
+def merge_slab_meshes(meshes):
+    """Concatenate per-slab meshes (already carrying global vertex ids) in rank
+    order and bring them to the single-GPU canonical order: shared vertices of
+    all slabs first, then all centre vertices."""
+    nS = [m.counts["nShared"] for m in meshes]
+    nC = [m.counts["nCentre"] for m in meshes]
+    totS = sum(nS)
+    remap_parts, off_s, off_c, vb = [], 0, totS, 0
+    for m, s, c in zip(meshes, nS, nC):
+        r = np.empty(s + c, np.int64)
+        r[:s] = off_s + np.arange(s)
+        r[s:] = off_c + np.arange(c)
+        remap_parts.append(r)
+        off_s += s
+        off_c += c
+    remap = np.concatenate(remap_parts) if remap_parts else np.zeros(0, np.int64)
+    order = np.argsort(remap, kind="stable")
+    V = np.concatenate([m.V for m in meshes])[order]
+    N = np.concatenate([m.N for m in meshes])[order]
+    vkey = np.concatenate([m.vkey for m in meshes])[order]
+    T = remap[np.concatenate([m.T for m in meshes]).astype(np.int64)].astype(np.uint32)
+    tcell = np.concatenate([m.tcell for m in meshes])
+    return Mesh(V, N, T, vkey=vkey, tcell=tcell, nShared=totS, nCentre=sum(nC))

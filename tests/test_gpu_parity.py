@@ -1,0 +1,210 @@
+"""GPU parity: the sm_100a kernels, called through the C-ABI (include/mc33cu.h) and
+through the marching_cubes_33.h drop-in, against the oracle (oracle/) and the
+compiled reference (oracle/_ref, when it travelled with the snapshot).
+
+Bar: triangles bit exact (same triangles, same order, same winding, vertex ids
+identical in canonical order), positions bit exact, normals within 1e-6."""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from support import (DTYPES, Geometry, Mesh, MC33Lib, cfg1_grid, compare_exact, compare_to_reference, ct_grid,
+                     gyroid_grid, have_ref, inclined_geom, make_desc, noise_grid, oracle_extract, ref_lib)
+
+pytestmark = pytest.mark.gpu
+KATS = json.loads((Path(__file__).parent / "golden" / "kats.json").read_text())
+LIBDIR = Path(__file__).resolve().parent.parent / "mc33_c_library_b200" / "lib"
+
+
+def gpu_extract(data, iso, variant="f32", geom=None, keys=True):
+    import torch
+    from mc33_c_library_b200.device import Extractor
+    code, sdt, real = DTYPES[variant]
+    data = np.ascontiguousarray(data, dtype=sdt)
+    ex = Extractor(make_desc(data.shape, variant, geom))
+    ex.upload(data)
+    r = ex.extract(iso, keys=keys)
+    ex.close()
+    m = Mesh(r["V"], r["N"], r["T"], color=r["color"], vkey=r.get("vkey"), tcell=r.get("tcell"))
+    m.counts = dict(nShared=int(r["counts"].nShared), nCentre=int(r["counts"].nCentre))
+    return m
+
+
+def _same(o, g):
+    compare_exact(o, g, nrm_atol=1e-6)
+    assert np.array_equal(o.vkey.astype(np.int64), g.vkey) and np.array_equal(o.tcell.astype(np.int64), g.tcell)
+    assert (g.color == -10724260).all()
+
+
+def test_extension_is_loaded():
+    from mc33_c_library_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.mc33cu_device_count() >= 1
+    assert any("libmc33cu.so" in l for l in open("/proc/self/maps").read().splitlines())
+
+
+@pytest.mark.parametrize("variant,iso,scale", [("f32", 0.0, 0), ("f32", 0.05, 0), ("f64", 0.0, 0), ("u8", 3.0, 6),
+                                               ("u8", 2.5, 6), ("u16", 500.0, 1000), ("u16", 500.5, 1000),
+                                               ("u16", 1.0, 3)])
+def test_noise_vs_oracle(variant, iso, scale):
+    a = noise_grid(64, variant, scale=scale)
+    _same(oracle_extract(a, iso, variant), gpu_extract(a, iso, variant))
+
+
+def test_u32_vs_oracle():
+    a = noise_grid(0, "u16", scale=7, shape=(20, 30, 50)).astype(np.uint32)
+    _same(oracle_extract(a, 3.0, "u32"), gpu_extract(a, 3.0, "u32"))
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 2, 33), (2, 5, 34), (9, 4, 65), (5, 5, 32), (4, 3, 97), (30, 42, 38),
+                                   (3, 3, 300), (40, 3, 3), (3, 300, 3)])
+def test_ragged_shapes(shape):
+    a = noise_grid(0, "u8", scale=4, shape=shape)
+    for iso in (1.0, 2.0, 1.5):
+        _same(oracle_extract(a, iso, "u8"), gpu_extract(a, iso, "u8"))
+    f = noise_grid(0, "f32", shape=shape)
+    _same(oracle_extract(f, 0.0, "f32"), gpu_extract(f, 0.0, "f32"))
+
+
+@pytest.mark.parametrize("geom", [Geometry(r0=(1, 2, 3), d=(.5, .5, .5)), Geometry(r0=(1, 2, 3), d=(.5, .25, 2)),
+                                  inclined_geom(), inclined_geom(tsa=1, d=(.5, .25, 2), r0=(1, 2, 3)),
+                                  Geometry(normal_neg=1)])
+def test_store_variants(geom):
+    for variant, iso in (("f32", 0.0), ("u8", 3.0), ("f64", 0.0)):
+        a = noise_grid(0, variant, scale=6, shape=(24, 33, 47))
+        _same(oracle_extract(a, iso, variant, geom), gpu_extract(a, iso, variant, geom))
+
+
+def test_smooth_and_ct():
+    g = gyroid_grid(96, periods=3)
+    for iso in (-1.2, -0.3, 0.0, 0.9):
+        _same(oracle_extract(g, iso), gpu_extract(g, iso))
+    c = ct_grid(64)
+    for iso in (1500.0, 1500.5):
+        _same(oracle_extract(c, iso, "u16"), gpu_extract(c, iso, "u16"))
+
+
+def test_plateaus_and_empty():
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 3, size=(20, 22, 67)).astype(np.uint8)
+    for iso in (0.0, 1.0, 2.0):
+        _same(oracle_extract(a, iso, "u8"), gpu_extract(a, iso, "u8"))
+    z = np.zeros((5, 6, 7), np.float32)
+    for iso in (1.0, -1.0, 0.0):
+        g = gpu_extract(z, iso)
+        assert g.nV == 0 and g.nT == 0
+
+
+def test_kats_counts():
+    """BASELINE.md K1..K6 known answers of the reference, counts through the GPU count pass"""
+    from mc33_c_library_b200.device import Extractor
+
+    def count(data, iso, variant, geom=None):
+        ex = Extractor(make_desc(data.shape, variant, geom))
+        ex.upload(np.ascontiguousarray(data))
+        k = ex.count(iso)
+        ex.close()
+        return int(k.nV), int(k.nT), int(k.nCentre)
+    F, geom = cfg1_grid()
+    assert count(F, 0.0, "f32", geom)[:2] == (KATS["K1"]["nV"], KATS["K1"]["nT"])
+    assert count(F, 0.5, "f32", geom)[:2] == (KATS["K2"]["nV"], KATS["K2"]["nT"])
+    assert count(noise_grid(128, "f32"), 0.0, "f32")[:2] == (KATS["K3"]["nV"], KATS["K3"]["nT"])
+    assert count(noise_grid(256, "f32"), 0.0, "f32")[:2] == (KATS["K4"]["nV"], KATS["K4"]["nT"])
+    u = noise_grid(128, "u16", scale=1000)
+    assert count(u, 500.0, "u16")[:2] == (KATS["K5a"]["nV"], KATS["K5a"]["nT"])
+    assert count(u, 500.5, "u16")[:2] == (KATS["K5b"]["nV"], KATS["K5b"]["nT"])
+    nV, nT, nC = count(noise_grid(128, "u8", scale=6), 3.0, "u8")
+    assert (nV, nT, nC) == (KATS["K6"]["nV"], KATS["K6"]["nT"], KATS["K6"]["nCentre"])
+
+
+def test_cfg1_full_mesh_vs_oracle():
+    F, geom = cfg1_grid()
+    _same(oracle_extract(F, 0.0, "f32", geom), gpu_extract(F, 0.0, "f32", geom))
+
+
+def test_large_noise_vs_oracle():
+    a = noise_grid(160, "f32")
+    _same(oracle_extract(a, 0.0), gpu_extract(a, 0.0))
+
+
+def test_full_size_properties():
+    """512^3 gyroid (BASELINE config 2): size independent invariants + the
+    reference's counts from BASELINE.md section 2"""
+    import torch
+    from mc33_c_library_b200.device import Extractor
+    g = gyroid_grid(512, periods=4)
+    ex = Extractor(make_desc(g.shape, "f32"))
+    ex.upload(g)
+    for iso, key in ((-1.2, "G512_-1.2"), (0.0, "G512_0.0")):
+        r = ex.extract(iso, keys=True)
+        k = r["counts"]
+        nV, nT = int(k.nV), int(k.nT)
+        assert (nV, nT) == (KATS[key]["nV"], KATS[key]["nT"])
+        T = r["T"].astype(np.int64)
+        assert T.max() == nV - 1 and T.min() == 0
+        assert (T[:, 0] != T[:, 1]).all() and (T[:, 1] != T[:, 2]).all() and (T[:, 0] != T[:, 2]).all()
+        assert np.bincount(T.reshape(-1), minlength=nV).min() >= 1          # every vertex used
+        assert (np.diff(r["tcell"]) >= 0).all()                              # cell-major order
+        assert (np.diff(r["vkey"][: int(k.nShared)] // 4 // g.shape[2]) >= 0).all()   # row-major order
+        n = r["N"].astype(np.float64)
+        assert np.abs(np.sqrt((n * n).sum(1)) - 1).max() < 1e-6
+        # closed manifold away from the boundary: every edge is shared by two triangles
+        e = np.sort(np.concatenate([T[:, [0, 1]], T[:, [1, 2]], T[:, [2, 0]]]), axis=1)
+        _, cnt = np.unique(e[:, 0] * nV + e[:, 1], return_counts=True)
+        assert cnt.max() == 2
+    ex.close()
+
+
+# ---- the drop-in C API (include/marching_cubes_33.h) --------------------------
+def dropin(variant):
+    return MC33Lib(LIBDIR / f"libMC33_b200_{variant}.so", variant)
+
+
+@pytest.mark.parametrize("variant,iso,scale", [("f32", 0.0, 0), ("f64", 0.0, 0), ("u8", 3.0, 6), ("u16", 500.0, 1000)])
+def test_dropin_api_vs_oracle_and_reference(variant, iso, scale):
+    a = noise_grid(48, variant, scale=scale)
+    lib = dropin(variant)
+    for geom in (None, Geometry(r0=(1, 2, 3), d=(.5, .25, 2)), inclined_geom()):
+        mine = lib.extract(a, iso, geom)
+        orc = oracle_extract(a, iso, variant, geom)
+        compare_exact(orc, mine, nrm_atol=1e-6)
+        assert (mine.color == -10724260).all() and mine.iso == pytest.approx(iso)
+        if have_ref(variant):
+            ref = ref_lib(variant).extract(a, iso, geom)
+            compare_to_reference(ref, mine, exact_pos=geom is None or not geom.nonortho, pos_rtol=2e-6)
+    sz, nV, nT = lib.size(a, iso)
+    assert (nV, nT) == (orc.nV, orc.nT)
+    assert sz == nV * (6 * (8 if variant == "f64" else 4) + 4) + nT * 12 + 64
+
+
+def test_dropin_generate_grid_from_fn_cfg1():
+    """BASELINE config 1 end to end through the C API: generate_grid_from_fn with a
+    C callback (libm cos), create_MC33, calculate_isosurface -> K1"""
+    lib = dropin("f32")
+    libm = C.CDLL("libm.so.6")
+    libm.cos.restype = C.c_double
+    libm.cos.argtypes = [C.c_double]
+    FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_double)
+    fn = FN(lambda x, y, z: libm.cos(x) + libm.cos(y) + libm.cos(z))
+    L = lib.lib
+    L.generate_grid_from_fn.argtypes = [C.c_double] * 9 + [FN]
+    G = L.generate_grid_from_fn(-4, -4, -4, 4, 4, 4, .04, .04, .04, fn)
+    assert G and tuple(G.contents.N) == (200, 200, 200) and G.contents.internal_data == 1
+    M = L.create_MC33(G)
+    S = L.calculate_isosurface(M, C.c_float(0.0))
+    assert (S.contents.nV, S.contents.nT) == (KATS["K1"]["nV"], KATS["K1"]["nT"])
+    L.free_surface_memory(S); L.free_MC33(M); L.free_memory_grd(G)
+
+
+def test_dropin_empty_surface_and_null_safety():
+    lib = dropin("f32")
+    a = np.zeros((4, 5, 6), np.float32)
+    m = lib.extract(a, 1.0)
+    assert m.nV == 0 and m.nT == 0 and m.iso == 0.0   # zeroed struct (reference c:1880-1883)
+    L = lib.lib
+    L.free_surface_memory(None); L.free_MC33(None); L.free_memory_grd(None)
+    assert not L.create_MC33(None)
+    assert not L.grid_from_data_pointer(0, 4, 4, a.ctypes.data)

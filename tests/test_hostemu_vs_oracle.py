@@ -1,0 +1,81 @@
+"""CPU check of the per-word device logic (mc33_core.cuh stepped on the host by
+tests/hostemu, test infrastructure) against the oracle, including the z-slab
+decomposition used for multi-GPU runs.  No GPU needed; the kernels proper are
+covered by the -m gpu tests."""
+import numpy as np
+import pytest
+
+from mc33_c_library_b200 import slabs
+from support import (DTYPES, Geometry, compare_exact, emu_count, emu_emit, emu_extract, gyroid_grid,
+                     inclined_geom, make_desc, merge_slab_meshes, noise_grid, oracle_extract)
+
+
+def _same(o, e):
+    compare_exact(o, e, nrm_atol=0)
+    assert np.array_equal(o.vkey, e.vkey) and np.array_equal(o.tcell, e.tcell)
+
+
+@pytest.mark.parametrize("variant,iso,scale", [("f32", 0.0, 0), ("f64", 0.0, 0), ("u8", 3.0, 6), ("u8", 2.5, 6),
+                                               ("u16", 500.0, 1000), ("u16", 1.0, 3), ("u32", 2.0, 5)])
+def test_noise(variant, iso, scale):
+    if variant == "u32":
+        a = noise_grid(0, "u16", scale=scale, shape=(14, 19, 70)).astype(np.uint32)
+    else:
+        a = noise_grid(0, variant, scale=scale, shape=(14, 19, 70))
+    _same(oracle_extract(a, iso, variant), emu_extract(a, iso, variant))
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 2, 33), (2, 5, 34), (9, 4, 65), (5, 5, 32), (4, 3, 97)])
+def test_word_boundaries(shape):
+    a = noise_grid(0, "u8", scale=4, shape=shape)
+    for iso in (1.0, 2.0, 1.5):
+        _same(oracle_extract(a, iso, "u8"), emu_extract(a, iso, "u8"))
+    f = noise_grid(0, "f32", shape=shape)
+    _same(oracle_extract(f, 0.0, "f32"), emu_extract(f, 0.0, "f32"))
+
+
+@pytest.mark.parametrize("geom", [Geometry(r0=(1, 2, 3), d=(.5, .5, .5)), Geometry(r0=(1, 2, 3), d=(.5, .25, 2)),
+                                  inclined_geom(), inclined_geom(tsa=1, d=(.5, .25, 2), r0=(1, 2, 3)),
+                                  Geometry(normal_neg=1)])
+def test_geometry(geom):
+    for variant, iso in (("f32", 0.0), ("u8", 3.0), ("f64", 0.0)):
+        a = noise_grid(0, variant, scale=6, shape=(12, 17, 35))
+        _same(oracle_extract(a, iso, variant, geom), emu_extract(a, iso, variant, geom))
+
+
+def test_smooth():
+    g = gyroid_grid(48, periods=2)
+    for iso in (-0.9, 0.0, 0.3):
+        _same(oracle_extract(g, iso), emu_extract(g, iso))
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+@pytest.mark.parametrize("variant,iso,scale", [("f32", 0.0, 0), ("u8", 2.0, 4)])
+def test_slab_decomposition(world, variant, iso, scale):
+    """every slab seam: per-slab extraction with halos + index bases == one slab"""
+    _, sdt, real = DTYPES[variant]
+    a = noise_grid(0, variant, scale=scale, shape=(23, 9, 40))
+    whole = oracle_extract(a, iso, variant)
+    parts = [s for s in slabs.partition(a.shape[0] - 1, world) if s is not None]
+    descs, datas, counts = [], [], []
+    for s in parts:
+        sub = np.ascontiguousarray(a[s.z_lo:s.z_hi])
+        d = make_desc(a.shape, variant, None, s)
+        descs.append(d); datas.append(sub)
+        counts.append(emu_count(sub, iso, d))
+    b = slabs.bases([(int(k.nV), int(k.nT)) for k in counts])
+    # the shared-vertex count a slab computes for its upper halo slice must be the
+    # first-slice count of the next slab
+    meshes = []
+    for s, d, sub, k, (vb, vbn) in zip(parts, descs, datas, counts, b):
+        meshes.append(emu_emit(sub, iso, d, k, real, vbase=vb, vbase_next=vbn))
+    m = merge_slab_meshes(meshes)
+    assert m.nV == whole.nV and m.nT == whole.nT
+    assert np.array_equal(m.tcell, whole.tcell)
+    # vertex order differs only by slab-major vs global order of centres; keys identify them
+    order_m, order_w = np.argsort(m.vkey, kind="stable"), np.argsort(whole.vkey, kind="stable")
+    assert np.array_equal(m.vkey[order_m], whole.vkey[order_w])
+    inv = np.empty(m.nV, np.int64); inv[order_m] = order_w
+    assert np.array_equal(inv[m.T.astype(np.int64)], whole.T.astype(np.int64))
+    assert np.array_equal(m.V[order_m], whole.V[order_w])
+    assert np.array_equal(m.N[order_m], whole.N[order_w], equal_nan=True)
