@@ -119,7 +119,9 @@ struct Totals {                   // written by the scan kernel
 	uint32_t nT;
 	uint32_t nSharedHalo;         // shared vertices of the halo slice (next slab's first)
 	uint32_t overflow;            // set by emit kernels if a capacity was exceeded
-	uint32_t pad_[3];
+	uint32_t nSharedAll;          // shared vertices counted (own + halo slice)
+	uint32_t range;               // 1: more than 2^32-1 vertices or triangles
+	uint32_t anyZ;                // classify: some sample is exactly on the isovalue
 };
 
 struct Tables {
@@ -135,16 +137,18 @@ struct Params {
 	uint32_t pz0, pz1;            // point slices whose shared vertices this slab owns
 	uint32_t cz0, cz1;            // cell layers this slab owns
 	uint32_t hz;                  // halo point slice numbered in the next slab (== pz1) or 0xFFFFFFFF
-	uint32_t W, WC, WP;           // words per point row, per cell row, row stride (>= W+1)
+	uint32_t W, WC, WP, W1;       // words per point row, per cell row, bitmap row stride (>= W+1), W+1
 	uint32_t Lrows;               // (zhi-zlo)*NY
+	uint32_t R, CW;               // a batch = R whole rows (CW == W), or CW words of one row (R == 1)
+	uint32_t mCW, mNY;            // floor(2^32/CW), floor(2^32/NY) for fastdiv
 	uint32_t *S, *Z;              // bitmaps [Lrows][WP]
 	uint8_t *rowZ;                // [Lrows] any Z bit in the row
-	uint64_t *wpreV;              // [Lrows][W]  row-local exclusive prefix: X | Y<<21 | Z<<42
-	uint64_t *wpreC;              // [Lrows][W]  row-local exclusive prefix: T | C<<32
-	uint32_t *rowNX, *rowNY, *rowNZ, *rowNC, *rowNT;   // [Lrows] counts
-	uint32_t *rowBX, *rowBY, *rowBZ, *rowBC, *rowBT;   // [Lrows] exclusive bases (scan)
+	uint64_t *wpreV;              // [Lrows][W1] row-local exclusive prefix X | Y<<21 | Z<<42; entry W = row totals
+	uint64_t *wpreT;              // [Lrows][W1] row-local exclusive prefix T | C<<32; entry W = row totals
+	uint32_t *rowBV, *rowBT, *rowBC;   // [Lrows+1] slab-local exclusive bases: vertices, triangles, centres
 	Totals *totals;
 	double iso;
+	uint32_t ithr, ieq_lo, ieq_hi, inone;   // integer grids: sample >= ithr <=> above iso; [ieq_lo,ieq_hi] on iso
 	Geom geom;
 	// outputs (device)
 	void *V; float *N; int32_t *color; uint32_t *T;
@@ -343,11 +347,8 @@ MC_HDN unsigned select_pattern(const Tables &tb, unsigned i, const Real *v, unsi
 // ---------------------------------------------------------------------------
 // bitmap helpers.  Rows are addressed by LOCAL row index lr = (z - zlo)*NY + y.
 // Bits beyond x = nx are zero; word W (one past the last) exists and is zero.
+// Word indices fit 32 bits (checked at context creation).
 // ---------------------------------------------------------------------------
-MC_HD uint32_t ldw(const uint32_t *B, const Params &P, uint32_t lr, uint32_t w)
-{
-	return B[(uint64_t)lr * P.WP + w];
-}
 MC_HD uint32_t shr1(uint32_t lo, uint32_t hi) { return (lo >> 1) | (hi << 31); }
 
 // mask of the bits of word w that denote x <= lim
@@ -359,91 +360,96 @@ MC_HD uint32_t mask_le(uint32_t w, uint32_t lim)
 	return n >= 31 ? 0xFFFFFFFFu : ((2u << n) - 1u);
 }
 
-struct Planes { uint32_t X, Y, Z; };
-
-// which points of word w in point row (z,y) own an X/POINT, Y, Z vertex
-MC_HDN Planes planes(const Params &P, uint32_t z, uint32_t y, uint32_t w)
+// exact n / d for 32-bit n given m = floor(2^32 / d) -- one mulhi + fix-up
+MC_HD uint32_t fastdiv(uint32_t n, uint32_t d, uint32_t m)
 {
-	Planes r;
-	const uint32_t lr = (z - P.zlo) * P.NY + y;
-	const bool hasY = y < P.ny, hasZ = z < P.nz;
-	const uint32_t vp = mask_le(w, P.nx);
-	const uint32_t vx = P.nx ? mask_le(w, P.nx - 1) : 0u;
-	const uint32_t s0 = ldw(P.S, P, lr, w), s0n = ldw(P.S, P, lr, w + 1);
-	const uint32_t sx = shr1(s0, s0n);
-	const uint32_t sy = hasY ? ldw(P.S, P, lr + 1, w) : s0;
-	const uint32_t sz = hasZ ? ldw(P.S, P, lr + P.NY, w) : s0;
-	r.X = (s0 ^ sx) & vx;
-	r.Y = (s0 ^ sy) & vp;
-	r.Z = (s0 ^ sz) & vp;
-	unsigned zf = P.rowZ[lr];
-	if (hasY) zf |= P.rowZ[lr + 1];
-	if (hasZ) zf |= P.rowZ[lr + P.NY];
-	if (zf) {
-		const uint32_t z0 = ldw(P.Z, P, lr, w), z0n = ldw(P.Z, P, lr, w + 1);
-		const uint32_t zx = shr1(z0, z0n);
-		const uint32_t zy = hasY ? ldw(P.Z, P, lr + 1, w) : 0u;
-		const uint32_t zz = hasZ ? ldw(P.Z, P, lr + P.NY, w) : 0u;
-		r.X &= ~(z0 | zx);
-		r.Y &= ~(z0 | zy);
-		r.Z &= ~(z0 | zz);
-		if (z0) {
-			// POINT vertex: on-iso sample with at least one of its <=6 axis
-			// neighbours above the isovalue
-			uint32_t nb = sx | (s0 << 1) | (w ? ldw(P.S, P, lr, w - 1) >> 31 : 0u);
-			if (hasY) nb |= sy;
-			if (y > 0) nb |= ldw(P.S, P, lr - 1, w);
-			if (hasZ) nb |= sz;
-			if (z > 0) nb |= ldw(P.S, P, lr - P.NY, w);
-			r.X |= z0 & nb;
-		}
-	}
-	return r;
+	if (d == 1) return n;
+#if defined(__CUDA_ARCH__)
+	uint32_t q = __umulhi(n, m);
+#else
+	uint32_t q = (uint32_t)(((uint64_t)n * m) >> 32);
+#endif
+	uint32_t r = n - q * d;
+	if (r >= d) { q++; r -= d; }
+	if (r >= d) { q++; }
+	return q;
 }
+
+// What the count kernel leaves per (point row, word): which of the 32 points own
+// an X/POINT, Y, Z vertex, and which of the 32 cells (same x range, cell row of
+// the same (z,y)) are active.
+struct WordRec { uint32_t X, Y, Z, act; };
 
 // corner sign words of the 32 cells of word w in cell row (z,y): c[k] bit b =
 // index bit of corner k of cell x = 32w+b; zc[k] likewise for "on-iso".
-struct CellWords { uint32_t c[8]; uint32_t zc[8]; uint32_t active; uint32_t zany; };
+struct CellWords { uint32_t c[8]; uint32_t zc[8]; uint32_t zany; };
 
-MC_HDN void cell_words(const Params &P, uint32_t z, uint32_t y, uint32_t w, CellWords &cw)
+// One pass over the bitmaps for word w of row (z,y).  gz: the grid has at least
+// one on-iso sample (uniform flag from the classify kernel); when it is false
+// the Z bitmap is not touched at all.
+MC_HDN void word_masks(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, WordRec &rec, CellWords &cw)
 {
 	const uint32_t lr = (z - P.zlo) * P.NY + y;
-	const uint32_t r00 = lr, r10 = lr + 1, r01 = lr + P.NY, r11 = lr + P.NY + 1;
-	uint32_t a, b;
-	a = ldw(P.S, P, r00, w); b = ldw(P.S, P, r00, w + 1); cw.c[0] = a; cw.c[4] = shr1(a, b);
-	a = ldw(P.S, P, r10, w); b = ldw(P.S, P, r10, w + 1); cw.c[1] = a; cw.c[5] = shr1(a, b);
-	a = ldw(P.S, P, r11, w); b = ldw(P.S, P, r11, w + 1); cw.c[2] = a; cw.c[6] = shr1(a, b);
-	a = ldw(P.S, P, r01, w); b = ldw(P.S, P, r01, w + 1); cw.c[3] = a; cw.c[7] = shr1(a, b);
-	uint32_t any = 0, all = 0xFFFFFFFFu;
-#pragma unroll
-	for (int k = 0; k < 8; k++) { any |= cw.c[k]; all &= cw.c[k]; }
-	cw.active = any & ~all & (P.nx ? mask_le(w, P.nx - 1) : 0u);
+	const bool hasY = y < P.ny, hasZ = z < P.nz;
+	const uint32_t dY = hasY ? P.WP : 0u, dZ = hasZ ? P.NY * P.WP : 0u;
+	const uint32_t i00 = lr * P.WP + w, i10 = i00 + dY, i01 = i00 + dZ, i11 = i01 + dY;
+	const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
+	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
+	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
+	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
+	rec.X = (s00 ^ x00) & vx;
+	rec.Y = (s00 ^ s10) & vp;       // zero when !hasY (s10 is s00 then)
+	rec.Z = (s00 ^ s01) & vp;
+	cw.c[0] = s00; cw.c[4] = x00; cw.c[1] = s10; cw.c[5] = x10;
+	cw.c[2] = s11; cw.c[6] = x11; cw.c[3] = s01; cw.c[7] = x01;
+	const uint32_t any = s00 | s10 | s01 | s11 | x00 | x10 | x01 | x11;
+	const uint32_t all = s00 & s10 & s01 & s11 & x00 & x10 & x01 & x11;
+	rec.act = (hasY && hasZ) ? (any & ~all & vx) : 0u;
 	cw.zany = 0;
-	if (P.rowZ[r00] | P.rowZ[r10] | P.rowZ[r01] | P.rowZ[r11]) {
-		a = ldw(P.Z, P, r00, w); b = ldw(P.Z, P, r00, w + 1); cw.zc[0] = a; cw.zc[4] = shr1(a, b);
-		a = ldw(P.Z, P, r10, w); b = ldw(P.Z, P, r10, w + 1); cw.zc[1] = a; cw.zc[5] = shr1(a, b);
-		a = ldw(P.Z, P, r11, w); b = ldw(P.Z, P, r11, w + 1); cw.zc[2] = a; cw.zc[6] = shr1(a, b);
-		a = ldw(P.Z, P, r01, w); b = ldw(P.Z, P, r01, w + 1); cw.zc[3] = a; cw.zc[7] = shr1(a, b);
+#pragma unroll
+	for (int k = 0; k < 8; k++) cw.zc[k] = 0;
+	if (!gz) return;
+	const unsigned f00 = P.rowZ[lr], f10 = hasY ? P.rowZ[lr + 1] : 0u, f01 = hasZ ? P.rowZ[lr + P.NY] : 0u;
+	const unsigned f11 = (hasY && hasZ) ? P.rowZ[lr + P.NY + 1] : 0u;
+	if (!(f00 | f10 | f01 | f11)) return;
+	const uint32_t z00 = P.Z[i00], z10 = hasY ? P.Z[i10] : 0u, z01 = hasZ ? P.Z[i01] : 0u;
+	const uint32_t z11 = (hasY && hasZ) ? P.Z[i11] : 0u;
+	const uint32_t zx00 = shr1(z00, P.Z[i00 + 1]);
+	rec.X &= ~(z00 | zx00);
+	rec.Y &= ~(z00 | z10);
+	rec.Z &= ~(z00 | z01);
+	if (z00) {
+		// POINT vertex: on-iso sample with at least one of its <= 6 axis neighbours
+		// above the isovalue; it lives in the X plane
+		uint32_t nb = x00 | (s00 << 1) | (w ? P.S[i00 - 1] >> 31 : 0u);
+		if (hasY) nb |= s10;
+		if (y > 0) nb |= P.S[i00 - P.WP];
+		if (hasZ) nb |= s01;
+		if (z > 0) nb |= P.S[i00 - P.NY * P.WP];
+		rec.X |= z00 & nb;
+	}
+	if (rec.act) {
+		cw.zc[0] = z00; cw.zc[4] = zx00;
+		cw.zc[1] = z10; cw.zc[5] = shr1(z10, P.Z[i10 + 1]);
+		cw.zc[2] = z11; cw.zc[6] = shr1(z11, P.Z[i11 + 1]);
+		cw.zc[3] = z01; cw.zc[7] = shr1(z01, P.Z[i01 + 1]);
 #pragma unroll
 		for (int k = 0; k < 8; k++) cw.zany |= cw.zc[k];
-	} else {
-#pragma unroll
-		for (int k = 0; k < 8; k++) cw.zc[k] = 0;
 	}
 }
 
-MC_HD unsigned cell_index(const CellWords &cw, int b)
+MC_HD unsigned cell_index(const uint32_t *c, uint32_t stride, int b)
 {
 	unsigned i = 0;
 #pragma unroll
-	for (int k = 0; k < 8; k++) i |= ((cw.c[k] >> b) & 1u) << (7 - k);
+	for (int k = 0; k < 8; k++) i = (i << 1) | ((c[k * stride] >> b) & 1u);
 	return i;
 }
-MC_HD unsigned cell_zmask(const CellWords &cw, int b)
+MC_HD unsigned cell_zmask(const uint32_t *zc, uint32_t stride, int b)
 {
 	unsigned i = 0;
 #pragma unroll
-	for (int k = 0; k < 8; k++) i |= ((cw.zc[k] >> b) & 1u) << k;
+	for (int k = 0; k < 8; k++) i |= ((zc[k * stride] >> b) & 1u) << k;
 	return i;
 }
 
@@ -508,39 +514,36 @@ MC_HDN CellPattern cell_pattern(const Params &P, const Tables &tb, uint32_t x, u
 
 // ---------------------------------------------------------------------------
 // count step for one (row, word): vertices owned by the 32 points, triangles and
-// centre vertices of the 32 cells.  Returns packed counts:
+// centre vertices of the 32 cells.  Packed counts:
 //   cv = nX | nY<<21 | nZ<<42        cc = nT | nC<<32
+// rec is what the emit kernels read back.
 // ---------------------------------------------------------------------------
 template <typename Sample>
-MC_HDN void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w,
-                       bool own_points, bool own_cells, uint64_t &cv, uint64_t &cc)
+MC_HDN void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,
+                       bool own_points, bool own_cells, WordRec &rec, uint64_t &cv, uint64_t &cc)
 {
-	cv = 0; cc = 0;
-	if (own_points) {
-		Planes pl = planes(P, z, y, w);
-		cv = (uint64_t)popc32(pl.X) | ((uint64_t)popc32(pl.Y) << 21) | ((uint64_t)popc32(pl.Z) << 42);
-	}
-	if (own_cells && w < P.WC) {
-		CellWords cw;
-		cell_words(P, z, y, w, cw);
-		uint32_t act = cw.active;
-		uint32_t nt = 0, nc = 0;
-		while (act) {
-			int b = ffs32(act);
-			act &= act - 1;
-			unsigned idx = cell_index(cw, b);
-			unsigned zm = cw.zany ? cell_zmask(cw, b) : 0u;
-			unsigned e = tb.simple256[idx];
-			if (e != 0xFFFFu && !zm) {
-				nt += e >> 12;
-			} else {
-				CellPattern cp = cell_pattern<Sample>(P, tb, (w << 5) + b, y, z, idx, zm);
-				nt += cp.ntri;
-				nc += cp.centre;
-			}
+	CellWords cw;
+	word_masks(P, z, y, w, gz, rec, cw);
+	if (!own_points) { rec.X = rec.Y = rec.Z = 0; }
+	if (!own_cells) rec.act = 0;
+	cv = (uint64_t)popc32(rec.X) | ((uint64_t)popc32(rec.Y) << 21) | ((uint64_t)popc32(rec.Z) << 42);
+	uint32_t act = rec.act;
+	uint32_t nt = 0, nc = 0;
+	while (act) {
+		int b = ffs32(act);
+		act &= act - 1;
+		unsigned idx = cell_index(cw.c, 1, b);
+		unsigned zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
+		unsigned e = tb.simple256[idx];
+		if (e != 0xFFFFu && !zm) {
+			nt += e >> 12;
+		} else {
+			CellPattern cp = cell_pattern<Sample>(P, tb, (w << 5) + b, y, z, idx, zm);
+			nt += cp.ntri;
+			nc += cp.centre;
 		}
-		cc = (uint64_t)nt | ((uint64_t)nc << 32);
 	}
+	cc = (uint64_t)nt | ((uint64_t)nc << 32);
 }
 
 // ---------------------------------------------------------------------------
@@ -598,88 +601,77 @@ MC_HDN void store_vertex(const Params &P, Real *r, uint32_t id)
 	P.color[id] = P.color_value;
 }
 
-// transverse component of the edge normal (e.g. c:993-998)
-template <typename Sample>
-MC_HDN typename Traits<Sample>::Real transverse(const Params &P, typename Traits<Sample>::Real iso,
-                                               uint32_t x, uint32_t y, uint32_t z, int a, int c,
-                                               typename Traits<Sample>::Real t)
-{
-	typedef typename Traits<Sample>::Real Real;
-	const uint32_t n[3] = {P.nx, P.ny, P.nz};
-	uint32_t p0[3] = {x, y, z}, p1[3] = {x, y, z};
-	p1[a] += 1;
-	const Real one_t = rsub((Real)1, t);
-	const uint32_t q = p0[c];
-	if (q == 0 || q == n[c]) {
-		uint32_t q0[3] = {p0[0], p0[1], p0[2]}, q1[3] = {p1[0], p1[1], p1[2]};
-		Real d0, d1;
-		if (q == 0) {
-			q0[c] += 1; q1[c] += 1;
-			d0 = rsub(ld_val<Sample>(P, iso, q0[0], q0[1], q0[2]), ld_val<Sample>(P, iso, p0[0], p0[1], p0[2]));
-			d1 = rsub(ld_val<Sample>(P, iso, q1[0], q1[1], q1[2]), ld_val<Sample>(P, iso, p1[0], p1[1], p1[2]));
-		} else {
-			q0[c] -= 1; q1[c] -= 1;
-			d0 = rsub(ld_val<Sample>(P, iso, p0[0], p0[1], p0[2]), ld_val<Sample>(P, iso, q0[0], q0[1], q0[2]));
-			d1 = rsub(ld_val<Sample>(P, iso, p1[0], p1[1], p1[2]), ld_val<Sample>(P, iso, q1[0], q1[1], q1[2]));
-		}
-		return radd(rmul(d0, one_t), rmul(d1, t));
-	}
-	uint32_t l0[3] = {p0[0], p0[1], p0[2]}, h0[3] = {p0[0], p0[1], p0[2]};
-	uint32_t l1[3] = {p1[0], p1[1], p1[2]}, h1[3] = {p1[0], p1[1], p1[2]};
-	l0[c] -= 1; h0[c] += 1; l1[c] -= 1; h1[c] += 1;
-	Real e0 = rawdiff(ld_sample<Sample>(P, l0[0], l0[1], l0[2]), ld_sample<Sample>(P, h0[0], h0[1], h0[2]));
-	Real e1 = rawdiff(ld_sample<Sample>(P, l1[0], l1[1], l1[2]), ld_sample<Sample>(P, h1[0], h1[1], h1[2]));
-	return rmul((Real)0.5f, radd(rmul(e0, one_t), rmul(e1, t)));
-}
-
-// MC33_surfint gradient (marching_cubes_33.c:628-647)
-template <typename Sample>
-MC_HDN typename Traits<Sample>::Real point_grad(const Params &P, uint32_t x, uint32_t y, uint32_t z, int c)
-{
-	typedef typename Traits<Sample>::Real Real;
-	const uint32_t n[3] = {P.nx, P.ny, P.nz};
-	uint32_t p[3] = {x, y, z}, lo[3] = {x, y, z}, hi[3] = {x, y, z};
-	if (p[c] == 0) {
-		hi[c] += 1;
-		return rawdiff(ld_sample<Sample>(P, x, y, z), ld_sample<Sample>(P, hi[0], hi[1], hi[2]));
-	} else if (p[c] == n[c]) {
-		lo[c] -= 1;
-		return rawdiff(ld_sample<Sample>(P, lo[0], lo[1], lo[2]), ld_sample<Sample>(P, x, y, z));
-	}
-	lo[c] -= 1; hi[c] += 1;
-	// 0.5f*(F - F): float product for float and integer grids, double for double
-	return (Real)rmul((Real)0.5f, rawdiff(ld_sample<Sample>(P, lo[0], lo[1], lo[2]), ld_sample<Sample>(P, hi[0], hi[1], hi[2])));
-}
-
+// ---------------------------------------------------------------------------
+// EDGE vertex of plane a (0 X, 1 Y, 2 Z) at grid point (x,y,z): reference
+// marching_cubes_33.c:780-1224 (e.g. :990-1000), normal stencil SURVEY.md A.7.
+// Written without a per-plane code path (a is a run-time value selected by
+// predication) so that a warp whose lanes hold vertices of different planes
+// does not diverge; only grid-boundary points take a separate branch.
+// ---------------------------------------------------------------------------
 template <typename Sample>
 MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, int a, uint32_t id)
 {
 	typedef typename Traits<Sample>::Real Real;
 	const Real iso = (Real)P.iso;
-	uint32_t q[3] = {x, y, z};
-	const uint32_t p[3] = {x, y, z};
-	q[a] += 1;
-	const Real va = ld_val<Sample>(P, iso, x, y, z), vb = ld_val<Sample>(P, iso, q[0], q[1], q[2]);
+	const int64_t sy = (int64_t)P.NX, sz = (int64_t)P.NX * P.NY;
+	const Sample *p0 = (const Sample *)P.data + ((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x;
+	const Sample *p1 = p0 + (a == 0 ? (int64_t)1 : (a == 1 ? sy : sz));
+	const Real va = rsub(iso, (Real)p0[0]), vb = rsub(iso, (Real)p1[0]);
 	const Real t = rdiv(va, rsub(va, vb));
+	const Real one_t = rsub((Real)1, t);
 	Real r[6];
 #pragma unroll
 	for (int c = 0; c < 3; c++) {
-		if (c == a) { r[c] = radd((Real)p[c], t); r[3 + c] = rsub(vb, va); }
-		else { r[c] = (Real)p[c]; r[3 + c] = transverse<Sample>(P, iso, x, y, z, a, c, t); }
+		const int64_t sc = c == 0 ? (int64_t)1 : (c == 1 ? sy : sz);
+		const uint32_t q = c == 0 ? x : (c == 1 ? y : z);
+		const uint32_t nq = c == 0 ? P.nx : (c == 1 ? P.ny : P.nz);
+		if (c == a) {
+			r[c] = radd((Real)q, t);
+			r[3 + c] = rsub(vb, va);
+		} else {
+			r[c] = (Real)q;
+			if (q != 0 && q != nq) {
+				// central difference on raw samples (e.g. c:993-994)
+				const Real e0 = rawdiff(p0[-sc], p0[sc]), e1 = rawdiff(p1[-sc], p1[sc]);
+				r[3 + c] = rmul((Real)0.5f, radd(rmul(e0, one_t), rmul(e1, t)));
+			} else {
+				Real d0, d1;
+				if (q == 0) {   // forward difference of the iso-subtracted values (e.g. c:813)
+					d0 = rsub(rsub(iso, (Real)p0[sc]), va);
+					d1 = rsub(rsub(iso, (Real)p1[sc]), vb);
+				} else {        // backward (e.g. c:995 else-branch)
+					d0 = rsub(va, rsub(iso, (Real)p0[-sc]));
+					d1 = rsub(vb, rsub(iso, (Real)p1[-sc]));
+				}
+				r[3 + c] = radd(rmul(d0, one_t), rmul(d1, t));
+			}
+		}
 	}
 	store_vertex<Real>(P, r, id);
 }
 
+// POINT vertex: MC33_surfint (marching_cubes_33.c:628-649)
 template <typename Sample>
 MC_HDN void emit_point_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
 {
 	typedef typename Traits<Sample>::Real Real;
+	const int64_t sy = (int64_t)P.NX, sz = (int64_t)P.NX * P.NY;
+	const Sample *p = (const Sample *)P.data + ((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x;
 	Real r[6] = {(Real)x, (Real)y, (Real)z, 0, 0, 0};
 #pragma unroll
-	for (int c = 0; c < 3; c++) r[3 + c] = point_grad<Sample>(P, x, y, z, c);
+	for (int c = 0; c < 3; c++) {
+		const int64_t sc = c == 0 ? (int64_t)1 : (c == 1 ? sy : sz);
+		const uint32_t q = c == 0 ? x : (c == 1 ? y : z);
+		const uint32_t nq = c == 0 ? P.nx : (c == 1 ? P.ny : P.nz);
+		if (q == 0) r[3 + c] = rawdiff(p[0], p[sc]);
+		else if (q == nq) r[3 + c] = rawdiff(p[-sc], p[0]);
+		// 0.5f*(F - F): float product for float and integer grids, double for double
+		else r[3 + c] = (Real)rmul((Real)0.5f, rawdiff(p[-sc], p[sc]));
+	}
 	store_vertex<Real>(P, r, id);
 }
 
+// CENTRE vertex (edge code 12): marching_cubes_33.c:1225-1230
 template <typename Sample>
 MC_HDN void emit_centre_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
 {
@@ -699,142 +691,155 @@ MC_HD bool row_points_owned(const Params &P, uint32_t z) { return z >= P.pz0 && 
 MC_HD bool row_points_halo(const Params &P, uint32_t z) { return z == P.hz; }
 MC_HD bool row_cells_owned(const Params &P, uint32_t z, uint32_t y) { return z >= P.cz0 && z < P.cz1 && y < P.ny; }
 
-// slab-local index of the first vertex of plane `pl` (0 X,1 Y,2 Z) in word w of
-// point row (z,y).  Vertex ARRAYS are indexed locally; triangle CONTENTS are
+// ---------------------------------------------------------------------------
+// vertex numbering.  wpreV[lr][w] packs the number of X / Y / Z plane vertices
+// of row lr in words < w (21 bits each), entry W the row totals; rowBV[lr] is
+// the slab-local id of the row's first vertex.  Within a row: X plane by x,
+// then Y, then Z.  Vertex ARRAYS are indexed locally; triangle CONTENTS are
 // global ids (local + vbase).
-MC_HD uint32_t plane_base_local(const Params &P, uint32_t z, uint32_t y, uint32_t w, int pl)
+// ---------------------------------------------------------------------------
+MC_HD uint32_t fldV(uint64_t p, int pl) { return (uint32_t)(p >> (21 * pl)) & 0x1FFFFFu; }
+
+MC_HD uint32_t plane_base_local(const Params &P, uint32_t lr, uint32_t w, int pl)
 {
-	const uint32_t lr = (z - P.zlo) * P.NY + y;
-	const uint64_t pre = P.wpreV[(uint64_t)lr * P.W + w];
-	const uint32_t rb = pl == 0 ? P.rowBX[lr] : (pl == 1 ? P.rowBY[lr] : P.rowBZ[lr]);
-	return rb + (uint32_t)((pre >> (21 * pl)) & 0x1FFFFF);
+	const uint64_t *row = P.wpreV + (uint64_t)lr * P.W1;
+	uint32_t b = P.rowBV[lr] + fldV(row[w], pl);
+	if (pl) {
+		const uint64_t tot = row[P.W];
+		b += fldV(tot, 0);
+		if (pl == 2) b += fldV(tot, 1);
+	}
+	return b;
 }
-MC_HD uint32_t plane_base_global(const Params &P, uint32_t z, uint32_t y, uint32_t w, int pl)
+MC_HD uint32_t local_to_global(const Params &P, uint32_t z, uint32_t local)
 {
-	const uint32_t local = plane_base_local(P, z, y, w, pl);
 	// rows of the halo slice are numbered in the next slab's index space
 	if (z == P.hz) return (P.dbases ? P.dbases[1] : P.vbase_next) + (local - P.totals->nShared);
 	return (P.dbases ? P.dbases[0] : P.vbase) + local;
 }
 
-// ---------------------------------------------------------------------------
-// vertex emit for one (row, word)
-// ---------------------------------------------------------------------------
+// one vertex: plane a of grid point (x,y,z) -> slab-local vertex index id
 template <typename Sample>
-MC_HDN void emit_vertices_word(const Params &P, uint32_t z, uint32_t y, uint32_t w)
+MC_HDN void emit_vertex_task(const Params &P, uint32_t x, uint32_t y, uint32_t z, int a, bool is_point, uint32_t id)
 {
-	const Planes pl = planes(P, z, y, w);
-	if (!(pl.X | pl.Y | pl.Z)) return;
-	const uint32_t lr = (z - P.zlo) * P.NY + y;
-	const uint32_t zw = P.rowZ[lr] ? ldw(P.Z, P, lr, w) : 0u;
-	const uint64_t prow = ((uint64_t)z * P.NY + y) * P.NX;
-	uint32_t m, id;
-	for (int a = 0; a < 3; a++) {
-		m = a == 0 ? pl.X : (a == 1 ? pl.Y : pl.Z);
-		if (!m) continue;
-		id = plane_base_local(P, z, y, w, a);
-		while (m) {
-			int b = ffs32(m);
-			m &= m - 1;
-			uint32_t x = (w << 5) + b;
-			if (id < P.capV) {
-				if (a == 0 && ((zw >> b) & 1)) emit_point_vertex<Sample>(P, x, y, z, id);
-				else emit_edge_vertex<Sample>(P, x, y, z, a, id);
-				if (P.vkey) P.vkey[id] = (prow + x) * 4 + (unsigned)a;
-			} else {
-				P.totals->overflow = 1;
-			}
-			id++;
-		}
-	}
+	if (id >= P.capV) { P.totals->overflow = 1; return; }
+	if (is_point) emit_point_vertex<Sample>(P, x, y, z, id);
+	else emit_edge_vertex<Sample>(P, x, y, z, a, id);
+	if (P.vkey) P.vkey[id] = (((uint64_t)z * P.NY + y) * P.NX + x) * 4 + (unsigned)a;
 }
 
 // ---------------------------------------------------------------------------
-// triangle (+ centre vertex) emit for one (cell row, word).
-// scr: per-thread scratch of 8 (plane mask, base id) pairs, element k of this thread at
-// scr_mask[k*stride], scr_base[k*stride]  (shared memory in the kernel).
+// Vertex ids referenced by the cells of word w of cell row (z,y): eight
+// (plane mask, global id of the plane's first vertex in this word) pairs
 // plane combos: 0 X00  1 Y00  2 Z00  3 X10  4 Z10  5 X01  6 Y01  7 X11
-// (row suffix = dy dz of the point row relative to the cell row)
+// (suffix = dy dz of the point row relative to the cell row).  Ranks only count
+// bits below the queried one (offset <= 32), so the 32 bits of word w are all
+// that is needed even for x = 32w+32.
 // ---------------------------------------------------------------------------
 MC_HD unsigned combo_of_edge(unsigned e)  { return (0x573026412641ull >> (4 * e)) & 15; }
 MC_HD unsigned cx_of_edge(unsigned e)     { return (0x0F0u >> e) & 1; }
 MC_HD unsigned combo_of_corner(unsigned c) { return (0x57305730u >> (4 * c)) & 15; }
 
-template <typename Sample>
-MC_HDN void emit_triangles_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w,
-                                uint32_t *scr_mask, uint32_t *scr_base, uint32_t stride)
+struct CellPairs { uint32_t mask[8], base[8]; };
+
+MC_HDN void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, const WordRec &rec00, CellPairs &cp)
 {
-	CellWords cw;
-	cell_words(P, z, y, w, cw);
-	uint32_t act = cw.active;
-	if (!act) return;
 	const uint32_t lr = (z - P.zlo) * P.NY + y;
-	{
-		// plane masks of word w and the id of their first vertex
-		const int dy[8] = {0, 0, 0, 1, 1, 0, 0, 1}, dz[8] = {0, 0, 0, 0, 0, 1, 1, 1}, pln[8] = {0, 1, 2, 0, 2, 0, 1, 0};
-		Planes p0[4];          // per point row (dy + 2*dz) at word w
-		for (int r = 0; r < 4; r++) p0[r] = planes(P, z + (r >> 1), y + (r & 1), w);
-		for (int k = 0; k < 8; k++) {
-			int r = dy[k] + 2 * dz[k];
-			// ranks only count bits below the queried one (offset <= 32), so the
-			// 32 bits of word w are all that is needed even for x = 32w+32
-			scr_mask[k * stride] = pln[k] == 0 ? p0[r].X : (pln[k] == 1 ? p0[r].Y : p0[r].Z);
-			scr_base[k * stride] = plane_base_global(P, z + dz[k], y + dy[k], w, pln[k]);
-		}
+	WordRec r10, r01, r11;
+	if (!gz) {
+		// no on-iso sample anywhere: plane masks straight from the sign bitmap
+		const uint32_t i00 = lr * P.WP + w, i10 = i00 + P.WP, i01 = i00 + P.NY * P.WP, i11 = i01 + P.WP;
+		const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
+		const uint32_t s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
+		r10.X = (s10 ^ shr1(s10, P.S[i10 + 1])) & vx;
+		r01.X = (s01 ^ shr1(s01, P.S[i01 + 1])) & vx;
+		r11.X = (s11 ^ shr1(s11, P.S[i11 + 1])) & vx;
+		r10.Z = (s10 ^ s11) & vp;
+		r01.Y = (s01 ^ s11) & vp;
+	} else {
+		CellWords dummy;
+		word_masks(P, z, y + 1, w, true, r10, dummy);
+		word_masks(P, z + 1, y, w, true, r01, dummy);
+		word_masks(P, z + 1, y + 1, w, true, r11, dummy);
 	}
-	const uint64_t pre = P.wpreC[(uint64_t)lr * P.W + w];
-	uint32_t tid = P.rowBT[lr] + (uint32_t)(pre & 0xFFFFFFFFu);                         // slab-local
-	uint32_t cid = P.totals->nShared + P.rowBC[lr] + (uint32_t)(pre >> 32);             // slab-local
-	const uint64_t crow = ((uint64_t)z * P.ny + y) * P.nx;
-	while (act) {
-		int b = ffs32(act);
-		act &= act - 1;
-		const uint32_t x = (w << 5) + b;
-		const unsigned idx = cell_index(cw, b);
-		const unsigned zm = cw.zany ? cell_zmask(cw, b) : 0u;
-		const CellPattern cp = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
-		uint32_t centre_id = 0;
-		if (cp.centre) {
-			const uint32_t cl = cid++;
-			if (cl < P.capV) {
-				emit_centre_vertex<Sample>(P, x, y, z, cl);
-				if (P.vkey) P.vkey[cl] = (crow + x) * 4 + 3;
-			} else {
-				P.totals->overflow = 1;
-			}
-			centre_id = (P.dbases ? P.dbases[0] : P.vbase) + cl;
-		}
-		for (unsigned tw_i = cp.start;; tw_i++) {
-			const unsigned tw = tb.tri[tw_i];
-			uint32_t ti[3];
-			unsigned key[3];
+	const uint32_t l10 = lr + 1, l01 = lr + P.NY, l11 = l01 + 1;
+	cp.mask[0] = rec00.X; cp.base[0] = local_to_global(P, z, plane_base_local(P, lr, w, 0));
+	cp.mask[1] = rec00.Y; cp.base[1] = local_to_global(P, z, plane_base_local(P, lr, w, 1));
+	cp.mask[2] = rec00.Z; cp.base[2] = local_to_global(P, z, plane_base_local(P, lr, w, 2));
+	cp.mask[3] = r10.X;   cp.base[3] = local_to_global(P, z, plane_base_local(P, l10, w, 0));
+	cp.mask[4] = r10.Z;   cp.base[4] = local_to_global(P, z, plane_base_local(P, l10, w, 2));
+	cp.mask[5] = r01.X;   cp.base[5] = local_to_global(P, z + 1, plane_base_local(P, l01, w, 0));
+	cp.mask[6] = r01.Y;   cp.base[6] = local_to_global(P, z + 1, plane_base_local(P, l01, w, 1));
+	cp.mask[7] = r11.X;   cp.base[7] = local_to_global(P, z + 1, plane_base_local(P, l11, w, 0));
+}
+
+// global id of the vertex a triangle corner refers to: edge code e (0..11) of the
+// cell at bit b; zm = on-iso corner mask of the cell; key = identity used by the
+// zero-area test (marching_cubes_33.c:1235)
+MC_HD uint32_t corner_vertex(const uint32_t *pmask, const uint32_t *pbase, uint32_t stride, unsigned e, unsigned b,
+                             unsigned zm, unsigned &key)
+{
+	unsigned combo = combo_of_edge(e), off = b + cx_of_edge(e);
+	key = e;
+	if (zm) {
+		const unsigned a = edge_a(e), bb = edge_b(e);
+		if ((zm >> a) & 1) { key = 16 + a; combo = combo_of_corner(a); off = b + MC_CX(a); }
+		else if ((zm >> bb) & 1) { key = 16 + bb; combo = combo_of_corner(bb); off = b + MC_CX(bb); }
+	}
+	const uint32_t mk = pmask[combo * stride];
+	return pbase[combo * stride] + (uint32_t)popc32(off >= 32 ? mk : (mk & ((1u << off) - 1u)));
+}
+
+MC_HD void write_triangle(const Params &P, uint32_t tid, const uint32_t *ti, unsigned m, uint64_t cell)
+{
+	if (tid >= P.capT) { P.totals->overflow = 1; return; }
+	// winding: marching_cubes_33.c:1246-1250 (ti[0] = nibble 2, ti[1] = nibble 1, ti[2] = nibble 0)
+	uint32_t a0 = m ? ti[0] : ti[1], a1 = m ? ti[1] : ti[0];
+	if (P.geom.normal_neg) { uint32_t t = a0; a0 = a1; a1 = t; }
+	uint32_t *T = P.T + 3 * (uint64_t)tid;
+	T[0] = a0; T[1] = a1; T[2] = ti[2];
+	if (P.tcell) P.tcell[tid] = cell;
+}
+
+// one triangle of a cell WITHOUT on-iso corners: table word tw, cell at bit b
+MC_HD void emit_triangle_task(const Params &P, unsigned tw, unsigned b, unsigned m, uint32_t centre_id,
+                              const uint32_t *pmask, const uint32_t *pbase, uint32_t stride, uint32_t tid, uint64_t cell)
+{
+	uint32_t ti[3];
 #pragma unroll
-			for (int j = 0; j < 3; j++) {
-				const unsigned e = (tw >> (8 - 4 * j)) & 15;
-				if (e == 12) { ti[j] = centre_id; key[j] = 12; continue; }
-				const unsigned a = edge_a(e), bb = edge_b(e);
-				unsigned combo, off;
-				if (zm && ((zm >> a) & 1)) { key[j] = 16 + a; combo = combo_of_corner(a); off = b + MC_CX(a); }
-				else if (zm && ((zm >> bb) & 1)) { key[j] = 16 + bb; combo = combo_of_corner(bb); off = b + MC_CX(bb); }
-				else { key[j] = e; combo = combo_of_edge(e); off = b + cx_of_edge(e); }
-				const uint32_t mk = scr_mask[combo * stride];
-				ti[j] = scr_base[combo * stride] + (uint32_t)popc32(off >= 32 ? mk : (mk & ((1u << off) - 1u)));
-			}
-			if (key[0] != key[1] && key[0] != key[2] && key[1] != key[2]) {
-				if (tid < P.capT) {
-					uint32_t a0 = cp.m ? ti[0] : ti[1], a1 = cp.m ? ti[1] : ti[0];
-					if (P.geom.normal_neg) { uint32_t s = a0; a0 = a1; a1 = s; }
-					uint32_t *T = P.T + 3 * (uint64_t)tid;
-					T[0] = a0; T[1] = a1; T[2] = ti[2];
-					if (P.tcell) P.tcell[tid] = crow + x;
-				} else {
-					P.totals->overflow = 1;
-				}
-				tid++;
-			}
-			if (!(tw >> 12)) break;
-		}
+	for (int j = 0; j < 3; j++) {
+		const unsigned e = (tw >> (8 - 4 * j)) & 15;
+		unsigned key;
+		ti[j] = e == 12 ? centre_id : corner_vertex(pmask, pbase, stride, e, b, 0u, key);
 	}
+	write_triangle(P, tid, ti, m, cell);
+}
+
+// all triangles of a cell WITH on-iso corners (zero-area triangles are dropped);
+// only ids in [lo, hi) are written.  Returns the number of triangles kept.
+MC_HDN uint32_t emit_cell_triangles_z(const Params &P, const Tables &tb, unsigned b, const CellPattern &cp, unsigned zm,
+                                      uint32_t centre_id, const uint32_t *pmask, const uint32_t *pbase, uint32_t stride,
+                                      uint32_t tid, uint32_t lo, uint32_t hi, uint64_t cell)
+{
+	uint32_t n = 0;
+	for (unsigned tw_i = cp.start;; tw_i++) {
+		const unsigned tw = tb.tri[tw_i];
+		uint32_t ti[3];
+		unsigned key[3];
+#pragma unroll
+		for (int j = 0; j < 3; j++) {
+			const unsigned e = (tw >> (8 - 4 * j)) & 15;
+			if (e == 12) { ti[j] = centre_id; key[j] = 12; }
+			else ti[j] = corner_vertex(pmask, pbase, stride, e, b, zm, key[j]);
+		}
+		if (key[0] != key[1] && key[0] != key[2] && key[1] != key[2]) {
+			const uint32_t id = tid + n;
+			if (id >= lo && id < hi) write_triangle(P, id, ti, cp.m, cell);
+			n++;
+		}
+		if (!(tw >> 12)) break;
+	}
+	return n;
 }
 
 }  // namespace mc33

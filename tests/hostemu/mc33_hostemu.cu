@@ -25,7 +25,7 @@ static void run(Params &P, bool emit)
 	for (int i = 0; i < MC33_NTRI_WORDS; i++) pat[i] = (uint8_t)(MC33_PAT_NTRI[i] | (MC33_PAT_CENTRE[i] << 7));
 	tb.case256 = MC33_CASE256; tb.simple256 = MC33_SIMPLE256; tb.tri = MC33_TRI; tb.pat = pat;
 	const Real iso = (Real)P.iso;
-	// K1
+	// K1 (the kernel takes the two bits by comparison; here as the reference does)
 	for (uint32_t lr = 0; lr < P.Lrows; lr++) {
 		const Sample *src = (const Sample *)P.data + (uint64_t)lr * P.NX;
 		bool anyz = false;
@@ -43,51 +43,97 @@ static void run(Params &P, bool emit)
 			anyz |= z != 0;
 		}
 		P.rowZ[lr] = anyz;
+		if (anyz) P.totals->anyZ = 1;
 	}
-	// K2
-	for (uint32_t lr = 0; lr < P.Lrows; lr++) {
-		const uint32_t zl = lr / P.NY, y = lr - zl * P.NY, z = zl + P.zlo;
-		const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
-		const bool own_c = row_cells_owned(P, z, y);
-		uint64_t av = 0, ac = 0;
-		for (uint32_t w = 0; w < P.W; w++) {
-			uint64_t cv = 0, cc = 0;
-			if (own_p || own_c) count_word<Sample>(P, tb, z, y, w, own_p, own_c, cv, cc);
-			P.wpreV[(uint64_t)lr * P.W + w] = av;
-			P.wpreC[(uint64_t)lr * P.W + w] = ac;
-			av += cv; ac += cc;
-		}
-		P.rowNX[lr] = (uint32_t)(av & 0x1FFFFF);
-		P.rowNY[lr] = (uint32_t)((av >> 21) & 0x1FFFFF);
-		P.rowNZ[lr] = (uint32_t)((av >> 42) & 0x1FFFFF);
-		P.rowNT[lr] = (uint32_t)(ac & 0xFFFFFFFFu);
-		P.rowNC[lr] = (uint32_t)(ac >> 32);
-	}
-	// K3
+	const bool gz = P.totals->anyZ != 0;
+	// K2: word prefixes, row bases
 	{
 		uint64_t bv = 0, bc = 0, bt = 0;
 		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
-		for (uint32_t r = 0; r < P.Lrows; r++) {
-			if (r == owned_end) P.totals->nShared = (uint32_t)bv;
-			P.rowBX[r] = (uint32_t)bv; P.rowBY[r] = (uint32_t)(bv + P.rowNX[r]);
-			P.rowBZ[r] = (uint32_t)(bv + P.rowNX[r] + P.rowNY[r]);
-			P.rowBC[r] = (uint32_t)bc; P.rowBT[r] = (uint32_t)bt;
-			bv += (uint64_t)P.rowNX[r] + P.rowNY[r] + P.rowNZ[r]; bc += P.rowNC[r]; bt += P.rowNT[r];
+		for (uint32_t lr = 0; lr < P.Lrows; lr++) {
+			const uint32_t zl = lr / P.NY, y = lr - zl * P.NY, z = zl + P.zlo;
+			const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
+			const bool own_c = row_cells_owned(P, z, y);
+			uint64_t av = 0, ac = 0;
+			for (uint32_t w = 0; w < P.W; w++) {
+				uint64_t cv = 0, cc = 0;
+				WordRec rec;
+				if (own_p || own_c) count_word<Sample>(P, tb, z, y, w, gz, own_p, own_c, rec, cv, cc);
+				P.wpreV[(uint64_t)lr * P.W1 + w] = av;
+				P.wpreT[(uint64_t)lr * P.W1 + w] = ac;
+				av += cv; ac += cc;
+			}
+			P.wpreV[(uint64_t)lr * P.W1 + P.W] = av;
+			P.wpreT[(uint64_t)lr * P.W1 + P.W] = ac;
+			if (lr == owned_end) P.totals->nShared = (uint32_t)bv;
+			P.rowBV[lr] = (uint32_t)bv; P.rowBT[lr] = (uint32_t)bt; P.rowBC[lr] = (uint32_t)bc;
+			bv += fldV(av, 0) + fldV(av, 1) + fldV(av, 2); bt += ac & 0xFFFFFFFFu; bc += ac >> 32;
 		}
+		P.rowBV[P.Lrows] = (uint32_t)bv; P.rowBT[P.Lrows] = (uint32_t)bt; P.rowBC[P.Lrows] = (uint32_t)bc;
 		if (owned_end >= P.Lrows) P.totals->nShared = (uint32_t)bv;
-		P.totals->nCentre = (uint32_t)bc; P.totals->nT = (uint32_t)bt; P.totals->pad_[0] = (uint32_t)bv;
+		P.totals->nCentre = (uint32_t)bc; P.totals->nT = (uint32_t)bt; P.totals->nSharedAll = (uint32_t)bv;
 	}
 	if (!emit) return;
-	// K4v
-	for (uint32_t lr = (P.pz0 - P.zlo) * P.NY; lr < (P.pz1 - P.zlo) * P.NY; lr++)
-		for (uint32_t w = 0; w < P.W; w++)
-			emit_vertices_word<Sample>(P, lr / P.NY + P.zlo, lr % P.NY, w);
-	// K4t
-	uint32_t scr_mask[8], scr_base[8];
+	// K3: vertices
+	for (uint32_t lr = (P.pz0 - P.zlo) * P.NY; lr < (P.pz1 - P.zlo) * P.NY; lr++) {
+		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
+		for (uint32_t w = 0; w < P.W; w++) {
+			WordRec rec; CellWords cw;
+			word_masks(P, z, y, w, gz, rec, cw);
+			const uint32_t zw = (gz && P.rowZ[lr]) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
+			for (int a = 0; a < 3; a++) {
+				uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
+				uint32_t id = plane_base_local(P, lr, w, a);
+				while (m) {
+					int b = ffs32(m);
+					m &= m - 1;
+					emit_vertex_task<Sample>(P, (w << 5) + b, y, z, a, a == 0 && ((zw >> b) & 1), id++);
+				}
+			}
+		}
+	}
+	// K4: triangles (+ centre vertices)
+	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
 	for (uint32_t lr = (P.cz0 - P.zlo) * P.NY; lr < (P.cz1 - P.zlo) * P.NY; lr++) {
-		if (lr % P.NY >= P.ny) continue;
-		for (uint32_t w = 0; w < P.WC; w++)
-			emit_triangles_word<Sample>(P, tb, lr / P.NY + P.zlo, lr % P.NY, w, scr_mask, scr_base, 1);
+		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
+		if (y >= P.ny) continue;
+		for (uint32_t w = 0; w < P.WC; w++) {
+			const uint64_t pre0 = P.wpreT[(uint64_t)lr * P.W1 + w], pre1 = P.wpreT[(uint64_t)lr * P.W1 + w + 1];
+			if (pre0 == pre1) continue;
+			WordRec rec; CellWords cw; CellPairs cp;
+			word_masks(P, z, y, w, gz, rec, cw);
+			cell_pairs(P, z, y, w, gz, rec, cp);
+			const uint32_t cloc = P.totals->nShared + P.rowBC[lr] + (uint32_t)(pre0 >> 32);
+			uint32_t act = rec.act, tid = P.rowBT[lr] + (uint32_t)pre0, cord = 0;
+			while (act) {
+				int b = ffs32(act);
+				act &= act - 1;
+				const unsigned idx = cell_index(cw.c, 1, b);
+				const unsigned zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
+				const uint32_t x = (w << 5) + b;
+				const CellPattern cpat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
+				const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
+				if (cpat.centre) {
+					const uint32_t cl = cloc + cord;
+					if (cl < P.capV) {
+						emit_centre_vertex<Sample>(P, x, y, z, cl);
+						if (P.vkey) P.vkey[cl] = cell * 4 + 3;
+					} else {
+						P.totals->overflow = 1;
+					}
+				}
+				if (zm) {
+					tid += emit_cell_triangles_z(P, tb, (unsigned)b, cpat, zm, vb + cloc + cord, cp.mask, cp.base, 1, tid, 0u,
+					                             0xFFFFFFFFu, cell);
+				} else {
+					for (uint32_t j = 0; j < cpat.ntri; j++)
+						emit_triangle_task(P, tb.tri[cpat.start + j], (unsigned)b, cpat.m, vb + cloc + cord, cp.mask, cp.base, 1,
+						                   tid + j, cell);
+					tid += cpat.ntri;
+				}
+				cord += cpat.centre;
+			}
+		}
 	}
 }
 
@@ -102,21 +148,22 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.zlo = d->z_lo; P.zhi = d->z_hi; P.cz0 = d->cell_z0; P.cz1 = d->cell_z1;
 	P.pz0 = d->cell_z0; P.pz1 = d->is_last ? NZ : d->cell_z1;
 	P.hz = d->is_last ? 0xFFFFFFFFu : d->cell_z1;
-	P.W = (P.NX + 31) / 32; P.WC = (P.nx + 31) / 32; P.WP = (P.W + 1 + 3) & ~3u;
+	P.W = (P.NX + 31) / 32; P.WC = (P.nx + 31) / 32; P.WP = (P.W + 1 + 3) & ~3u; P.W1 = P.W + 1;
 	P.Lrows = (P.zhi - P.zlo) * P.NY;
+	P.R = P.W >= 256 ? 1 : 256 / P.W; P.CW = P.W < 256 ? P.W : 256;
+	P.mCW = P.CW >= 2 ? (uint32_t)(0x100000000ull / P.CW) : 0u; P.mNY = (uint32_t)(0x100000000ull / P.NY);
 	P.geom.store = d->store; P.geom.normal_neg = d->normal_neg; P.geom.tsa = d->tsa;
 	for (int i = 0; i < 3; i++) { P.geom.O[i] = d->O[i]; P.geom.D[i] = d->D[i]; }
 	P.geom.ca = d->ca; P.geom.cb = d->cb;
 	for (int i = 0; i < 9; i++) { P.geom.A[i] = d->A[i]; P.geom.Ai[i] = d->Ai[i]; }
 	P.iso = d->dtype == MC33CU_F64 ? iso + 0.0 : (double)((float)iso + 0.0f);
-	std::vector<uint32_t> S((size_t)P.Lrows * P.WP, 0), Z((size_t)P.Lrows * P.WP, 0), rn((size_t)P.Lrows * 5), rb((size_t)P.Lrows * 5);
+	std::vector<uint32_t> S((size_t)P.Lrows * P.WP, 0), Z((size_t)P.Lrows * P.WP, 0), rb(((size_t)P.Lrows + 1) * 3);
 	std::vector<uint8_t> rz(P.Lrows);
-	std::vector<uint64_t> wv((size_t)P.Lrows * P.W), wc((size_t)P.Lrows * P.W);
+	std::vector<uint64_t> wv((size_t)P.Lrows * P.W1), wc((size_t)P.Lrows * P.W1);
 	Totals tot;
 	memset(&tot, 0, sizeof tot);
-	P.S = S.data(); P.Z = Z.data(); P.rowZ = rz.data(); P.wpreV = wv.data(); P.wpreC = wc.data();
-	P.rowNX = rn.data(); P.rowNY = P.rowNX + P.Lrows; P.rowNZ = P.rowNY + P.Lrows; P.rowNC = P.rowNZ + P.Lrows; P.rowNT = P.rowNC + P.Lrows;
-	P.rowBX = rb.data(); P.rowBY = P.rowBX + P.Lrows; P.rowBZ = P.rowBY + P.Lrows; P.rowBC = P.rowBZ + P.Lrows; P.rowBT = P.rowBC + P.Lrows;
+	P.S = S.data(); P.Z = Z.data(); P.rowZ = rz.data(); P.wpreV = wv.data(); P.wpreT = wc.data();
+	P.rowBV = rb.data(); P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
 	P.totals = &tot;
 	bool emit = o != nullptr;
 	if (emit) {
@@ -134,7 +181,7 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	}
 	if (counts) {
 		counts->nShared = tot.nShared; counts->nCentre = tot.nCentre; counts->nT = tot.nT;
-		counts->nSharedHalo = tot.pad_[0] - tot.nShared; counts->nV = (uint64_t)tot.nShared + tot.nCentre;
+		counts->nSharedHalo = tot.nSharedAll - tot.nShared; counts->nV = (uint64_t)tot.nShared + tot.nCentre;
 	}
 	return tot.overflow ? MC33CU_ERR_CAPACITY : 0;
 }
