@@ -137,14 +137,16 @@ struct Params {
 	uint32_t pz0, pz1;            // point slices whose shared vertices this slab owns
 	uint32_t cz0, cz1;            // cell layers this slab owns
 	uint32_t hz;                  // halo point slice numbered in the next slab (== pz1) or 0xFFFFFFFF
-	uint32_t W, WC, WP, W1;       // words per point row, per cell row, bitmap row stride (>= W+1), W+1
+	uint32_t W, WC;               // words per point row, per cell row
+	uint32_t Q, WP;               // quads (4 words, one 16-byte load) per row; row stride in words = 4Q+4
+	uint32_t G;                   // rows per warp: a warp takes G whole rows, one lane per quad (Q <= 32),
+	                              // or one row in passes of 32 quads (G == 1)
 	uint32_t Lrows;               // (zhi-zlo)*NY
-	uint32_t R, CW;               // a batch = R whole rows (CW == W), or CW words of one row (R == 1)
-	uint32_t mCW, mNY;            // floor(2^32/CW), floor(2^32/NY) for fastdiv
-	uint32_t *S, *Z;              // bitmaps [Lrows][WP]
+	uint32_t mQ, mNY;             // floor(2^32/Q), floor(2^32/NY) for fastdiv
+	uint32_t *S, *Z;              // bitmaps [Lrows][WP]; words >= W of a row are zero
 	uint8_t *rowZ;                // [Lrows] any Z bit in the row
-	uint64_t *wpreV;              // [Lrows][W1] row-local exclusive prefix X | Y<<21 | Z<<42; entry W = row totals
-	uint64_t *wpreT;              // [Lrows][W1] row-local exclusive prefix T | C<<32; entry W = row totals
+	uint64_t *wpreV;              // [Lrows][WP] row-local exclusive prefix X | Y<<21 | Z<<42 of the vertices in
+	                              // words < k; entries W..4Q hold the row totals
 	uint32_t *rowBV, *rowBT, *rowBC;   // [Lrows+1] slab-local exclusive bases: vertices, triangles, centres
 	Totals *totals;
 	double iso;
@@ -438,6 +440,46 @@ MC_HDN void word_masks(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool
 	}
 }
 
+// ---------------------------------------------------------------------------
+// quads: four consecutive bitmap words of a row (one 16-byte load) plus the
+// word after them (for the x+1 neighbour of bit 31 of the fourth word)
+// ---------------------------------------------------------------------------
+struct Quad { uint32_t s[5]; };
+
+MC_HD Quad load_quad(const uint32_t *B, uint64_t i)   // i = word index, multiple of 4
+{
+	Quad q;
+#if defined(__CUDA_ARCH__)
+	const uint4 v = *reinterpret_cast<const uint4 *>(B + i);
+	q.s[0] = v.x; q.s[1] = v.y; q.s[2] = v.z; q.s[3] = v.w;
+#else
+	q.s[0] = B[i]; q.s[1] = B[i + 1]; q.s[2] = B[i + 2]; q.s[3] = B[i + 3];
+#endif
+	q.s[4] = B[i + 4];
+	return q;
+}
+
+// word k (0..3, compile time) of quad q of row (z,y) when the grid has NO on-iso
+// sample: the same record and corner words word_masks() yields.  q10 / q01 / q11
+// are the quads of rows y+1, z+1, (y+1,z+1); where such a row does not exist the
+// caller passes the row itself, which zeroes the corresponding plane.
+MC_HD void quad_word(const Params &P, const Quad &q00, const Quad &q10, const Quad &q01, const Quad &q11, int k,
+                     uint32_t w, bool cells, WordRec &rec, uint32_t *c)
+{
+	const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
+	const uint32_t s00 = q00.s[k], s10 = q10.s[k], s01 = q01.s[k], s11 = q11.s[k];
+	const uint32_t x00 = shr1(s00, q00.s[k + 1]), x10 = shr1(s10, q10.s[k + 1]);
+	const uint32_t x01 = shr1(s01, q01.s[k + 1]), x11 = shr1(s11, q11.s[k + 1]);
+	rec.X = (s00 ^ x00) & vx;
+	rec.Y = (s00 ^ s10) & vp;
+	rec.Z = (s00 ^ s01) & vp;
+	c[0] = s00; c[4] = x00; c[1] = s10; c[5] = x10;
+	c[2] = s11; c[6] = x11; c[3] = s01; c[7] = x01;
+	const uint32_t any = s00 | s10 | s01 | s11 | x00 | x10 | x01 | x11;
+	const uint32_t all = s00 & s10 & s01 & s11 & x00 & x10 & x01 & x11;
+	rec.act = cells ? (any & ~all & vx) : 0u;
+}
+
 MC_HD unsigned cell_index(const uint32_t *c, uint32_t stride, int b)
 {
 	unsigned i = 0;
@@ -513,27 +555,27 @@ MC_HDN CellPattern cell_pattern(const Params &P, const Tables &tb, uint32_t x, u
 }
 
 // ---------------------------------------------------------------------------
-// count step for one (row, word): vertices owned by the 32 points, triangles and
-// centre vertices of the 32 cells.  Packed counts:
-//   cv = nX | nY<<21 | nZ<<42        cc = nT | nC<<32
-// rec is what the emit kernels read back.
+// count step.  Packed counts of one (row, word):
+//   cv = nX | nY<<21 | nZ<<42   vertices owned by the 32 points
+//   cc = nT | nC<<32            triangles / centre vertices of the 32 cells
 // ---------------------------------------------------------------------------
-template <typename Sample>
-MC_HDN void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,
-                       bool own_points, bool own_cells, WordRec &rec, uint64_t &cv, uint64_t &cc)
+MC_HD uint64_t pack_planes(const WordRec &rec)
 {
-	CellWords cw;
-	word_masks(P, z, y, w, gz, rec, cw);
-	if (!own_points) { rec.X = rec.Y = rec.Z = 0; }
-	if (!own_cells) rec.act = 0;
-	cv = (uint64_t)popc32(rec.X) | ((uint64_t)popc32(rec.Y) << 21) | ((uint64_t)popc32(rec.Z) << 42);
-	uint32_t act = rec.act;
+	return (uint64_t)popc32(rec.X) | ((uint64_t)popc32(rec.Y) << 21) | ((uint64_t)popc32(rec.Z) << 42);
+}
+
+// walk the active cells of word w of cell row (z,y): c[k] / zc[k] = corner sign /
+// on-iso words (zc only read when zany)
+template <typename Sample>
+MC_HDN uint64_t count_cells(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, uint32_t act,
+                            const uint32_t *c, const uint32_t *zc, uint32_t zany)
+{
 	uint32_t nt = 0, nc = 0;
 	while (act) {
 		int b = ffs32(act);
 		act &= act - 1;
-		unsigned idx = cell_index(cw.c, 1, b);
-		unsigned zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
+		unsigned idx = cell_index(c, 1, b);
+		unsigned zm = zany ? cell_zmask(zc, 1, b) : 0u;
 		unsigned e = tb.simple256[idx];
 		if (e != 0xFFFFu && !zm) {
 			nt += e >> 12;
@@ -543,7 +585,21 @@ MC_HDN void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y
 			nc += cp.centre;
 		}
 	}
-	cc = (uint64_t)nt | ((uint64_t)nc << 32);
+	return (uint64_t)nt | ((uint64_t)nc << 32);
+}
+
+// generic form (any grid, on-iso samples included) straight from the bitmaps
+template <typename Sample>
+MC_HDN void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,
+                       bool own_points, bool own_cells, uint64_t &cv, uint64_t &cc)
+{
+	WordRec rec;
+	CellWords cw;
+	word_masks(P, z, y, w, gz, rec, cw);
+	if (!own_points) { rec.X = rec.Y = rec.Z = 0; }
+	if (!own_cells) rec.act = 0;
+	cv = pack_planes(rec);
+	cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
 }
 
 // ---------------------------------------------------------------------------
@@ -693,7 +749,7 @@ MC_HD bool row_cells_owned(const Params &P, uint32_t z, uint32_t y) { return z >
 
 // ---------------------------------------------------------------------------
 // vertex numbering.  wpreV[lr][w] packs the number of X / Y / Z plane vertices
-// of row lr in words < w (21 bits each), entry W the row totals; rowBV[lr] is
+// of row lr in words < w (21 bits each), entry 4Q the row totals; rowBV[lr] is
 // the slab-local id of the row's first vertex.  Within a row: X plane by x,
 // then Y, then Z.  Vertex ARRAYS are indexed locally; triangle CONTENTS are
 // global ids (local + vbase).
@@ -702,10 +758,10 @@ MC_HD uint32_t fldV(uint64_t p, int pl) { return (uint32_t)(p >> (21 * pl)) & 0x
 
 MC_HD uint32_t plane_base_local(const Params &P, uint32_t lr, uint32_t w, int pl)
 {
-	const uint64_t *row = P.wpreV + (uint64_t)lr * P.W1;
+	const uint64_t *row = P.wpreV + (uint64_t)lr * P.WP;
 	uint32_t b = P.rowBV[lr] + fldV(row[w], pl);
 	if (pl) {
-		const uint64_t tot = row[P.W];
+		const uint64_t tot = row[4 * P.Q];
 		b += fldV(tot, 0);
 		if (pl == 2) b += fldV(tot, 1);
 	}
@@ -742,20 +798,20 @@ MC_HD unsigned combo_of_corner(unsigned c) { return (0x57305730u >> (4 * c)) & 1
 
 struct CellPairs { uint32_t mask[8], base[8]; };
 
-MC_HDN void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, const WordRec &rec00, CellPairs &cp)
+MC_HDN void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, const WordRec &rec00,
+                       const CellWords &cw, CellPairs &cp)
 {
 	const uint32_t lr = (z - P.zlo) * P.NY + y;
 	WordRec r10, r01, r11;
 	if (!gz) {
-		// no on-iso sample anywhere: plane masks straight from the sign bitmap
-		const uint32_t i00 = lr * P.WP + w, i10 = i00 + P.WP, i01 = i00 + P.NY * P.WP, i11 = i01 + P.WP;
+		// no on-iso sample anywhere: plane masks straight from the corner sign words
+		// (c[1],c[5] = row y+1 at x, x+1; c[3],c[7] = row z+1; c[2],c[6] = row (y+1,z+1))
 		const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
-		const uint32_t s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
-		r10.X = (s10 ^ shr1(s10, P.S[i10 + 1])) & vx;
-		r01.X = (s01 ^ shr1(s01, P.S[i01 + 1])) & vx;
-		r11.X = (s11 ^ shr1(s11, P.S[i11 + 1])) & vx;
-		r10.Z = (s10 ^ s11) & vp;
-		r01.Y = (s01 ^ s11) & vp;
+		r10.X = (cw.c[1] ^ cw.c[5]) & vx;
+		r01.X = (cw.c[3] ^ cw.c[7]) & vx;
+		r11.X = (cw.c[2] ^ cw.c[6]) & vx;
+		r10.Z = (cw.c[1] ^ cw.c[2]) & vp;
+		r01.Y = (cw.c[3] ^ cw.c[2]) & vp;
 	} else {
 		CellWords dummy;
 		word_masks(P, z, y + 1, w, true, r10, dummy);

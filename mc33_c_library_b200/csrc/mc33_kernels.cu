@@ -130,7 +130,7 @@ template <> struct Cls<uint8_t> : ClsInt<uint8_t> { __device__ __forceinline__ C
 template <> struct Cls<uint16_t> : ClsInt<uint16_t> { __device__ __forceinline__ Cls(const Params &P) : ClsInt<uint16_t>(P) {} };
 template <> struct Cls<uint32_t> : ClsInt<uint32_t> { __device__ __forceinline__ Cls(const Params &P) : ClsInt<uint32_t>(P) {} };
 
-#define CLS_THREADS 128
+#define CLS_THREADS 256
 #define CLS_STAGES 4
 
 struct ClsPlan {
@@ -215,49 +215,46 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 		const int s = (int)(k % CLS_STAGES);
 		const uint32_t c = blockIdx.x + k * gridDim.x;
 		const ClsChunk ck = cls_chunk<Sample>(P, pl, c);
+		const bool whole = pl.nwchunk == 1;
+		// the row's old on-iso flag is fetched before waiting for the samples
+		const uint32_t rr0 = wid;
+		uint32_t zold_next = rr0 < ck.nrows ? P.rowZ[ck.lr0 + rr0] : 0u;
 		mbar_wait(&full[s], (k / CLS_STAGES) & 1);
 		const unsigned char *st = smem + (size_t)s * pl.stage_bytes + (((uint64_t)(uintptr_t)gbase + ck.b0) & 15);
-		for (uint32_t rr = wid; rr < ck.nrows; rr += CLS_THREADS / 32) {
+		// full (32 valid samples) words of this chunk's word range
+		const uint32_t nf = nfull > ck.w0 ? min(ck.nw, nfull - ck.w0) : 0u;
+		for (uint32_t rr = rr0; rr < ck.nrows; rr += CLS_THREADS / 32) {
 			const uint32_t lr = ck.lr0 + rr;
+			const bool zold = zold_next != 0;
+			if (rr + CLS_THREADS / 32 < ck.nrows) zold_next = P.rowZ[lr + CLS_THREADS / 32];
 			// sample x of this row sits at src[x - 32*w0]
 			const Sample *src = (const Sample *)st + (size_t)rr * P.NX + lane;
-			uint32_t *Sr = P.S + (uint64_t)lr * P.WP + ck.w0;
+			uint32_t *Sr = P.S + (uint64_t)lr * P.WP + ck.w0;    // 16-byte aligned (WP, w0 multiples of 4)
 			bool zl = false;                                  // this lane saw an on-iso sample
-			for (uint32_t c0 = 0; c0 < ck.nw; c0 += 32) {     // 32 words per group: lane j keeps word c0+j
-				const uint32_t wg = ck.w0 + c0;               // global index of the group's first word
-				const uint32_t nwg = min(32u, ck.nw - c0);
-				const uint32_t limf = nfull > wg ? min(nwg, nfull - wg) : 0u;   // words with 32 valid samples
-				const Sample *q = src + ((size_t)c0 << 5);
-				uint32_t sw = 0;
-				uint32_t g = 0;
-				for (; g + 4 <= limf; g += 4) {
-					const Sample f0 = q[32 * g], f1 = q[32 * g + 32], f2 = q[32 * g + 64], f3 = q[32 * g + 96];
-					const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cls.gt(f0)), b1 = __ballot_sync(0xFFFFFFFFu, cls.gt(f1));
-					const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, cls.gt(f2)), b3 = __ballot_sync(0xFFFFFFFFu, cls.gt(f3));
-					zl = zl || cls.eq(f0) || cls.eq(f1) || cls.eq(f2) || cls.eq(f3);
-					sw = lane == g ? b0 : sw;
-					sw = lane == g + 1 ? b1 : sw;
-					sw = lane == g + 2 ? b2 : sw;
-					sw = lane == g + 3 ? b3 : sw;
-				}
-				for (; g < limf; g++) {
-					const Sample f = q[32 * g];
-					const uint32_t b = __ballot_sync(0xFFFFFFFFu, cls.gt(f));
-					zl = zl || cls.eq(f);
-					sw = lane == g ? b : sw;
-				}
-				if (tail && g < nwg && wg + g == nfull) {      // the partial last word of the row
-					const bool ok = lane < tail;
-					const Sample f = ok ? q[32 * g] : (Sample)0;
-					const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok && cls.gt(f));
-					zl = zl || (ok && cls.eq(f));
-					sw = lane == g ? b : sw;
-				}
-				if (lane < nwg) Sr[c0 + lane] = sw;
+			const Sample *q = src;
+			uint32_t g = 0;
+			for (; g + 4 <= nf; g += 4, q += 128) {
+				const Sample f0 = q[0], f1 = q[32], f2 = q[64], f3 = q[96];
+				uint4 b;
+				b.x = __ballot_sync(0xFFFFFFFFu, cls.gt(f0)); b.y = __ballot_sync(0xFFFFFFFFu, cls.gt(f1));
+				b.z = __ballot_sync(0xFFFFFFFFu, cls.gt(f2)); b.w = __ballot_sync(0xFFFFFFFFu, cls.gt(f3));
+				zl = zl || cls.eq(f0) || cls.eq(f1) || cls.eq(f2) || cls.eq(f3);
+				if (lane == 0) *reinterpret_cast<uint4 *>(Sr + g) = b;
+			}
+			for (; g < nf; g++, q += 32) {
+				const Sample f = q[0];
+				const uint32_t b = __ballot_sync(0xFFFFFFFFu, cls.gt(f));
+				zl = zl || cls.eq(f);
+				if (lane == 0) Sr[g] = b;
+			}
+			if (tail && g < ck.nw && ck.w0 + g == nfull) {     // the partial last word of the row
+				const bool ok = lane < tail;
+				const Sample f = ok ? q[0] : (Sample)0;
+				const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok && cls.gt(f));
+				zl = zl || (ok && cls.eq(f));
+				if (lane == 0) Sr[g] = b;
 			}
 			const bool zany = __any_sync(0xFFFFFFFFu, zl);
-			const bool whole = pl.nwchunk == 1;
-			const bool zold = P.rowZ[lr] != 0;
 			if (zany || zold || !whole) {                    // rare: (re)write this row's Z words
 				uint32_t *Zr = P.Z + (uint64_t)lr * P.WP + ck.w0;
 				for (uint32_t w = 0; w < ck.nw; w++) {
@@ -278,7 +275,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 }
 
 // ---------------------------------------------------------------------------
-// block-wide exclusive scan of two packed 64-bit counters (256 threads)
+// block-wide exclusive scan of two 64-bit counters (256 threads)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void block_exscan2(uint64_t &a, uint64_t &b, uint64_t &ta, uint64_t &tb,
                                               uint64_t (*sw)[8])
@@ -304,318 +301,396 @@ __device__ __forceinline__ void block_exscan2(uint64_t &a, uint64_t &b, uint64_t
 	ta = sa; tb = sb;
 }
 
-// ---------------------------------------------------------------------------
-// K2: count + scan.
-//
-// Batches of R whole rows (R*W <= 256, one thread per (row, word); a row longer
-// than 256 words is one batch walked in passes) are taken in ticket order.  One
-// block scan gives the row-local word prefixes; the batch totals then go through
-// a single-pass decoupled look-back (status word = flag<<62 | epoch<<42 | value;
-// flag 1 = batch aggregate, 2 = inclusive prefix; the epoch makes stale words of
-// earlier extractions read as "not ready", so the array is never cleared), which
-// yields the slab-local base of every row: the implicit running M->nV++ / nT++ of
-// the reference (marching_cubes_33.c:487, :1245).
-// ---------------------------------------------------------------------------
-#define ST_FLAG(s) ((unsigned)((s) >> 62))
-#define ST_EPOCH(s) ((uint32_t)((s) >> 42) & 0xFFFFFu)
-#define ST_VAL(s) ((s) & ((1ull << 42) - 1))
-#define ST_MAKE(flag, epoch, val) (((uint64_t)(flag) << 62) | ((uint64_t)((epoch) & 0xFFFFFu) << 42) | (val))
-
 __device__ __forceinline__ uint32_t sumV(uint64_t p) { return fldV(p, 0) + fldV(p, 1) + fldV(p, 2); }
 
+// lane -> (row within the warp's group, quad) of pass `pass`
+__device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32_t pass, uint32_t &r, uint32_t &q)
+{
+	if (P.Q <= 32) { r = fastdiv(lane, P.Q, P.mQ); q = lane - r * P.Q; }
+	else { r = 0; q = pass * 32 + lane; }
+}
+
+// ---------------------------------------------------------------------------
+// K2: count.  Warp-synchronous: a warp takes G whole rows, one lane per quad
+// (four bitmap words = one 16-byte load per neighbouring row), so the row-local
+// word prefixes come out of one shuffle scan with no block barrier; rows longer
+// than 128 words are walked in passes of 32 quads with a carry.  The per-row
+// totals of the CTA's 8G rows are then scanned once per CTA, leaving CTA-relative
+// row bases and one (V, T, C) sum per CTA for k_rowscan.
+// ---------------------------------------------------------------------------
+#define CNT_WARPS 8
+
 template <typename Sample>
-__global__ void __launch_bounds__(256) k_count(Params P, uint64_t *status, uint32_t *ticket, uint32_t nbatch, uint32_t epoch,
-                                               uint32_t owned_end_row)
+__global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t *blkSum)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	__shared__ uint64_t s_preV[257], s_preT[257];
+	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
 	__shared__ uint64_t s_w[2][8];
-	__shared__ uint64_t s_excl[3];
-	__shared__ uint32_t s_batch;
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const bool gz = P.totals->anyZ != 0;
-	const uint32_t n = P.R * P.W;
+	const uint32_t RB = CNT_WARPS * P.G;
+	const uint32_t npass = (P.Q + 31) / 32;
 
-	while (true) {
-		if (threadIdx.x == 0) s_batch = atomicAdd(ticket, 1u);
+	for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+		s_row[0][threadIdx.x] = 0; s_row[1][threadIdx.x] = 0; s_row[2][threadIdx.x] = 0;
 		__syncthreads();
-		const uint32_t batch = s_batch;
-		if (batch >= nbatch) break;
-		const uint32_t row0 = batch * P.R;
+		const uint32_t row0 = blk * RB + wid * P.G;
 		uint64_t carryV = 0, carryT = 0;
-		for (uint32_t base = 0; base < n; base += 256) {
-			const uint32_t it = base + threadIdx.x;
-			uint64_t cv = 0, ct = 0;
-			uint32_t r = 0, w = 0, lr = 0xFFFFFFFFu;
-			if (it < n) {
-				r = P.R > 1 ? fastdiv(it, P.W, P.mCW) : 0u;
-				w = it - r * P.W;
-				if (row0 + r < P.Lrows) lr = row0 + r;
-			}
-			if (lr != 0xFFFFFFFFu) {
+		for (uint32_t pass = 0; pass < npass; pass++) {
+			uint32_t r, q;
+			lane_item(P, lane, pass, r, q);
+			const uint32_t lr = row0 + r;
+			const bool valid = r < P.G && q < P.Q && lr < P.Lrows;
+			uint64_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, tt = 0;
+			if (valid) {
 				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
 				const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
 				const bool own_c = row_cells_owned(P, z, y);
 				if (own_p || own_c) {
-					WordRec rec;
-					count_word<Sample>(P, tb, z, y, w, gz, own_p, own_c, rec, cv, ct);
-				}
-			}
-			const uint64_t mv = cv, mt = ct;
-			uint64_t tv, tt;
-			block_exscan2(cv, ct, tv, tt, s_w);
-			cv += carryV; ct += carryT;
-			s_preV[threadIdx.x] = cv; s_preT[threadIdx.x] = ct;
-			__syncthreads();
-			if (lr != 0xFFFFFFFFu) {
-				const uint64_t rsV = P.R > 1 ? s_preV[r * P.W] : 0ull, rsT = P.R > 1 ? s_preT[r * P.W] : 0ull;
-				uint64_t *pv = P.wpreV + (uint64_t)lr * P.W1, *pt = P.wpreT + (uint64_t)lr * P.W1;
-				pv[w] = cv - rsV; pt[w] = ct - rsT;
-				if (w == P.W - 1) { pv[P.W] = cv + mv - rsV; pt[P.W] = ct + mt - rsT; }
-			}
-			carryV += tv; carryT += tt;
-			if (base + 256 < n) __syncthreads();
-		}
-		// batch aggregates -> look-back; warps 0..2 handle vertices / triangles / centres
-		if (wid < 3) {
-			const unsigned q = wid;
-			const uint64_t agg = q == 0 ? (uint64_t)sumV(carryV) : (q == 1 ? (carryT & 0xFFFFFFFFull) : (carryT >> 32));
-			volatile uint64_t *st = status;
-			uint64_t excl = 0;
-			if (batch == 0) {
-				if (lane == 0) st[q] = ST_MAKE(2, epoch, agg);
-			} else {
-				if (lane == 0) st[3 * (uint64_t)batch + q] = ST_MAKE(1, epoch, agg);
-				int64_t pos = (int64_t)batch - 1;
-				while (true) {
-					const int64_t idx = pos - (int64_t)lane;
-					uint64_t s = ST_MAKE(2, epoch, 0);       // batches before the first one: prefix 0
-					if (idx >= 0) {
-						do { s = st[3 * (uint64_t)idx + q]; } while (ST_FLAG(s) == 0 || ST_EPOCH(s) != (epoch & 0xFFFFFu));
-					}
-					const unsigned pre_mask = __ballot_sync(0xFFFFFFFFu, ST_FLAG(s) == 2);
-					// lanes up to and including the first inclusive prefix contribute
-					const unsigned first = pre_mask ? (unsigned)__ffs((int)pre_mask) - 1u : 32u;
-					uint64_t v = (lane <= first) ? ST_VAL(s) : 0;
+					if (!gz) {
+						const bool hasY = y < P.ny, hasZ = z < P.nz;
+						const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u;
+						const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
+						const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
+						const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
+						uint64_t pv[4];
 #pragma unroll
-					for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-					excl += v;
-					if (pre_mask) break;
-					pos -= 32;
+						for (int k = 0; k < 4; k++) {
+							WordRec rec;
+							uint32_t c[8];
+							quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c && hasZ, rec, c);
+							if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
+							pv[k] = pack_planes(rec);
+							if (rec.act) tt += count_cells<Sample>(P, tb, z, y, 4 * q + k, rec.act, c, c, 0u);
+						}
+						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
+					} else {
+						uint64_t pv[4] = {0, 0, 0, 0};
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							const uint32_t w = 4 * q + k;
+							if (w < P.W) {
+								uint64_t cc;
+								count_word<Sample>(P, tb, z, y, w, true, own_p, own_c, pv[k], cc);
+								tt += cc;
+							}
+						}
+						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
+					}
 				}
-				if (lane == 0) st[3 * (uint64_t)batch + q] = ST_MAKE(2, epoch, excl + agg);
 			}
-			if (lane == 0) s_excl[q] = excl;
+			// lane-local exclusive prefix over the four words, then the warp scan
+			const uint64_t e1 = pv0, e2 = e1 + pv1, e3 = e2 + pv2, tv = e3 + pv3;
+			uint64_t iv = tv, it = tt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint64_t xv = __shfl_up_sync(0xFFFFFFFFu, iv, d), xt = __shfl_up_sync(0xFFFFFFFFu, it, d);
+				if (lane >= (unsigned)d) { iv += xv; it += xt; }
+			}
+			const uint64_t xv = iv - tv, xt = it - tt;
+			uint64_t rsv = 0, rst = 0;
+			if (P.Q <= 32) {
+				const int srcl = (int)min(r * P.Q, 31u);
+				rsv = __shfl_sync(0xFFFFFFFFu, xv, srcl); rst = __shfl_sync(0xFFFFFFFFu, xt, srcl);
+			}
+			const uint64_t lv = carryV + xv - rsv;           // row-local prefix in front of this quad
+			if (valid) {
+				uint64_t *pw = P.wpreV + (uint64_t)lr * P.WP + 4 * q;
+				*reinterpret_cast<ulonglong2 *>(pw) = make_ulonglong2(lv, lv + e1);
+				*reinterpret_cast<ulonglong2 *>(pw + 2) = make_ulonglong2(lv + e2, lv + e3);
+				if (q == P.Q - 1) {
+					const uint64_t rowV = lv + tv, rowT = carryT + it - rst;
+					pw[4] = rowV;
+					s_row[0][wid * P.G + r] = sumV(rowV);
+					s_row[1][wid * P.G + r] = (uint32_t)rowT;
+					s_row[2][wid * P.G + r] = (uint32_t)(rowT >> 32);
+				}
+			}
+			if (P.Q > 32) { carryV += __shfl_sync(0xFFFFFFFFu, iv, 31); carryT += __shfl_sync(0xFFFFFFFFu, it, 31); }
 		}
 		__syncthreads();
-		const uint64_t eV = s_excl[0], eT = s_excl[1], eC = s_excl[2];
-		if (threadIdx.x < P.R && row0 + threadIdx.x < P.Lrows) {
-			const uint32_t lr = row0 + threadIdx.x;
-			const uint64_t rsV = P.R > 1 ? s_preV[threadIdx.x * P.W] : 0ull, rsT = P.R > 1 ? s_preT[threadIdx.x * P.W] : 0ull;
-			const uint64_t bv = eV + sumV(rsV);
-			P.rowBV[lr] = (uint32_t)bv;
-			P.rowBT[lr] = (uint32_t)(eT + (rsT & 0xFFFFFFFFull));
-			P.rowBC[lr] = (uint32_t)(eC + (rsT >> 32));
-			if (lr == owned_end_row) P.totals->nShared = (uint32_t)bv;
+		// CTA-relative row bases
+		{
+			const uint32_t t = threadIdx.x;
+			uint64_t a = (uint64_t)s_row[0][t] | ((uint64_t)s_row[2][t] << 32), b = s_row[1][t], ta, tb2;
+			block_exscan2(a, b, ta, tb2, s_w);
+			const uint32_t lr = blk * RB + t;
+			if (t < RB && lr < P.Lrows) {
+				P.rowBV[lr] = (uint32_t)a; P.rowBC[lr] = (uint32_t)(a >> 32); P.rowBT[lr] = (uint32_t)b;
+			}
+			if (t == 0) { blkSum[blk] = (uint32_t)ta; blkSum[nblk + blk] = (uint32_t)tb2; blkSum[2 * nblk + blk] = (uint32_t)(ta >> 32); }
 		}
-		if (batch == nbatch - 1 && threadIdx.x == 0) {
-			const uint64_t tv = eV + sumV(carryV), tt = eT + (carryT & 0xFFFFFFFFull), tc = eC + (carryT >> 32);
-			P.rowBV[P.Lrows] = (uint32_t)tv; P.rowBT[P.Lrows] = (uint32_t)tt; P.rowBC[P.Lrows] = (uint32_t)tc;
-			if (owned_end_row >= P.Lrows) P.totals->nShared = (uint32_t)tv;
-			P.totals->nCentre = (uint32_t)tc;
-			P.totals->nT = (uint32_t)tt;
-			P.totals->nSharedAll = (uint32_t)tv;
-			// 32-bit index range check (include/marching_cubes_33.h:140 uses unsigned int)
-			P.totals->range = (tv + tc >= 0xFFFFFFFFull || tt >= 0xFFFFFFFFull) ? 1u : 0u;
-		}
-		__syncthreads();
 	}
 }
 
 // ---------------------------------------------------------------------------
-// K3: vertices.  A tile = R consecutive point rows; its vertices are the id range
-// [rowBV[first row], rowBV[last row + 1]).  Pass 1: one thread per (row, word)
-// that owns vertices (known from the word prefixes without touching the bitmaps)
-// recomputes its plane masks and drops one task per vertex into the shared-memory
-// list at slot id - window start.  Pass 2: thread t computes vertex
-// window start + t, so consecutive threads write consecutive V / N / color
-// entries.  Tiles with more vertices than the list holds take several windows.
-// task word: x | plane << 16 | is_point << 18 | (row in tile) << 19
+// K2b: row scan.  Thread t of CTA j owns k_count block 256j + t: the CTA first
+// sums every earlier block (at most a few thousand values), scans its own 256,
+// and turns the CTA-relative row bases into slab-local ones: the implicit running
+// M->nV++ / nT++ of the reference (marching_cubes_33.c:487, :1245).
 // ---------------------------------------------------------------------------
-#define VCAP 2048
+__global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32_t RB, const uint32_t *blkSum, uint32_t owned_end_row)
+{
+	__shared__ uint64_t s_w[2][8];
+	__shared__ uint64_t s_base[3][256];
+	const uint32_t b0 = blockIdx.x * 256, me = b0 + threadIdx.x;
+	uint64_t aV = 0, aT = 0, aC = 0;
+	for (uint32_t i = threadIdx.x; i < b0; i += 256) { aV += blkSum[i]; aT += blkSum[nblk + i]; aC += blkSum[2 * nblk + i]; }
+	uint64_t mV = me < nblk ? blkSum[me] : 0, mT = me < nblk ? blkSum[nblk + me] : 0, mC = me < nblk ? blkSum[2 * nblk + me] : 0;
+	uint64_t preV, preT, preC, dummy, totV, totT, totC;
+	block_exscan2(aV, aT, preV, preT, s_w);              // totals = sums over all earlier blocks
+	block_exscan2(aC, mV, preC, totV, s_w);              // mV becomes this block's exclusive prefix within the CTA
+	block_exscan2(mT, mC, totT, totC, s_w);
+	(void)dummy;
+	const uint64_t bV = preV + mV, bT = preT + mT, bC = preC + mC;
+	s_base[0][threadIdx.x] = bV; s_base[1][threadIdx.x] = bT; s_base[2][threadIdx.x] = bC;
+	__syncthreads();
+	const uint64_t rows0 = (uint64_t)b0 * RB;
+	for (uint32_t i = threadIdx.x; i < 256 * RB; i += 256) {
+		const uint64_t lr = rows0 + i;
+		if (lr >= P.Lrows) break;
+		const uint32_t bl = i / RB;
+		const uint32_t v = P.rowBV[lr] + (uint32_t)s_base[0][bl];
+		P.rowBV[lr] = v;
+		P.rowBT[lr] += (uint32_t)s_base[1][bl];
+		P.rowBC[lr] += (uint32_t)s_base[2][bl];
+		if (lr == owned_end_row) P.totals->nShared = v;
+	}
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+		const uint64_t tv = preV + totV, tt = preT + totT, tc = preC + totC;
+		P.rowBV[P.Lrows] = (uint32_t)tv; P.rowBT[P.Lrows] = (uint32_t)tt; P.rowBC[P.Lrows] = (uint32_t)tc;
+		if (owned_end_row >= P.Lrows) P.totals->nShared = (uint32_t)tv;
+		P.totals->nCentre = (uint32_t)tc;
+		P.totals->nT = (uint32_t)tt;
+		P.totals->nSharedAll = (uint32_t)tv;
+		// 32-bit index range check (include/marching_cubes_33.h:140 uses unsigned int)
+		P.totals->range = (tv + tc >= 0xFFFFFFFFull || tt >= 0xFFFFFFFFull) ? 1u : 0u;
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K3: emit.  Warp-synchronous, one warp per group of G rows, no block barrier:
+//
+// vertices  the group's vertices are the id range [rowBV[first row], rowBV[last+1]).
+//           Fill: a lane whose quad owns vertices (known from the word prefixes)
+//           recomputes its plane masks and drops one task per vertex into the
+//           warp's queue at slot id - window start.  Drain: lane t computes vertex
+//           window start + t, so consecutive lanes write consecutive V / N / color.
+//           task word: x | plane << 16 | is_point << 18 | (row in group) << 19
+// cells     Fill: the active cells are compacted in sweep order (shuffle scan of
+//           the popcounts).  Drain: one lane per ACTIVE CELL picks the MC33 pattern,
+//           builds the eight (plane mask, first id) pairs its vertex ids are read
+//           from, and after a shuffle scan of the triangle counts writes its
+//           triangles (and centre vertex) at the ids the reference's sweep order
+//           gives them.
+// Groups with more vertices / cells than a queue holds take several windows.
+// ---------------------------------------------------------------------------
+#define EM_WARPS 8
+#define VQ 256
+#define CQ 256
+#define EM_SMEM (TBL_BYTES + EM_WARPS * (VQ * 4 + CQ * 4 + 16 * 32 * 4))
 
 template <typename Sample>
-__global__ void __launch_bounds__(256) k_emit_vertices(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ntiles)
+__global__ void __launch_bounds__(256) k_emit(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
-	__shared__ uint32_t vlist[VCAP];
+	extern __shared__ __align__(128) unsigned char smem[];
+	const Tables tb = load_tables(smem);
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t *vq = (uint32_t *)(smem + TBL_BYTES) + wid * VQ;
+	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * VQ + wid * CQ;
+	uint32_t *pm = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (VQ + CQ) + wid * 512;   // [8][32]
+	uint32_t *pb = pm + 256;                                                             // [8][32]
 	const bool gz = P.totals->anyZ != 0;
-	const uint32_t n = P.R * P.W;
-	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		const uint32_t lr0 = row_begin + tile * P.R, lrE = min(lr0 + P.R, row_end);
+	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
+	const uint32_t nShared = P.totals->nShared;
+	const uint32_t npass = (P.Q + 31) / 32;
+
+	for (uint32_t g = blockIdx.x * EM_WARPS + wid; g < ngroups; g += gridDim.x * EM_WARPS) {
+		const uint32_t lr0 = row_begin + g * P.G, lrE = min(lr0 + P.G, row_end);
+		// ======================= vertices =======================
 		const uint32_t vfirst = P.rowBV[lr0], vend = P.rowBV[lrE];
-		for (uint32_t win0 = vfirst; win0 < vend; win0 += VCAP) {
-			for (uint32_t it = threadIdx.x; it < n; it += 256) {
-				const uint32_t r = P.R > 1 ? fastdiv(it, P.W, P.mCW) : 0u, w = it - r * P.W, lr = lr0 + r;
-				if (lr >= lrE) continue;
-				const uint64_t *pv = P.wpreV + (uint64_t)lr * P.W1;
-				const uint64_t pre0 = pv[w], pre1 = pv[w + 1];
-				if (pre0 == pre1) continue;
-				const uint64_t tot = pv[P.W];
-				uint32_t id[3], cnt[3];
-				id[0] = P.rowBV[lr] + fldV(pre0, 0);
-				id[1] = P.rowBV[lr] + fldV(tot, 0) + fldV(pre0, 1);
-				id[2] = P.rowBV[lr] + fldV(tot, 0) + fldV(tot, 1) + fldV(pre0, 2);
-				bool hit = false;
-#pragma unroll
-				for (int a = 0; a < 3; a++) {
-					cnt[a] = fldV(pre1, a) - fldV(pre0, a);
-					hit = hit || (cnt[a] && id[a] < win0 + VCAP && id[a] + cnt[a] > win0);
+		for (uint32_t win0 = vfirst; win0 < vend; win0 += VQ) {
+			for (uint32_t pass = 0; pass < npass; pass++) {
+				uint32_t r, q;
+				lane_item(P, lane, pass, r, q);
+				const uint32_t lr = lr0 + r;
+				if (!(r < P.G && q < P.Q && lr < lrE)) continue;
+				const uint64_t *pw = P.wpreV + (uint64_t)lr * P.WP + 4 * q;
+				const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(pw), pc = *reinterpret_cast<const ulonglong2 *>(pw + 2);
+				const uint64_t p4 = pw[4];
+				if (p4 == pa.x) continue;                    // no vertex in this quad
+				const uint64_t tot = P.wpreV[(uint64_t)lr * P.WP + 4 * P.Q];
+				const uint32_t bX = P.rowBV[lr], bY = bX + fldV(tot, 0), bZ = bY + fldV(tot, 1);
+				{
+					// does any of the quad's three id ranges meet the window?
+					const uint32_t wl = win0, wh = win0 + VQ;
+					const uint32_t x0 = bX + fldV(pa.x, 0), x1 = bX + fldV(p4, 0);
+					const uint32_t y0 = bY + fldV(pa.x, 1), y1 = bY + fldV(p4, 1);
+					const uint32_t z0 = bZ + fldV(pa.x, 2), z1 = bZ + fldV(p4, 2);
+					if (!((x1 > x0 && x0 < wh && x1 > wl) || (y1 > y0 && y0 < wh && y1 > wl) || (z1 > z0 && z0 < wh && z1 > wl))) continue;
 				}
-				if (!hit) continue;
 				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
-				WordRec rec; CellWords cw;
-				word_masks(P, z, y, w, gz, rec, cw);
-				const uint32_t zw = (gz && P.rowZ[lr]) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
+				Quad q00, q10, q01;
+				if (!gz) {
+					const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
+					q00 = load_quad(P.S, i00);
+					q10 = y < P.ny ? load_quad(P.S, i00 + P.WP) : q00;
+					q01 = z < P.nz ? load_quad(P.S, i00 + (uint64_t)P.NY * P.WP) : q00;
+				}
+				const bool zrow = gz && P.rowZ[lr];
+				const uint64_t pk[4] = {pa.x, pa.y, pc.x, pc.y};
 #pragma unroll
-				for (int a = 0; a < 3; a++) {
-					uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
-					uint32_t slot = id[a] - win0;
-					while (m) {
-						const int b = __ffs((int)m) - 1;
-						m &= m - 1;
-						if (slot < VCAP)
-							vlist[slot] = ((w << 5) + b) | ((uint32_t)a << 16) | ((a == 0 ? (zw >> b) & 1u : 0u) << 18) | (r << 19);
-						slot++;
+				for (int k = 0; k < 4; k++) {
+					const uint32_t w = 4 * q + k;
+					WordRec rec;
+					if (!gz) {
+						uint32_t c[8];
+						quad_word(P, q00, q10, q01, q10, k, w, false, rec, c);
+					} else {
+						CellWords cw;
+						if (w < P.W) word_masks(P, z, y, w, true, rec, cw); else { rec.X = rec.Y = rec.Z = 0; }
+					}
+					const uint32_t zw = (zrow && w < P.W) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
+#pragma unroll
+					for (int a = 0; a < 3; a++) {
+						uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
+						uint32_t slot = (a == 0 ? bX : (a == 1 ? bY : bZ)) + fldV(pk[k], a) - win0;
+						while (m) {
+							const int b = __ffs((int)m) - 1;
+							m &= m - 1;
+							if (slot < VQ)
+								vq[slot] = ((w << 5) + b) | ((uint32_t)a << 16) | ((a == 0 ? (zw >> b) & 1u : 0u) << 18) | (r << 19);
+							slot++;
+						}
 					}
 				}
 			}
-			__syncthreads();
-			const uint32_t nt = min((uint32_t)VCAP, vend - win0);
-			for (uint32_t t = threadIdx.x; t < nt; t += 256) {
-				const uint32_t e = vlist[t];
+			__syncwarp();
+			const uint32_t nt = min((uint32_t)VQ, vend - win0);
+			for (uint32_t t = lane; t < nt; t += 32) {
+				const uint32_t e = vq[t];
 				const uint32_t lr = lr0 + (e >> 19);
 				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
 				emit_vertex_task<Sample>(P, e & 0xFFFFu, y, z, (int)((e >> 16) & 3u), ((e >> 18) & 1u) != 0, win0 + t);
 			}
-			__syncthreads();
+			__syncwarp();
 		}
-	}
-}
-
-// ---------------------------------------------------------------------------
-// K4: triangles (+ centre vertices).  A tile = R cell rows (or a 256-word piece
-// of one long row); its triangles are a contiguous id range.  Pass 1: a thread
-// whose word has active cells builds the eight (plane mask, first id) pairs its
-// cells' vertex ids are read from, walks the cells, picks each cell's MC33
-// pattern and drops one task per triangle into the list.  Pass 2: thread t writes
-// triangle window start + t: 12 consecutive bytes per thread.
-// task word: item | bit << 8 | (table word index) << 13 | m << 25 | (centre ordinal) << 26; bit 31 = skip
-// (cells with on-iso corners emit in pass 1: the zero-area drop is order dependent)
-// ---------------------------------------------------------------------------
-#define TCAP 4096
-#define TSKIP 0x80000000u
-#define EMT_SMEM (TBL_BYTES + 17 * 256 * 4 + TCAP * 4)
-
-template <typename Sample>
-__global__ void __launch_bounds__(256) k_emit_triangles(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ntiles, uint32_t nchunk)
-{
-	extern __shared__ __align__(128) unsigned char smem[];
-	const Tables tb = load_tables(smem);
-	uint32_t *pmask = (uint32_t *)(smem + TBL_BYTES);        // [8][256]
-	uint32_t *pbase = pmask + 8 * 256;                       // [8][256]
-	uint32_t *cbase = pbase + 8 * 256;                       // [256] global id of the word's first centre vertex
-	uint32_t *tlist = cbase + 256;                           // [TCAP]
-	const bool gz = P.totals->anyZ != 0;
-	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
-	const uint32_t nShared = P.totals->nShared;
-	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		const uint32_t rb = tile / nchunk, ch = tile - rb * nchunk;
-		const uint32_t lr0 = row_begin + rb * P.R, lrE = min(lr0 + P.R, row_end), w0 = ch * P.CW;
-		uint32_t tfirst, tend;
-		if (nchunk == 1) { tfirst = P.rowBT[lr0]; tend = P.rowBT[lrE]; }
-		else {
-			const uint64_t *pt = P.wpreT + (uint64_t)lr0 * P.W1;
-			tfirst = P.rowBT[lr0] + (uint32_t)pt[w0];
-			tend = P.rowBT[lr0] + (uint32_t)pt[min(w0 + P.CW, P.W)];
-		}
-		// item of this thread
-		const uint32_t r = P.R > 1 ? fastdiv(threadIdx.x, P.CW, P.mCW) : 0u, wl = threadIdx.x - r * P.CW;
-		const uint32_t w = w0 + wl, lr = lr0 + r;
-		const bool valid = r < P.R && lr < lrE && w < P.WC;
-		uint64_t pre0 = 0, pre1 = 0;
-		uint32_t t0 = 0, y = 0, z = 0;
-		if (valid) {
-			const uint64_t *pt = P.wpreT + (uint64_t)lr * P.W1;
-			pre0 = pt[w]; pre1 = pt[w + 1];
-			t0 = P.rowBT[lr] + (uint32_t)pre0;
-			const uint32_t zl = fastdiv(lr, P.NY, P.mNY);
-			y = lr - zl * P.NY; z = zl + P.zlo;
-		}
-		const uint32_t t1 = t0 + (uint32_t)(pre1 - pre0);
-		for (uint32_t win0 = tfirst; win0 == tfirst || win0 < tend; win0 += TCAP) {
-			const uint32_t win1 = win0 + TCAP;
-			const bool last = win1 >= tend;
-			if (pre0 != pre1 && (t0 < win1 || last) && t1 >= win0) {
-				WordRec rec; CellWords cw; CellPairs cp;
-				word_masks(P, z, y, w, gz, rec, cw);
-				cell_pairs(P, z, y, w, gz, rec, cp);
+		// ======================= cells =======================
+		const uint32_t tbase = P.rowBT[lr0], cloc0 = nShared + P.rowBC[lr0];
+		uint32_t runT = 0, runC = 0;                             // triangles / centres of the group so far
+		for (uint32_t pass = 0; pass < npass; pass++) {
+			uint32_t r, q;
+			lane_item(P, lane, pass, r, q);
+			uint32_t act0 = 0, act1 = 0, act2 = 0, act3 = 0;
+			{
+				const uint32_t lr = lr0 + r;
+				if (r < P.G && q < P.Q && lr < lrE) {
+					const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+					if (row_cells_owned(P, z, y)) {
+						uint32_t act[4] = {0, 0, 0, 0};
+						if (!gz) {
+							const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q, dZ = (uint64_t)P.NY * P.WP;
+							const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + P.WP);
+							const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + P.WP + dZ);
 #pragma unroll
-				for (int k = 0; k < 8; k++) { pmask[k * 256 + threadIdx.x] = cp.mask[k]; pbase[k * 256 + threadIdx.x] = cp.base[k]; }
-				const uint32_t cloc = nShared + P.rowBC[lr] + (uint32_t)(pre0 >> 32);   // slab-local id of the word's first centre
-				cbase[threadIdx.x] = vb + cloc;
-				uint32_t act = rec.act, tid = t0, cord = 0;
-				while (act) {
-					const int b = __ffs((int)act) - 1;
-					act &= act - 1;
-					const unsigned idx = cell_index(cw.c, 1, b);
-					const unsigned zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
-					const uint32_t x = (w << 5) + b;
-					const CellPattern pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
-					const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
-					const bool mine = (tid >= win0 && tid < win1) || (last && tid >= win1);   // the window that owns this cell
-					if (pat.centre && mine) {
-						const uint32_t cl = cloc + cord;
-						if (cl < P.capV) {
-							emit_centre_vertex<Sample>(P, x, y, z, cl);
-							if (P.vkey) P.vkey[cl] = cell * 4 + 3;
+							for (int k = 0; k < 4; k++) {
+								WordRec rec;
+								uint32_t c[8];
+								quad_word(P, q00, q10, q01, q11, k, 4 * q + k, true, rec, c);
+								act[k] = rec.act;
+							}
 						} else {
-							P.totals->overflow = 1;
+#pragma unroll
+							for (int k = 0; k < 4; k++) {
+								if (4 * q + k < P.WC) {
+									WordRec rec; CellWords cw;
+									word_masks(P, z, y, 4 * q + k, true, rec, cw);
+									act[k] = rec.act;
+								}
+							}
+						}
+						act0 = act[0]; act1 = act[1]; act2 = act[2]; act3 = act[3];
+					}
+				}
+			}
+			const uint32_t na = (uint32_t)(__popc(act0) + __popc(act1) + __popc(act2) + __popc(act3));
+			uint32_t ia = na;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, ia, d);
+				if (lane >= (unsigned)d) ia += x;
+			}
+			const uint32_t pos0 = ia - na, ncp = __shfl_sync(0xFFFFFFFFu, ia, 31);
+			for (uint32_t cw0 = 0; cw0 < ncp; cw0 += CQ) {
+				// fill: cells cw0 .. cw0+CQ-1 of this pass, in sweep order
+				if (na && pos0 < cw0 + CQ && pos0 + na > cw0) {
+					uint32_t slot = pos0 - cw0;
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						uint32_t m = k == 0 ? act0 : (k == 1 ? act1 : (k == 2 ? act2 : act3));
+						while (m) {
+							const int b = __ffs((int)m) - 1;
+							m &= m - 1;
+							if (slot < CQ) cq[slot] = (((4 * q + k) << 5) + b) | (r << 16);
+							slot++;
 						}
 					}
-					if (zm) {
-						// (the pairs are read back from shared memory: indexing the register copy
-						// dynamically would push it to local memory for every thread)
-						const uint32_t kept = emit_cell_triangles_z(P, tb, (unsigned)b, pat, zm, vb + cloc + cord, pmask + threadIdx.x,
-						                                            pbase + threadIdx.x, 256, tid, win0, win1, cell);
-						for (uint32_t j = 0; j < kept; j++)
-							if (tid + j - win0 < TCAP) tlist[tid + j - win0] = TSKIP;
-						tid += kept;
-					} else {
-						const uint32_t e = threadIdx.x | ((uint32_t)b << 8) | (pat.m << 25) | (cord << 26);
-						for (uint32_t j = 0; j < pat.ntri; j++)
-							if (tid + j - win0 < TCAP) tlist[tid + j - win0] = e | ((pat.start + j) << 13);
-						tid += pat.ntri;
+				}
+				__syncwarp();
+				const uint32_t ncw = min((uint32_t)CQ, ncp - cw0);
+				for (uint32_t j0 = 0; j0 < ncw; j0 += 32) {
+					const bool on = j0 + lane < ncw;
+					CellPattern pat;
+					pat.start = 0; pat.m = 0; pat.ntri = 0; pat.centre = 0;
+					unsigned zm = 0, b = 0;
+					uint32_t x = 0, y = 0, z = 0;
+					if (on) {
+						const uint32_t e = cq[j0 + lane];
+						x = e & 0xFFFFu; b = x & 31u;
+						const uint32_t lr = lr0 + (e >> 16);
+						const uint32_t zl = fastdiv(lr, P.NY, P.mNY);
+						y = lr - zl * P.NY; z = zl + P.zlo;
+						WordRec rec; CellWords cw; CellPairs cp;
+						word_masks(P, z, y, x >> 5, gz, rec, cw);
+						cell_pairs(P, z, y, x >> 5, gz, rec, cw, cp);
+#pragma unroll
+						for (int k = 0; k < 8; k++) { pm[k * 32 + lane] = cp.mask[k]; pb[k * 32 + lane] = cp.base[k]; }
+						const unsigned idx = cell_index(cw.c, 1, (int)b);
+						zm = cw.zany ? cell_zmask(cw.zc, 1, (int)b) : 0u;
+						pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
 					}
-					cord += pat.centre;
+					// triangle / centre offsets: shuffle scan in sweep order
+					const uint32_t v = pat.ntri | (pat.centre << 16);
+					uint32_t iv = v;
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						const uint32_t xs = __shfl_up_sync(0xFFFFFFFFu, iv, d);
+						if (lane >= (unsigned)d) iv += xs;
+					}
+					const uint32_t ex = iv - v, tot = __shfl_sync(0xFFFFFFFFu, iv, 31);
+					if (on) {
+						const uint32_t tid = tbase + runT + (ex & 0xFFFFu), cl = cloc0 + runC + (ex >> 16);
+						const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
+						if (pat.centre) {
+							if (cl < P.capV) {
+								emit_centre_vertex<Sample>(P, x, y, z, cl);
+								if (P.vkey) P.vkey[cl] = cell * 4 + 3;
+							} else {
+								P.totals->overflow = 1;
+							}
+						}
+						if (zm) {
+							emit_cell_triangles_z(P, tb, b, pat, zm, vb + cl, pm + lane, pb + lane, 32, tid, 0u, 0xFFFFFFFFu, cell);
+						} else {
+							for (uint32_t j = 0; j < pat.ntri; j++)
+								emit_triangle_task(P, tb.tri[pat.start + j], b, pat.m, vb + cl, pm + lane, pb + lane, 32, tid + j, cell);
+						}
+					}
+					runT += tot & 0xFFFFu; runC += tot >> 16;
 				}
+				__syncwarp();
 			}
-			__syncthreads();
-			const uint32_t nt = tend > win0 ? min((uint32_t)TCAP, tend - win0) : 0u;
-			for (uint32_t t = threadIdx.x; t < nt; t += 256) {
-				const uint32_t e = tlist[t];
-				if (e & TSKIP) continue;
-				const uint32_t item = e & 255u, b = (e >> 8) & 31u;
-				uint64_t cell = 0;
-				if (P.tcell) {
-					const uint32_t ir = P.R > 1 ? fastdiv(item, P.CW, P.mCW) : 0u, iw = w0 + item - ir * P.CW, ilr = lr0 + ir;
-					const uint32_t izl = fastdiv(ilr, P.NY, P.mNY);
-					cell = ((uint64_t)(izl + P.zlo) * P.ny + (ilr - izl * P.NY)) * P.nx + (iw << 5) + b;
-				}
-				emit_triangle_task(P, tb.tri[(e >> 13) & 0xFFFu], b, (e >> 25) & 1u, cbase[item] + ((e >> 26) & 31u),
-				                   pmask + item, pbase + item, 256, win0 + t, cell);
-			}
-			__syncthreads();
 		}
 	}
 }
@@ -647,9 +722,8 @@ struct mc33cu_ctx {
 	uint64_t n_samples;
 	void *grid_owned;        // device copy made by the upload calls
 	void *pinned; size_t pinned_bytes;   // staging for row-wise uploads
-	// scan state
-	uint64_t *scan_status; uint32_t *scan_ticket; uint32_t nbatch, epoch;
-	uint32_t nchunk;         // 256-word pieces per row in the triangle kernel
+	// k_count blocks (CNT_WARPS * G rows each) and their (V, T, C) sums
+	uint32_t *blk_sum; uint32_t nblk;
 	// host mirror of totals
 	Totals *h_totals;
 	bool counted;
@@ -693,9 +767,9 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	Params &P = c->P;
-	cudaFree(P.S); cudaFree(P.Z); cudaFree(P.rowZ); cudaFree(P.wpreV); cudaFree(P.wpreT);
+	cudaFree(P.S); cudaFree(P.Z); cudaFree(P.rowZ); cudaFree(P.wpreV);
 	cudaFree(P.rowBV); cudaFree(P.totals);
-	cudaFree(c->scan_status);
+	cudaFree(c->blk_sum);
 	cudaFree(c->grid_owned);
 	cudaFree(c->oV); cudaFree(c->oN); cudaFree(c->oC); cudaFree(c->oT);
 	if (c->pinned) cudaFreeHost(c->pinned);
@@ -710,7 +784,7 @@ static int set_geom(mc33cu_ctx *c, const mc33cu_desc *d);
 template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 {
 	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES)));
-	CU(cudaFuncSetAttribute(k_emit_triangles<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMT_SMEM));
+	CU(cudaFuncSetAttribute(k_emit<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM));
 	return MC33CU_OK;
 }
 
@@ -750,33 +824,33 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	P.pz0 = d->cell_z0; P.pz1 = d->is_last ? NZ : d->cell_z1;
 	P.hz = d->is_last ? 0xFFFFFFFFu : d->cell_z1;
 	P.W = (P.NX + 31) / 32; P.WC = (P.nx + 31) / 32;
-	P.WP = (P.W + 1 + 3) & ~3u;
-	P.W1 = P.W + 1;
+	P.Q = (P.W + 3) / 4;
+	P.WP = 4 * P.Q + 4;
+	P.G = P.Q <= 32 ? 32 / P.Q : 1;
 	P.Lrows = (P.zhi - P.zlo) * P.NY;
 	if (P.NX > 65535) { free(c); return fail(MC33CU_ERR_ARG, "rows longer than 65535 samples are not supported"); }
 	if ((uint64_t)(P.zhi - P.zlo) * P.NY > 0x7FFFFFFFull / P.WP) { free(c); return fail(MC33CU_ERR_ARG, "too many rows"); }
-	P.R = P.W >= 256 ? 1 : 256 / P.W;
-	P.CW = P.W < 256 ? P.W : 256;
-	P.mCW = P.CW >= 2 ? (uint32_t)(0x100000000ull / P.CW) : 0u;
+	P.mQ = P.Q >= 2 ? (uint32_t)(0x100000000ull / P.Q) : 0u;
 	P.mNY = (uint32_t)(0x100000000ull / P.NY);
-	c->nchunk = (P.W + P.CW - 1) / P.CW;
 	set_geom(c, d);
 	static const size_t ssz[5] = {4, 8, 1, 2, 4};
 	c->sample_size = ssz[d->dtype];
 	c->real_size = d->dtype == MC33CU_F64 ? 8 : 4;
 	c->n_samples = (uint64_t)P.Lrows * P.NX;
-	c->nbatch = (P.Lrows + P.R - 1) / P.R;
+	c->nblk = (P.Lrows + CNT_WARPS * P.G - 1) / (CNT_WARPS * P.G);
 	{
-		// classify chunks: ~16 KB of whole rows, or 16 KB pieces of one long row
+		// classify chunks: ~16 KB of whole rows (a multiple of the CTA's warp count
+		// when possible), or 16 KB pieces of one long row (a multiple of 4 words)
 		ClsPlan &pl = c->cls;
-		const size_t rowb = (size_t)P.NX * c->sample_size, target = 16384;
+		const size_t rowb = (size_t)P.NX * c->sample_size, target = 16384 + 512;
 		if (rowb <= target) {
 			pl.rows = (uint32_t)(target / rowb); pl.words = P.W; pl.nwchunk = 1;
+			if (pl.rows > CLS_THREADS / 32) pl.rows -= pl.rows % (CLS_THREADS / 32);
 			if (pl.rows > P.Lrows) pl.rows = P.Lrows;
 			pl.nchunks = (P.Lrows + pl.rows - 1) / pl.rows;
 			pl.stage_bytes = (uint32_t)(((size_t)pl.rows * rowb + 32 + 127) & ~(size_t)127);
 		} else {
-			pl.rows = 1; pl.words = (uint32_t)(target / (32 * c->sample_size));
+			pl.rows = 1; pl.words = (uint32_t)(16384 / (32 * c->sample_size));
 			pl.nwchunk = (P.W + pl.words - 1) / pl.words;
 			pl.nchunks = P.Lrows * pl.nwchunk;
 			pl.stage_bytes = (uint32_t)(((size_t)pl.words * 32 * c->sample_size + 32 + 127) & ~(size_t)127);
@@ -801,22 +875,13 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	TRYCU(cudaMemsetAsync(P.S, 0, bm * 4, c->stream)); TRYCU(cudaMemsetAsync(P.Z, 0, bm * 4, c->stream));
 	TRY(dalloc(&P.rowZ, (size_t)P.Lrows));
 	TRYCU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows, c->stream));
-	TRY(dalloc(&P.wpreV, (size_t)P.Lrows * P.W1)); TRY(dalloc(&P.wpreT, (size_t)P.Lrows * P.W1));
-	TRYCU(cudaMemsetAsync(P.wpreV, 0, (size_t)P.Lrows * P.W1 * 8, c->stream));
-	TRYCU(cudaMemsetAsync(P.wpreT, 0, (size_t)P.Lrows * P.W1 * 8, c->stream));
+	TRY(dalloc(&P.wpreV, (size_t)P.Lrows * P.WP));
+	TRYCU(cudaMemsetAsync(P.wpreV, 0, (size_t)P.Lrows * P.WP * 8, c->stream));
 	TRY(dalloc(&P.rowBV, ((size_t)P.Lrows + 1) * 3));
 	P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
-	{
-		// Totals (32 bytes) and the batch ticket share one block so that a single
-		// small memset re-arms both before every extraction
-		unsigned char *blk;
-		TRY(dalloc(&blk, 64));
-		P.totals = (Totals *)blk;
-		c->scan_ticket = (uint32_t *)(blk + sizeof(Totals));
-		TRYCU(cudaMemsetAsync(blk, 0, 64, c->stream));
-	}
-	TRY(dalloc(&c->scan_status, (size_t)c->nbatch * 3));
-	TRYCU(cudaMemsetAsync(c->scan_status, 0, (size_t)c->nbatch * 3 * 8, c->stream));
+	TRY(dalloc(&P.totals, 1));
+	TRYCU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), c->stream));
+	TRY(dalloc(&c->blk_sum, (size_t)c->nblk * 3));
 	TRYCU(cudaMallocHost((void **)&c->h_totals, sizeof(Totals)));
 	for (int i = 0; i < 6; i++) TRYCU(cudaEventCreate(&c->ev[i]));
 	TRYCU(cudaStreamSynchronize(c->stream));
@@ -932,13 +997,13 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 {
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
-	// re-arm totals (incl. the overflow / on-iso flags) and the batch ticket
-	CU(cudaMemsetAsync(P.totals, 0, 64, s));
+	// re-arm the totals (overflow / on-iso flags)
+	CU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), s));
 	if (c->timing) CU(cudaEventRecord(c->ev[0], s));
 	{
 		const ClsPlan &pl = c->cls;
 		const size_t smem = (size_t)pl.stage_bytes * CLS_STAGES;
-		uint32_t per_sm = (uint32_t)((200u << 10) / (smem + 1024));
+		uint32_t per_sm = (uint32_t)((220u << 10) / (smem + 1024));
 		if (per_sm < 1) per_sm = 1;
 		if (per_sm > 8) per_sm = 8;
 		uint32_t grid = (uint32_t)c->n_sm * per_sm;
@@ -948,14 +1013,18 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
 	{
-		c->epoch++;
 		uint32_t grid = (uint32_t)c->n_sm * 8;
-		if (grid > c->nbatch) grid = c->nbatch;
-		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
-		k_count<Sample><<<grid, 256, TBL_BYTES, s>>>(P, c->scan_status, c->scan_ticket, c->nbatch, c->epoch, owned_end);
+		if (grid > c->nblk) grid = c->nblk;
+		k_count<Sample><<<grid, 256, TBL_BYTES, s>>>(P, c->nblk, c->blk_sum);
 		c->launches++;
 	}
-	if (c->timing) { CU(cudaEventRecord(c->ev[2], s)); CU(cudaEventRecord(c->ev[3], s)); }
+	if (c->timing) CU(cudaEventRecord(c->ev[2], s));
+	{
+		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
+		k_rowscan<<<(c->nblk + 255) / 256, 256, 0, s>>>(P, c->nblk, CNT_WARPS * P.G, c->blk_sum, owned_end);
+		c->launches++;
+	}
+	if (c->timing) CU(cudaEventRecord(c->ev[3], s));
 	CU(cudaGetLastError());
 	return MC33CU_OK;
 }
@@ -965,23 +1034,15 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
 	{
+		// rows whose vertices (pz0..pz1) and cells (cz0..cz1, a prefix of them) this slab owns
 		const uint32_t rb = (P.pz0 - P.zlo) * P.NY, re = (P.pz1 - P.zlo) * P.NY;
-		const uint32_t ntiles = (re - rb + P.R - 1) / P.R;
-		uint32_t grid = (uint32_t)c->n_sm * 8;
-		if (grid > ntiles) grid = ntiles;
-		k_emit_vertices<Sample><<<grid, 256, 0, s>>>(P, rb, re, ntiles);
-		c->launches++;
-	}
-	if (c->timing) CU(cudaEventRecord(c->ev[4], s));
-	{
-		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (P.cz1 - P.zlo) * P.NY;
-		const uint32_t ntiles = ((re - rb + P.R - 1) / P.R) * c->nchunk;
+		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
 		uint32_t grid = (uint32_t)c->n_sm * 5;
-		if (grid > ntiles) grid = ntiles;
-		k_emit_triangles<Sample><<<grid, 256, EMT_SMEM, s>>>(P, rb, re, ntiles, c->nchunk);
+		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
+		k_emit<Sample><<<grid, 256, EM_SMEM, s>>>(P, rb, re, ngroups);
 		c->launches++;
 	}
-	if (c->timing) { CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
+	if (c->timing) { CU(cudaEventRecord(c->ev[4], s)); CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
 	CU(cudaGetLastError());
 	return MC33CU_OK;
 }

@@ -46,7 +46,20 @@ static void run(Params &P, bool emit)
 		if (anyz) P.totals->anyZ = 1;
 	}
 	const bool gz = P.totals->anyZ != 0;
-	// K2: word prefixes, row bases
+	// per-word record of row (z,y): through the quad fast path when the grid has no
+	// on-iso sample (as the kernels do), else the generic bitmap walk
+	auto word_rec = [&](uint32_t z, uint32_t y, uint32_t w, WordRec &rec, CellWords &cw) {
+		if (gz) { word_masks(P, z, y, w, true, rec, cw); return; }
+		const uint32_t lr = (z - P.zlo) * P.NY + y, q = w >> 2;
+		const bool hasY = y < P.ny, hasZ = z < P.nz;
+		const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u, i00 = (uint64_t)lr * P.WP + 4 * q;
+		const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY), q01 = load_quad(P.S, i00 + dZ),
+		           q11 = load_quad(P.S, i00 + dY + dZ);
+		quad_word(P, q00, q10, q01, q11, (int)(w & 3), w, hasY && hasZ, rec, cw.c);
+		cw.zany = 0;
+		for (int k = 0; k < 8; k++) cw.zc[k] = 0;
+	};
+	// K2 + K2b: word prefixes, row bases
 	{
 		uint64_t bv = 0, bc = 0, bt = 0;
 		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
@@ -55,16 +68,20 @@ static void run(Params &P, bool emit)
 			const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
 			const bool own_c = row_cells_owned(P, z, y);
 			uint64_t av = 0, ac = 0;
-			for (uint32_t w = 0; w < P.W; w++) {
+			for (uint32_t w = 0; w < 4 * P.Q; w++) {
 				uint64_t cv = 0, cc = 0;
-				WordRec rec;
-				if (own_p || own_c) count_word<Sample>(P, tb, z, y, w, gz, own_p, own_c, rec, cv, cc);
-				P.wpreV[(uint64_t)lr * P.W1 + w] = av;
-				P.wpreT[(uint64_t)lr * P.W1 + w] = ac;
+				if ((own_p || own_c) && w < P.W) {
+					WordRec rec; CellWords cw;
+					word_rec(z, y, w, rec, cw);
+					if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
+					if (!own_c) rec.act = 0;
+					cv = pack_planes(rec);
+					cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
+				}
+				P.wpreV[(uint64_t)lr * P.WP + w] = av;
 				av += cv; ac += cc;
 			}
-			P.wpreV[(uint64_t)lr * P.W1 + P.W] = av;
-			P.wpreT[(uint64_t)lr * P.W1 + P.W] = ac;
+			P.wpreV[(uint64_t)lr * P.WP + 4 * P.Q] = av;
 			if (lr == owned_end) P.totals->nShared = (uint32_t)bv;
 			P.rowBV[lr] = (uint32_t)bv; P.rowBT[lr] = (uint32_t)bt; P.rowBC[lr] = (uint32_t)bc;
 			bv += fldV(av, 0) + fldV(av, 1) + fldV(av, 2); bt += ac & 0xFFFFFFFFu; bc += ac >> 32;
@@ -74,12 +91,12 @@ static void run(Params &P, bool emit)
 		P.totals->nCentre = (uint32_t)bc; P.totals->nT = (uint32_t)bt; P.totals->nSharedAll = (uint32_t)bv;
 	}
 	if (!emit) return;
-	// K3: vertices
+	// K3, vertices
 	for (uint32_t lr = (P.pz0 - P.zlo) * P.NY; lr < (P.pz1 - P.zlo) * P.NY; lr++) {
 		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
 		for (uint32_t w = 0; w < P.W; w++) {
 			WordRec rec; CellWords cw;
-			word_masks(P, z, y, w, gz, rec, cw);
+			word_rec(z, y, w, rec, cw);
 			const uint32_t zw = (gz && P.rowZ[lr]) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
 			for (int a = 0; a < 3; a++) {
 				uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
@@ -92,19 +109,20 @@ static void run(Params &P, bool emit)
 			}
 		}
 	}
-	// K4: triangles (+ centre vertices)
+	// K3, cells: triangles (+ centre vertices) in sweep order
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
 	for (uint32_t lr = (P.cz0 - P.zlo) * P.NY; lr < (P.cz1 - P.zlo) * P.NY; lr++) {
 		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
 		if (y >= P.ny) continue;
+		uint32_t tid = P.rowBT[lr], cl = P.totals->nShared + P.rowBC[lr];
 		for (uint32_t w = 0; w < P.WC; w++) {
-			const uint64_t pre0 = P.wpreT[(uint64_t)lr * P.W1 + w], pre1 = P.wpreT[(uint64_t)lr * P.W1 + w + 1];
-			if (pre0 == pre1) continue;
 			WordRec rec; CellWords cw; CellPairs cp;
+			word_rec(z, y, w, rec, cw);
+			uint32_t act = rec.act;
+			if (!act) continue;
+			// the drain side recomputes the word through the generic path
 			word_masks(P, z, y, w, gz, rec, cw);
-			cell_pairs(P, z, y, w, gz, rec, cp);
-			const uint32_t cloc = P.totals->nShared + P.rowBC[lr] + (uint32_t)(pre0 >> 32);
-			uint32_t act = rec.act, tid = P.rowBT[lr] + (uint32_t)pre0, cord = 0;
+			cell_pairs(P, z, y, w, gz, rec, cw, cp);
 			while (act) {
 				int b = ffs32(act);
 				act &= act - 1;
@@ -114,7 +132,6 @@ static void run(Params &P, bool emit)
 				const CellPattern cpat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
 				const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
 				if (cpat.centre) {
-					const uint32_t cl = cloc + cord;
 					if (cl < P.capV) {
 						emit_centre_vertex<Sample>(P, x, y, z, cl);
 						if (P.vkey) P.vkey[cl] = cell * 4 + 3;
@@ -123,15 +140,13 @@ static void run(Params &P, bool emit)
 					}
 				}
 				if (zm) {
-					tid += emit_cell_triangles_z(P, tb, (unsigned)b, cpat, zm, vb + cloc + cord, cp.mask, cp.base, 1, tid, 0u,
-					                             0xFFFFFFFFu, cell);
+					tid += emit_cell_triangles_z(P, tb, (unsigned)b, cpat, zm, vb + cl, cp.mask, cp.base, 1, tid, 0u, 0xFFFFFFFFu, cell);
 				} else {
 					for (uint32_t j = 0; j < cpat.ntri; j++)
-						emit_triangle_task(P, tb.tri[cpat.start + j], (unsigned)b, cpat.m, vb + cloc + cord, cp.mask, cp.base, 1,
-						                   tid + j, cell);
+						emit_triangle_task(P, tb.tri[cpat.start + j], (unsigned)b, cpat.m, vb + cl, cp.mask, cp.base, 1, tid + j, cell);
 					tid += cpat.ntri;
 				}
-				cord += cpat.centre;
+				cl += cpat.centre;
 			}
 		}
 	}
@@ -148,10 +163,10 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.zlo = d->z_lo; P.zhi = d->z_hi; P.cz0 = d->cell_z0; P.cz1 = d->cell_z1;
 	P.pz0 = d->cell_z0; P.pz1 = d->is_last ? NZ : d->cell_z1;
 	P.hz = d->is_last ? 0xFFFFFFFFu : d->cell_z1;
-	P.W = (P.NX + 31) / 32; P.WC = (P.nx + 31) / 32; P.WP = (P.W + 1 + 3) & ~3u; P.W1 = P.W + 1;
+	P.W = (P.NX + 31) / 32; P.WC = (P.nx + 31) / 32; P.Q = (P.W + 3) / 4; P.WP = 4 * P.Q + 4;
+	P.G = P.Q <= 32 ? 32 / P.Q : 1;
 	P.Lrows = (P.zhi - P.zlo) * P.NY;
-	P.R = P.W >= 256 ? 1 : 256 / P.W; P.CW = P.W < 256 ? P.W : 256;
-	P.mCW = P.CW >= 2 ? (uint32_t)(0x100000000ull / P.CW) : 0u; P.mNY = (uint32_t)(0x100000000ull / P.NY);
+	P.mQ = P.Q >= 2 ? (uint32_t)(0x100000000ull / P.Q) : 0u; P.mNY = (uint32_t)(0x100000000ull / P.NY);
 	P.geom.store = d->store; P.geom.normal_neg = d->normal_neg; P.geom.tsa = d->tsa;
 	for (int i = 0; i < 3; i++) { P.geom.O[i] = d->O[i]; P.geom.D[i] = d->D[i]; }
 	P.geom.ca = d->ca; P.geom.cb = d->cb;
@@ -159,10 +174,10 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.iso = d->dtype == MC33CU_F64 ? iso + 0.0 : (double)((float)iso + 0.0f);
 	std::vector<uint32_t> S((size_t)P.Lrows * P.WP, 0), Z((size_t)P.Lrows * P.WP, 0), rb(((size_t)P.Lrows + 1) * 3);
 	std::vector<uint8_t> rz(P.Lrows);
-	std::vector<uint64_t> wv((size_t)P.Lrows * P.W1), wc((size_t)P.Lrows * P.W1);
+	std::vector<uint64_t> wv((size_t)P.Lrows * P.WP);
 	Totals tot;
 	memset(&tot, 0, sizeof tot);
-	P.S = S.data(); P.Z = Z.data(); P.rowZ = rz.data(); P.wpreV = wv.data(); P.wpreT = wc.data();
+	P.S = S.data(); P.Z = Z.data(); P.rowZ = rz.data(); P.wpreV = wv.data();
 	P.rowBV = rb.data(); P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
 	P.totals = &tot;
 	bool emit = o != nullptr;
