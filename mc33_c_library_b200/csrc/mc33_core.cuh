@@ -145,8 +145,8 @@ struct Params {
 	uint32_t mQ, mNY;             // floor(2^32/Q), floor(2^32/NY) for fastdiv
 	uint32_t *S, *Z;              // bitmaps [Lrows][WP]; words >= W of a row are zero
 	uint8_t *rowZ;                // [Lrows] any Z bit in the row
-	uint64_t *wpreV;              // [Lrows][WP] row-local exclusive prefix X | Y<<21 | Z<<42 of the vertices in
-	                              // words < k; entries W..4Q hold the row totals
+	uint64_t *wpreV;              // [Lrows][WP] X | Y<<21 | Z<<42: row-local index of each plane's first vertex
+	                              // in word k (entries W..4Q: one past the plane's last vertex)
 	uint32_t *rowBV, *rowBT, *rowBC;   // [Lrows+1] slab-local exclusive bases: vertices, triangles, centres
 	Totals *totals;
 	double iso;
@@ -748,24 +748,25 @@ MC_HD bool row_points_halo(const Params &P, uint32_t z) { return z == P.hz; }
 MC_HD bool row_cells_owned(const Params &P, uint32_t z, uint32_t y) { return z >= P.cz0 && z < P.cz1 && y < P.ny; }
 
 // ---------------------------------------------------------------------------
-// vertex numbering.  wpreV[lr][w] packs the number of X / Y / Z plane vertices
-// of row lr in words < w (21 bits each), entry 4Q the row totals; rowBV[lr] is
-// the slab-local id of the row's first vertex.  Within a row: X plane by x,
-// then Y, then Z.  Vertex ARRAYS are indexed locally; triangle CONTENTS are
+// vertex numbering.  Within a row: X plane by x, then Y, then Z.  wpreV[lr][w]
+// packs, per plane (21 bits each), the row-local index of the plane's first
+// vertex in word w -- i.e. the vertices of that plane in words < w, plus the
+// totals of the planes in front of it; rowBV[lr] is the slab-local id of the
+// row's first vertex.  Vertex ARRAYS are indexed locally; triangle CONTENTS are
 // global ids (local + vbase).
 // ---------------------------------------------------------------------------
 MC_HD uint32_t fldV(uint64_t p, int pl) { return (uint32_t)(p >> (21 * pl)) & 0x1FFFFFu; }
 
 MC_HD uint32_t plane_base_local(const Params &P, uint32_t lr, uint32_t w, int pl)
 {
-	const uint64_t *row = P.wpreV + (uint64_t)lr * P.WP;
-	uint32_t b = P.rowBV[lr] + fldV(row[w], pl);
-	if (pl) {
-		const uint64_t tot = row[4 * P.Q];
-		b += fldV(tot, 0);
-		if (pl == 2) b += fldV(tot, 1);
-	}
-	return b;
+	return P.rowBV[lr] + fldV(P.wpreV[(uint64_t)lr * P.WP + w], pl);
+}
+
+// what the count kernel adds to every prefix of a row whose plane totals are tot:
+// the Y plane starts after the X plane, the Z plane after both
+MC_HD uint64_t plane_offsets(uint64_t tot)
+{
+	return ((uint64_t)fldV(tot, 0) << 21) | ((uint64_t)(fldV(tot, 0) + fldV(tot, 1)) << 42);
 }
 MC_HD uint32_t local_to_global(const Params &P, uint32_t z, uint32_t local)
 {
@@ -829,6 +830,70 @@ MC_HDN void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool
 	cp.mask[7] = r11.X;   cp.base[7] = local_to_global(P, z + 1, plane_base_local(P, l11, w, 0));
 }
 
+MC_HD void write_triangle(const Params &P, uint32_t tid, const uint32_t *ti, unsigned m, uint64_t cell)
+{
+	if (tid >= P.capT) { P.totals->overflow = 1; return; }
+	// winding: marching_cubes_33.c:1246-1250 (ti[0] = nibble 2, ti[1] = nibble 1, ti[2] = nibble 0)
+	uint32_t a0 = m ? ti[0] : ti[1], a1 = m ? ti[1] : ti[0];
+	if (P.geom.normal_neg) { uint32_t t = a0; a0 = a1; a1 = t; }
+	uint32_t *T = P.T + 3 * (uint64_t)tid;
+	T[0] = a0; T[1] = a1; T[2] = ti[2];
+	if (P.tcell) P.tcell[tid] = cell;
+}
+
+// ---------------------------------------------------------------------------
+// Fast path for a cell of a grid WITHOUT on-iso samples: the 8-bit case index and
+// the global ids of the vertices on its 12 edges, straight from the sign bitmap,
+// the word prefixes and the row bases.  Every edge is evaluated (no dependence on
+// the pattern), ids of edges that carry no vertex are meaningless and never read.
+// g0 / g1: what turns a slab-local id of slice z / z+1 into a global one.
+// ---------------------------------------------------------------------------
+MC_HDN unsigned cell_fast(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t g0, uint32_t g1, uint32_t *id)
+{
+	const uint32_t w = x >> 5, b = x & 31u;
+	const uint32_t l00 = (z - P.zlo) * P.NY + y, l10 = l00 + 1, l01 = l00 + P.NY, l11 = l01 + 1;
+	const uint64_t i00 = (uint64_t)l00 * P.WP + w, i10 = i00 + P.WP, i01 = (uint64_t)l01 * P.WP + w, i11 = i01 + P.WP;
+	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
+	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
+	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
+	const uint64_t p00 = P.wpreV[i00], p10 = P.wpreV[i10], p01 = P.wpreV[i01], p11 = P.wpreV[i11];
+	const uint32_t r00 = P.rowBV[l00] + g0, r10 = P.rowBV[l10] + g0, r01 = P.rowBV[l01] + g1, r11 = P.rowBV[l11] + g1;
+	const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
+	const uint32_t lo0 = (1u << b) - 1u, lo1 = (lo0 << 1) | 1u;     // bits below x, below x+1
+	// plane masks (suffix = dy dz of the point row) and the id of their first vertex in word w
+	const uint32_t mX00 = (s00 ^ x00) & vx, mY00 = (s00 ^ s10) & vp, mZ00 = (s00 ^ s01) & vp;
+	const uint32_t mX10 = (s10 ^ x10) & vx, mZ10 = (s10 ^ s11) & vp;
+	const uint32_t mX01 = (s01 ^ x01) & vx, mY01 = (s01 ^ s11) & vp;
+	const uint32_t mX11 = (s11 ^ x11) & vx;
+	const uint32_t bX00 = r00 + fldV(p00, 0), bY00 = r00 + fldV(p00, 1), bZ00 = r00 + fldV(p00, 2);
+	const uint32_t bX10 = r10 + fldV(p10, 0), bZ10 = r10 + fldV(p10, 2);
+	const uint32_t bX01 = r01 + fldV(p01, 0), bY01 = r01 + fldV(p01, 1);
+	const uint32_t bX11 = r11 + fldV(p11, 0);
+	// edges: 0:(0,1)y 1:(1,2)z 2:(3,2)y 3:(0,3)z 4:(4,5)y 5:(5,6)z 6:(7,6)y 7:(4,7)z 8:(0,4)x 9:(1,5)x 10:(2,6)x 11:(3,7)x
+	id[0] = bY00 + (uint32_t)popc32(mY00 & lo0);  id[4] = bY00 + (uint32_t)popc32(mY00 & lo1);
+	id[1] = bZ10 + (uint32_t)popc32(mZ10 & lo0);  id[5] = bZ10 + (uint32_t)popc32(mZ10 & lo1);
+	id[2] = bY01 + (uint32_t)popc32(mY01 & lo0);  id[6] = bY01 + (uint32_t)popc32(mY01 & lo1);
+	id[3] = bZ00 + (uint32_t)popc32(mZ00 & lo0);  id[7] = bZ00 + (uint32_t)popc32(mZ00 & lo1);
+	id[8] = bX00 + (uint32_t)popc32(mX00 & lo0);
+	id[9] = bX10 + (uint32_t)popc32(mX10 & lo0);
+	id[10] = bX11 + (uint32_t)popc32(mX11 & lo0);
+	id[11] = bX01 + (uint32_t)popc32(mX01 & lo0);
+	// corner k -> index bit 7-k (corners 0..3 at x: rows 00 10 11 01; 4..7 at x+1)
+	return (((s00 >> b) & 1u) << 7) | (((s10 >> b) & 1u) << 6) | (((s11 >> b) & 1u) << 5) | (((s01 >> b) & 1u) << 4) |
+	       (((x00 >> b) & 1u) << 3) | (((x10 >> b) & 1u) << 2) | (((x11 >> b) & 1u) << 1) | ((x01 >> b) & 1u);
+}
+
+// triangle j of a cell whose 13 vertex ids (12 edges + centre) sit at ids[e * stride]
+MC_HD void emit_triangle_fast(const Params &P, unsigned tw, unsigned m, const uint32_t *ids, uint32_t stride, uint32_t tid,
+                              uint64_t cell)
+{
+	uint32_t ti[3];
+	ti[0] = ids[((tw >> 8) & 15u) * stride];
+	ti[1] = ids[((tw >> 4) & 15u) * stride];
+	ti[2] = ids[(tw & 15u) * stride];
+	write_triangle(P, tid, ti, m, cell);
+}
+
 // global id of the vertex a triangle corner refers to: edge code e (0..11) of the
 // cell at bit b; zm = on-iso corner mask of the cell; key = identity used by the
 // zero-area test (marching_cubes_33.c:1235)
@@ -844,17 +909,6 @@ MC_HD uint32_t corner_vertex(const uint32_t *pmask, const uint32_t *pbase, uint3
 	}
 	const uint32_t mk = pmask[combo * stride];
 	return pbase[combo * stride] + (uint32_t)popc32(off >= 32 ? mk : (mk & ((1u << off) - 1u)));
-}
-
-MC_HD void write_triangle(const Params &P, uint32_t tid, const uint32_t *ti, unsigned m, uint64_t cell)
-{
-	if (tid >= P.capT) { P.totals->overflow = 1; return; }
-	// winding: marching_cubes_33.c:1246-1250 (ti[0] = nibble 2, ti[1] = nibble 1, ti[2] = nibble 0)
-	uint32_t a0 = m ? ti[0] : ti[1], a1 = m ? ti[1] : ti[0];
-	if (P.geom.normal_neg) { uint32_t t = a0; a0 = a1; a1 = t; }
-	uint32_t *T = P.T + 3 * (uint64_t)tid;
-	T[0] = a0; T[1] = a1; T[2] = ti[2];
-	if (P.tcell) P.tcell[tid] = cell;
 }
 
 // one triangle of a cell WITHOUT on-iso corners: table word tw, cell at bit b

@@ -303,6 +303,23 @@ __device__ __forceinline__ void block_exscan2(uint64_t &a, uint64_t &b, uint64_t
 
 __device__ __forceinline__ uint32_t sumV(uint64_t p) { return fldV(p, 0) + fldV(p, 1) + fldV(p, 2); }
 
+// Does any row that the G rows starting at local row lr0 depend on hold an on-iso
+// sample?  (rows y..y+G+1 of slices z..z+2: the cells' corner rows and the rows
+// their vertex masks are built from.)  Warp-uniform; decides between the quad
+// fast paths and the generic bitmap walk for the whole group.
+__device__ __forceinline__ bool group_has_oniso(const Params &P, bool any, uint32_t lr0, unsigned lane)
+{
+	if (!any) return false;
+	bool f = false;
+	const uint32_t n = P.G + 2;
+	for (uint32_t i = lane; i < 3 * n; i += 32) {
+		const uint32_t dz = i / n, dy = i - dz * n;
+		const uint64_t row = (uint64_t)lr0 + dy + (uint64_t)dz * P.NY;
+		if (row < P.Lrows) f = f || P.rowZ[row] != 0;
+	}
+	return __any_sync(0xFFFFFFFFu, f);
+}
+
 // lane -> (row within the warp's group, quad) of pass `pass`
 __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32_t pass, uint32_t &r, uint32_t &q)
 {
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 	__shared__ uint64_t s_w[2][8];
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const bool gz = P.totals->anyZ != 0;
+	const bool anyz = P.totals->anyZ != 0;
 	const uint32_t RB = CNT_WARPS * P.G;
 	const uint32_t npass = (P.Q + 31) / 32;
 
@@ -336,6 +353,7 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 		s_row[0][threadIdx.x] = 0; s_row[1][threadIdx.x] = 0; s_row[2][threadIdx.x] = 0;
 		__syncthreads();
 		const uint32_t row0 = blk * RB + wid * P.G;
+		const bool gz = group_has_oniso(P, anyz, row0, lane);
 		uint64_t carryV = 0, carryT = 0;
 		for (uint32_t pass = 0; pass < npass; pass++) {
 			uint32_t r, q;
@@ -394,20 +412,30 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 				const int srcl = (int)min(r * P.Q, 31u);
 				rsv = __shfl_sync(0xFFFFFFFFu, xv, srcl); rst = __shfl_sync(0xFFFFFFFFu, xt, srcl);
 			}
-			const uint64_t lv = carryV + xv - rsv;           // row-local prefix in front of this quad
+			uint64_t lv = carryV + xv - rsv;                 // row-local prefix in front of this quad
+			if (P.Q <= 32) {
+				// fold the plane offsets in: Y ids follow the row's X ids, Z ids follow both
+				const int lastl = (int)min(r * P.Q + P.Q - 1, 31u);
+				lv += plane_offsets(__shfl_sync(0xFFFFFFFFu, lv + tv, lastl));
+			}
 			if (valid) {
 				uint64_t *pw = P.wpreV + (uint64_t)lr * P.WP + 4 * q;
 				*reinterpret_cast<ulonglong2 *>(pw) = make_ulonglong2(lv, lv + e1);
 				*reinterpret_cast<ulonglong2 *>(pw + 2) = make_ulonglong2(lv + e2, lv + e3);
 				if (q == P.Q - 1) {
-					const uint64_t rowV = lv + tv, rowT = carryT + it - rst;
-					pw[4] = rowV;
-					s_row[0][wid * P.G + r] = sumV(rowV);
+					const uint64_t rowT = carryT + it - rst;
+					pw[4] = lv + tv;
+					s_row[0][wid * P.G + r] = P.Q <= 32 ? fldV(lv + tv, 2) : sumV(lv + tv);
 					s_row[1][wid * P.G + r] = (uint32_t)rowT;
 					s_row[2][wid * P.G + r] = (uint32_t)(rowT >> 32);
 				}
 			}
 			if (P.Q > 32) { carryV += __shfl_sync(0xFFFFFFFFu, iv, 31); carryT += __shfl_sync(0xFFFFFFFFu, it, 31); }
+		}
+		if (P.Q > 32 && row0 < P.Lrows) {
+			// long rows: the plane totals are only known now; add the offsets in a second sweep
+			const uint64_t add = plane_offsets(carryV);
+			for (uint32_t i = lane; i <= 4 * P.Q; i += 32) P.wpreV[(uint64_t)row0 * P.WP + i] += add;
 		}
 		__syncthreads();
 		// CTA-relative row bases
@@ -430,24 +458,27 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 // and turns the CTA-relative row bases into slab-local ones: the implicit running
 // M->nV++ / nT++ of the reference (marching_cubes_33.c:487, :1245).
 // ---------------------------------------------------------------------------
+#define RS_BLOCKS 32     // k_count blocks per k_rowscan CTA
+
 __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32_t RB, const uint32_t *blkSum, uint32_t owned_end_row)
 {
 	__shared__ uint64_t s_w[2][8];
-	__shared__ uint64_t s_base[3][256];
-	const uint32_t b0 = blockIdx.x * 256, me = b0 + threadIdx.x;
+	__shared__ uint64_t s_base[3][RS_BLOCKS];
+	const uint32_t b0 = blockIdx.x * RS_BLOCKS, me = b0 + threadIdx.x;
+	const bool mine = threadIdx.x < RS_BLOCKS && me < nblk;
 	uint64_t aV = 0, aT = 0, aC = 0;
 	for (uint32_t i = threadIdx.x; i < b0; i += 256) { aV += blkSum[i]; aT += blkSum[nblk + i]; aC += blkSum[2 * nblk + i]; }
-	uint64_t mV = me < nblk ? blkSum[me] : 0, mT = me < nblk ? blkSum[nblk + me] : 0, mC = me < nblk ? blkSum[2 * nblk + me] : 0;
-	uint64_t preV, preT, preC, dummy, totV, totT, totC;
+	uint64_t mV = mine ? blkSum[me] : 0, mT = mine ? blkSum[nblk + me] : 0, mC = mine ? blkSum[2 * nblk + me] : 0;
+	uint64_t preV, preT, preC, totV, totT, totC;
 	block_exscan2(aV, aT, preV, preT, s_w);              // totals = sums over all earlier blocks
 	block_exscan2(aC, mV, preC, totV, s_w);              // mV becomes this block's exclusive prefix within the CTA
 	block_exscan2(mT, mC, totT, totC, s_w);
-	(void)dummy;
-	const uint64_t bV = preV + mV, bT = preT + mT, bC = preC + mC;
-	s_base[0][threadIdx.x] = bV; s_base[1][threadIdx.x] = bT; s_base[2][threadIdx.x] = bC;
+	if (threadIdx.x < RS_BLOCKS) {
+		s_base[0][threadIdx.x] = preV + mV; s_base[1][threadIdx.x] = preT + mT; s_base[2][threadIdx.x] = preC + mC;
+	}
 	__syncthreads();
 	const uint64_t rows0 = (uint64_t)b0 * RB;
-	for (uint32_t i = threadIdx.x; i < 256 * RB; i += 256) {
+	for (uint32_t i = threadIdx.x; i < RS_BLOCKS * RB; i += 256) {
 		const uint64_t lr = rows0 + i;
 		if (lr >= P.Lrows) break;
 		const uint32_t bl = i / RB;
@@ -489,25 +520,27 @@ __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32
 #define EM_WARPS 8
 #define VQ 256
 #define CQ 256
-#define EM_SMEM (TBL_BYTES + EM_WARPS * (VQ * 4 + CQ * 4 + 16 * 32 * 4))
+#define EM_SCR 512      // per-warp scratch words: 13 ids x 32 lanes, or 8 (mask, base) pairs x 32 lanes
+#define EM_SMEM (TBL_BYTES + EM_WARPS * (VQ + CQ + EM_SCR) * 4)
 
 template <typename Sample>
-__global__ void __launch_bounds__(256) k_emit(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, 3) k_emit(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t *vq = (uint32_t *)(smem + TBL_BYTES) + wid * VQ;
 	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * VQ + wid * CQ;
-	uint32_t *pm = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (VQ + CQ) + wid * 512;   // [8][32]
-	uint32_t *pb = pm + 256;                                                             // [8][32]
-	const bool gz = P.totals->anyZ != 0;
-	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
+	uint32_t *scr = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (VQ + CQ) + wid * EM_SCR;
+	const bool anyz = P.totals->anyZ != 0;
 	const uint32_t nShared = P.totals->nShared;
+	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
+	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
 	const uint32_t npass = (P.Q + 31) / 32;
 
 	for (uint32_t g = blockIdx.x * EM_WARPS + wid; g < ngroups; g += gridDim.x * EM_WARPS) {
 		const uint32_t lr0 = row_begin + g * P.G, lrE = min(lr0 + P.G, row_end);
+		const bool gz = group_has_oniso(P, anyz, lr0, lane);
 		// ======================= vertices =======================
 		const uint32_t vfirst = P.rowBV[lr0], vend = P.rowBV[lrE];
 		for (uint32_t win0 = vfirst; win0 < vend; win0 += VQ) {
@@ -520,15 +553,17 @@ __global__ void __launch_bounds__(256) k_emit(Params P, uint32_t row_begin, uint
 				const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(pw), pc = *reinterpret_cast<const ulonglong2 *>(pw + 2);
 				const uint64_t p4 = pw[4];
 				if (p4 == pa.x) continue;                    // no vertex in this quad
-				const uint64_t tot = P.wpreV[(uint64_t)lr * P.WP + 4 * P.Q];
-				const uint32_t bX = P.rowBV[lr], bY = bX + fldV(tot, 0), bZ = bY + fldV(tot, 1);
+				const uint32_t rb = P.rowBV[lr];
 				{
 					// does any of the quad's three id ranges meet the window?
-					const uint32_t wl = win0, wh = win0 + VQ;
-					const uint32_t x0 = bX + fldV(pa.x, 0), x1 = bX + fldV(p4, 0);
-					const uint32_t y0 = bY + fldV(pa.x, 1), y1 = bY + fldV(p4, 1);
-					const uint32_t z0 = bZ + fldV(pa.x, 2), z1 = bZ + fldV(p4, 2);
-					if (!((x1 > x0 && x0 < wh && x1 > wl) || (y1 > y0 && y0 < wh && y1 > wl) || (z1 > z0 && z0 < wh && z1 > wl))) continue;
+					const uint32_t wl = win0 - rb, wh = wl + VQ;     // window in row-local ids (may wrap: unsigned compares below)
+					bool hit = false;
+#pragma unroll
+					for (int a = 0; a < 3; a++) {
+						const uint32_t i0 = fldV(pa.x, a), i1 = fldV(p4, a);
+						hit = hit || (i1 > i0 && (int32_t)(i0 - wh) < 0 && (int32_t)(i1 - wl) > 0);
+					}
+					if (!hit) continue;
 				}
 				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
 				Quad q00, q10, q01;
@@ -555,7 +590,7 @@ __global__ void __launch_bounds__(256) k_emit(Params P, uint32_t row_begin, uint
 #pragma unroll
 					for (int a = 0; a < 3; a++) {
 						uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
-						uint32_t slot = (a == 0 ? bX : (a == 1 ? bY : bZ)) + fldV(pk[k], a) - win0;
+						uint32_t slot = rb + fldV(pk[k], a) - win0;
 						while (m) {
 							const int b = __ffs((int)m) - 1;
 							m &= m - 1;
@@ -651,14 +686,22 @@ __global__ void __launch_bounds__(256) k_emit(Params P, uint32_t row_begin, uint
 						const uint32_t lr = lr0 + (e >> 16);
 						const uint32_t zl = fastdiv(lr, P.NY, P.mNY);
 						y = lr - zl * P.NY; z = zl + P.zlo;
-						WordRec rec; CellWords cw; CellPairs cp;
-						word_masks(P, z, y, x >> 5, gz, rec, cw);
-						cell_pairs(P, z, y, x >> 5, gz, rec, cw, cp);
+						if (!gz) {
+							uint32_t id[12];
+							const unsigned idx = cell_fast(P, x, y, z, z == P.hz ? vbn : vb, z + 1 == P.hz ? vbn : vb, id);
 #pragma unroll
-						for (int k = 0; k < 8; k++) { pm[k * 32 + lane] = cp.mask[k]; pb[k * 32 + lane] = cp.base[k]; }
-						const unsigned idx = cell_index(cw.c, 1, (int)b);
-						zm = cw.zany ? cell_zmask(cw.zc, 1, (int)b) : 0u;
-						pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
+							for (int k = 0; k < 12; k++) scr[k * 32 + lane] = id[k];
+							pat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
+						} else {
+							WordRec rec; CellWords cw; CellPairs cp;
+							word_masks(P, z, y, x >> 5, true, rec, cw);
+							cell_pairs(P, z, y, x >> 5, true, rec, cw, cp);
+#pragma unroll
+							for (int k = 0; k < 8; k++) { scr[k * 32 + lane] = cp.mask[k]; scr[256 + k * 32 + lane] = cp.base[k]; }
+							const unsigned idx = cell_index(cw.c, 1, (int)b);
+							zm = cw.zany ? cell_zmask(cw.zc, 1, (int)b) : 0u;
+							pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
+						}
 					}
 					// triangle / centre offsets: shuffle scan in sweep order
 					const uint32_t v = pat.ntri | (pat.centre << 16);
@@ -680,11 +723,15 @@ __global__ void __launch_bounds__(256) k_emit(Params P, uint32_t row_begin, uint
 								P.totals->overflow = 1;
 							}
 						}
-						if (zm) {
-							emit_cell_triangles_z(P, tb, b, pat, zm, vb + cl, pm + lane, pb + lane, 32, tid, 0u, 0xFFFFFFFFu, cell);
+						if (!gz) {
+							scr[12 * 32 + lane] = vb + cl;
+							for (uint32_t j = 0; j < pat.ntri; j++)
+								emit_triangle_fast(P, tb.tri[pat.start + j], pat.m, scr + lane, 32, tid + j, cell);
+						} else if (zm) {
+							emit_cell_triangles_z(P, tb, b, pat, zm, vb + cl, scr + lane, scr + 256 + lane, 32, tid, 0u, 0xFFFFFFFFu, cell);
 						} else {
 							for (uint32_t j = 0; j < pat.ntri; j++)
-								emit_triangle_task(P, tb.tri[pat.start + j], b, pat.m, vb + cl, pm + lane, pb + lane, 32, tid + j, cell);
+								emit_triangle_task(P, tb.tri[pat.start + j], b, pat.m, vb + cl, scr + lane, scr + 256 + lane, 32, tid + j, cell);
 						}
 					}
 					runT += tot & 0xFFFFu; runC += tot >> 16;
@@ -1021,7 +1068,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 	if (c->timing) CU(cudaEventRecord(c->ev[2], s));
 	{
 		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
-		k_rowscan<<<(c->nblk + 255) / 256, 256, 0, s>>>(P, c->nblk, CNT_WARPS * P.G, c->blk_sum, owned_end);
+		k_rowscan<<<(c->nblk + RS_BLOCKS - 1) / RS_BLOCKS, 256, 0, s>>>(P, c->nblk, CNT_WARPS * P.G, c->blk_sum, owned_end);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[3], s));

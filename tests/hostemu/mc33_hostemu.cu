@@ -82,6 +82,7 @@ static void run(Params &P, bool emit)
 				av += cv; ac += cc;
 			}
 			P.wpreV[(uint64_t)lr * P.WP + 4 * P.Q] = av;
+			for (uint32_t w = 0; w <= 4 * P.Q; w++) P.wpreV[(uint64_t)lr * P.WP + w] += plane_offsets(av);
 			if (lr == owned_end) P.totals->nShared = (uint32_t)bv;
 			P.rowBV[lr] = (uint32_t)bv; P.rowBT[lr] = (uint32_t)bt; P.rowBC[lr] = (uint32_t)bc;
 			bv += fldV(av, 0) + fldV(av, 1) + fldV(av, 2); bt += ac & 0xFFFFFFFFu; bc += ac >> 32;
@@ -111,6 +112,7 @@ static void run(Params &P, bool emit)
 	}
 	// K3, cells: triangles (+ centre vertices) in sweep order
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
+	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - P.totals->nShared;
 	for (uint32_t lr = (P.cz0 - P.zlo) * P.NY; lr < (P.cz1 - P.zlo) * P.NY; lr++) {
 		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
 		if (y >= P.ny) continue;
@@ -120,15 +122,23 @@ static void run(Params &P, bool emit)
 			word_rec(z, y, w, rec, cw);
 			uint32_t act = rec.act;
 			if (!act) continue;
-			// the drain side recomputes the word through the generic path
-			word_masks(P, z, y, w, gz, rec, cw);
-			cell_pairs(P, z, y, w, gz, rec, cw, cp);
+			// the drain side: generic path with on-iso samples, else the fast per-cell path
+			if (gz) {
+				word_masks(P, z, y, w, gz, rec, cw);
+				cell_pairs(P, z, y, w, gz, rec, cw, cp);
+			}
 			while (act) {
 				int b = ffs32(act);
 				act &= act - 1;
-				const unsigned idx = cell_index(cw.c, 1, b);
-				const unsigned zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
 				const uint32_t x = (w << 5) + b;
+				uint32_t ids[13];
+				unsigned idx, zm = 0;
+				if (gz) {
+					idx = cell_index(cw.c, 1, b);
+					zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
+				} else {
+					idx = cell_fast(P, x, y, z, z == P.hz ? vbn : vb, z + 1 == P.hz ? vbn : vb, ids);
+				}
 				const CellPattern cpat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
 				const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
 				if (cpat.centre) {
@@ -139,7 +149,12 @@ static void run(Params &P, bool emit)
 						P.totals->overflow = 1;
 					}
 				}
-				if (zm) {
+				if (!gz) {
+					ids[12] = vb + cl;
+					for (uint32_t j = 0; j < cpat.ntri; j++)
+						emit_triangle_fast(P, tb.tri[cpat.start + j], cpat.m, ids, 1, tid + j, cell);
+					tid += cpat.ntri;
+				} else if (zm) {
 					tid += emit_cell_triangles_z(P, tb, (unsigned)b, cpat, zm, vb + cl, cp.mask, cp.base, 1, tid, 0u, 0xFFFFFFFFu, cell);
 				} else {
 					for (uint32_t j = 0; j < cpat.ntri; j++)

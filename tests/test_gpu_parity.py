@@ -87,6 +87,21 @@ def test_smooth_and_ct():
         _same(oracle_extract(c, iso, "u16"), gpu_extract(c, iso, "u16"))
 
 
+def test_sparse_on_iso_samples_mix_fast_and_generic_paths():
+    """a smooth float grid with a few samples planted exactly on the isovalue: most row
+    groups take the quad fast paths, the ones near a planted sample the generic walk"""
+    g = gyroid_grid(80, periods=2).copy()
+    rng = np.random.default_rng(11)
+    iso = np.float32(0.25)
+    idx = rng.integers(0, g.size, size=40)
+    g.reshape(-1)[idx] = iso
+    # also on the faces / corners of the grid
+    g[0, 0, 0] = iso; g[-1, -1, -1] = iso; g[0, 40, 79] = iso; g[79, 0, 33] = iso
+    _same(oracle_extract(g, float(iso)), gpu_extract(g, float(iso)))
+    d = g.astype(np.float64)
+    _same(oracle_extract(d, float(iso), "f64"), gpu_extract(d, float(iso), "f64"))
+
+
 def test_plateaus_and_empty():
     rng = np.random.default_rng(3)
     a = rng.integers(0, 3, size=(20, 22, 67)).astype(np.uint8)
