@@ -31,9 +31,14 @@
 #if defined(__CUDACC__)
 #define MC_HD __host__ __device__ __forceinline__
 #define MC_HDN __host__ __device__
+// cold paths (ambiguous cells, on-iso samples, inclined grids) are kept out of line:
+// inlined at every use they made the emit kernel 730 KB of SASS and the warps
+// spent 70 % of their time waiting for instruction fetches
+#define MC_COLD __host__ __device__ __noinline__
 #else
 #define MC_HD inline
 #define MC_HDN
+#define MC_COLD __attribute__((noinline))
 #endif
 
 namespace mc33 {
@@ -254,7 +259,7 @@ MC_HD int interior_test(int i, int flag13, const Real *v)
 
 // -> pattern start in MC33_TRI; m = the reference's winding flag
 template <typename Real>
-MC_HDN unsigned select_pattern(const Tables &tb, unsigned i, const Real *v, unsigned *mflag)
+MC_COLD unsigned select_pattern(const Tables &tb, unsigned i, const Real *v, unsigned *mflag)
 {
 	unsigned c = tb.case256[i];
 	int k = (int)(c & 0x7FF);
@@ -389,31 +394,17 @@ struct CellWords { uint32_t c[8]; uint32_t zc[8]; uint32_t zany; };
 // One pass over the bitmaps for word w of row (z,y).  gz: the grid has at least
 // one on-iso sample (uniform flag from the classify kernel); when it is false
 // the Z bitmap is not touched at all.
-MC_HDN void word_masks(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, WordRec &rec, CellWords &cw)
+// the on-iso part of word_masks(): rare, kept out of line
+MC_COLD void word_masks_z(const Params &P, uint32_t z, uint32_t y, uint32_t w, WordRec &rec, CellWords &cw)
 {
 	const uint32_t lr = (z - P.zlo) * P.NY + y;
 	const bool hasY = y < P.ny, hasZ = z < P.nz;
 	const uint32_t dY = hasY ? P.WP : 0u, dZ = hasZ ? P.NY * P.WP : 0u;
 	const uint32_t i00 = lr * P.WP + w, i10 = i00 + dY, i01 = i00 + dZ, i11 = i01 + dY;
-	const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
-	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
-	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
-	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
-	rec.X = (s00 ^ x00) & vx;
-	rec.Y = (s00 ^ s10) & vp;       // zero when !hasY (s10 is s00 then)
-	rec.Z = (s00 ^ s01) & vp;
-	cw.c[0] = s00; cw.c[4] = x00; cw.c[1] = s10; cw.c[5] = x10;
-	cw.c[2] = s11; cw.c[6] = x11; cw.c[3] = s01; cw.c[7] = x01;
-	const uint32_t any = s00 | s10 | s01 | s11 | x00 | x10 | x01 | x11;
-	const uint32_t all = s00 & s10 & s01 & s11 & x00 & x10 & x01 & x11;
-	rec.act = (hasY && hasZ) ? (any & ~all & vx) : 0u;
-	cw.zany = 0;
-#pragma unroll
-	for (int k = 0; k < 8; k++) cw.zc[k] = 0;
-	if (!gz) return;
 	const unsigned f00 = P.rowZ[lr], f10 = hasY ? P.rowZ[lr + 1] : 0u, f01 = hasZ ? P.rowZ[lr + P.NY] : 0u;
 	const unsigned f11 = (hasY && hasZ) ? P.rowZ[lr + P.NY + 1] : 0u;
 	if (!(f00 | f10 | f01 | f11)) return;
+	const uint32_t s00 = cw.c[0], x00 = cw.c[4], s10 = cw.c[1], s01 = cw.c[3];
 	const uint32_t z00 = P.Z[i00], z10 = hasY ? P.Z[i10] : 0u, z01 = hasZ ? P.Z[i01] : 0u;
 	const uint32_t z11 = (hasY && hasZ) ? P.Z[i11] : 0u;
 	const uint32_t zx00 = shr1(z00, P.Z[i00 + 1]);
@@ -438,6 +429,36 @@ MC_HDN void word_masks(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool
 #pragma unroll
 		for (int k = 0; k < 8; k++) cw.zany |= cw.zc[k];
 	}
+}
+
+MC_HDN void word_masks(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, WordRec &rec, CellWords &cw)
+{
+	const uint32_t lr = (z - P.zlo) * P.NY + y;
+	const bool hasY = y < P.ny, hasZ = z < P.nz;
+	const uint32_t dY = hasY ? P.WP : 0u, dZ = hasZ ? P.NY * P.WP : 0u;
+	const uint32_t i00 = lr * P.WP + w, i10 = i00 + dY, i01 = i00 + dZ, i11 = i01 + dY;
+	const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
+	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
+	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
+	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
+	rec.X = (s00 ^ x00) & vx;
+	rec.Y = (s00 ^ s10) & vp;       // zero when !hasY (s10 is s00 then)
+	rec.Z = (s00 ^ s01) & vp;
+	cw.c[0] = s00; cw.c[4] = x00; cw.c[1] = s10; cw.c[5] = x10;
+	cw.c[2] = s11; cw.c[6] = x11; cw.c[3] = s01; cw.c[7] = x01;
+	const uint32_t any = s00 | s10 | s01 | s11 | x00 | x10 | x01 | x11;
+	const uint32_t all = s00 & s10 & s01 & s11 & x00 & x10 & x01 & x11;
+	rec.act = (hasY && hasZ) ? (any & ~all & vx) : 0u;
+	cw.zany = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) cw.zc[k] = 0;
+	if (gz) word_masks_z(P, z, y, w, rec, cw);
+}
+
+// out-of-line form for the (rare) groups with on-iso samples
+MC_COLD void word_masks_generic(const Params &P, uint32_t z, uint32_t y, uint32_t w, WordRec &rec, CellWords &cw)
+{
+	word_masks(P, z, y, w, true, rec, cw);
 }
 
 // ---------------------------------------------------------------------------
@@ -520,9 +541,10 @@ MC_HD unsigned vertex_key(unsigned e, unsigned zmask)
 // zero-area drop (marching_cubes_33.c:1235), centre vertex flag
 struct CellPattern { unsigned start, m, ntri, centre; };
 
+// ambiguous index (face / interior tests on the corner values) or on-iso corners
 template <typename Sample>
-MC_HDN CellPattern cell_pattern(const Params &P, const Tables &tb, uint32_t x, uint32_t y, uint32_t z,
-                                unsigned idx, unsigned zmask)
+MC_COLD CellPattern cell_pattern_slow(const Params &P, const Tables &tb, uint32_t x, uint32_t y, uint32_t z,
+                                      unsigned idx, unsigned zmask)
 {
 	typedef typename Traits<Sample>::Real Real;
 	CellPattern cp;
@@ -554,6 +576,22 @@ MC_HDN CellPattern cell_pattern(const Params &P, const Tables &tb, uint32_t x, u
 	return cp;
 }
 
+template <typename Sample>
+MC_HD CellPattern cell_pattern(const Params &P, const Tables &tb, uint32_t x, uint32_t y, uint32_t z,
+                               unsigned idx, unsigned zmask)
+{
+	const unsigned e = tb.simple256[idx];
+	if (e != 0xFFFFu && !zmask) {
+		CellPattern cp;
+		cp.start = e & 0xFFF;
+		cp.ntri = e >> 12;
+		cp.m = (tb.case256[idx] >> 11) & 1;
+		cp.centre = 0;
+		return cp;
+	}
+	return cell_pattern_slow<Sample>(P, tb, x, y, z, idx, zmask);
+}
+
 // ---------------------------------------------------------------------------
 // count step.  Packed counts of one (row, word):
 //   cv = nX | nY<<21 | nZ<<42   vertices owned by the 32 points
@@ -580,7 +618,7 @@ MC_HDN uint64_t count_cells(const Params &P, const Tables &tb, uint32_t z, uint3
 		if (e != 0xFFFFu && !zm) {
 			nt += e >> 12;
 		} else {
-			CellPattern cp = cell_pattern<Sample>(P, tb, (w << 5) + b, y, z, idx, zm);
+			CellPattern cp = cell_pattern_slow<Sample>(P, tb, (w << 5) + b, y, z, idx, zm);
 			nt += cp.ntri;
 			nc += cp.centre;
 		}
@@ -590,12 +628,12 @@ MC_HDN uint64_t count_cells(const Params &P, const Tables &tb, uint32_t z, uint3
 
 // generic form (any grid, on-iso samples included) straight from the bitmaps
 template <typename Sample>
-MC_HDN void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,
+MC_COLD void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,
                        bool own_points, bool own_cells, uint64_t &cv, uint64_t &cc)
 {
 	WordRec rec;
 	CellWords cw;
-	word_masks(P, z, y, w, gz, rec, cw);
+	if (gz) word_masks_generic(P, z, y, w, rec, cw); else word_masks(P, z, y, w, false, rec, cw);
 	if (!own_points) { rec.X = rec.Y = rec.Z = 0; }
 	if (!own_cells) rec.act = 0;
 	cv = pack_planes(rec);
@@ -606,38 +644,45 @@ MC_HDN void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y
 // vertex store: MC33_spn0/A/B/C (marching_cubes_33.c:485-621,
 // MC33_util_grd.c:87-112); r[0..2] index-space position, r[3..5] = -grad F
 // ---------------------------------------------------------------------------
+// inclined grids, MC33_spnC (marching_cubes_33.c:595-621): p = _A r + O, n = A_^T n in double
 template <typename Real>
-MC_HDN void store_vertex(const Params &P, Real *r, uint32_t id)
+MC_COLD void store_spnc(const Geom &g, Real *r, Real *p)
+{
+	const double *A = g.A, *B = g.Ai;
+	Real c0, c1, c2;
+	double r0 = r[0], r1 = r[1], r2 = r[2];
+	if (g.tsa) {
+		c0 = (Real)radd(radd(rmul(A[0], r0), rmul(A[1], r1)), rmul(A[2], r2));
+		c1 = (Real)radd(rmul(A[4], r1), rmul(A[5], r2));
+		c2 = (Real)rmul(A[8], r2);
+	} else {
+		c0 = (Real)radd(radd(rmul(A[0], r0), rmul(A[1], r1)), rmul(A[2], r2));
+		c1 = (Real)radd(radd(rmul(A[3], r0), rmul(A[4], r1)), rmul(A[5], r2));
+		c2 = (Real)radd(radd(rmul(A[6], r0), rmul(A[7], r1)), rmul(A[8], r2));
+	}
+	p[0] = radd(c0, (Real)g.O[0]); p[1] = radd(c1, (Real)g.O[1]); p[2] = radd(c2, (Real)g.O[2]);
+	double n0 = r[3], n1 = r[4], n2 = r[5];
+	if (g.tsa) {
+		c2 = (Real)radd(radd(rmul(B[2], n0), rmul(B[5], n1)), rmul(B[8], n2));
+		c1 = (Real)radd(rmul(B[1], n0), rmul(B[4], n1));
+		c0 = (Real)rmul(B[0], n0);
+	} else {
+		c0 = (Real)radd(radd(rmul(B[0], n0), rmul(B[3], n1)), rmul(B[6], n2));
+		c1 = (Real)radd(radd(rmul(B[1], n0), rmul(B[4], n1)), rmul(B[7], n2));
+		c2 = (Real)radd(radd(rmul(B[2], n0), rmul(B[5], n1)), rmul(B[8], n2));
+	}
+	r[3] = c0; r[4] = c1; r[5] = c2;
+}
+
+template <typename Real>
+MC_HD void store_vertex(const Params &P, Real *r, uint32_t id)
 {
 	const Geom &g = P.geom;
 	Real p[3];
 	if (g.store == STORE_SPN0) {
 		p[0] = r[0]; p[1] = r[1]; p[2] = r[2];
 	} else if (g.store == STORE_SPNC) {
-		const double *A = g.A, *B = g.Ai;
-		Real c0, c1, c2;
-		double r0 = r[0], r1 = r[1], r2 = r[2];
-		if (g.tsa) {
-			c0 = (Real)radd(radd(rmul(A[0], r0), rmul(A[1], r1)), rmul(A[2], r2));
-			c1 = (Real)radd(rmul(A[4], r1), rmul(A[5], r2));
-			c2 = (Real)rmul(A[8], r2);
-		} else {
-			c0 = (Real)radd(radd(rmul(A[0], r0), rmul(A[1], r1)), rmul(A[2], r2));
-			c1 = (Real)radd(radd(rmul(A[3], r0), rmul(A[4], r1)), rmul(A[5], r2));
-			c2 = (Real)radd(radd(rmul(A[6], r0), rmul(A[7], r1)), rmul(A[8], r2));
-		}
-		p[0] = radd(c0, (Real)g.O[0]); p[1] = radd(c1, (Real)g.O[1]); p[2] = radd(c2, (Real)g.O[2]);
-		double n0 = r[3], n1 = r[4], n2 = r[5];
-		if (g.tsa) {
-			c2 = (Real)radd(radd(rmul(B[2], n0), rmul(B[5], n1)), rmul(B[8], n2));
-			c1 = (Real)radd(rmul(B[1], n0), rmul(B[4], n1));
-			c0 = (Real)rmul(B[0], n0);
-		} else {
-			c0 = (Real)radd(radd(rmul(B[0], n0), rmul(B[3], n1)), rmul(B[6], n2));
-			c1 = (Real)radd(radd(rmul(B[1], n0), rmul(B[4], n1)), rmul(B[7], n2));
-			c2 = (Real)radd(radd(rmul(B[2], n0), rmul(B[5], n1)), rmul(B[8], n2));
-		}
-		r[3] = c0; r[4] = c1; r[5] = c2;
+		store_spnc<Real>(g, r, p);
 	} else {
 		if (g.store == STORE_SPNB) {
 			r[3] = rmul(r[3], (Real)g.ca);
@@ -708,7 +753,7 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 
 // POINT vertex: MC33_surfint (marching_cubes_33.c:628-649)
 template <typename Sample>
-MC_HDN void emit_point_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
+MC_COLD void emit_point_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
 {
 	typedef typename Traits<Sample>::Real Real;
 	const int64_t sy = (int64_t)P.NX, sz = (int64_t)P.NX * P.NY;
@@ -729,7 +774,7 @@ MC_HDN void emit_point_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t 
 
 // CENTRE vertex (edge code 12): marching_cubes_33.c:1225-1230
 template <typename Sample>
-MC_HDN void emit_centre_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
+MC_COLD void emit_centre_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
 {
 	typedef typename Traits<Sample>::Real Real;
 	Real v[8], r[6];
@@ -799,7 +844,7 @@ MC_HD unsigned combo_of_corner(unsigned c) { return (0x57305730u >> (4 * c)) & 1
 
 struct CellPairs { uint32_t mask[8], base[8]; };
 
-MC_HDN void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, const WordRec &rec00,
+MC_COLD void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool gz, const WordRec &rec00,
                        const CellWords &cw, CellPairs &cp)
 {
 	const uint32_t lr = (z - P.zlo) * P.NY + y;
@@ -815,9 +860,9 @@ MC_HDN void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, bool
 		r01.Y = (cw.c[3] ^ cw.c[2]) & vp;
 	} else {
 		CellWords dummy;
-		word_masks(P, z, y + 1, w, true, r10, dummy);
-		word_masks(P, z + 1, y, w, true, r01, dummy);
-		word_masks(P, z + 1, y + 1, w, true, r11, dummy);
+		word_masks_generic(P, z, y + 1, w, r10, dummy);
+		word_masks_generic(P, z + 1, y, w, r01, dummy);
+		word_masks_generic(P, z + 1, y + 1, w, r11, dummy);
 	}
 	const uint32_t l10 = lr + 1, l01 = lr + P.NY, l11 = l01 + 1;
 	cp.mask[0] = rec00.X; cp.base[0] = local_to_global(P, z, plane_base_local(P, lr, w, 0));
@@ -927,7 +972,7 @@ MC_HD void emit_triangle_task(const Params &P, unsigned tw, unsigned b, unsigned
 
 // all triangles of a cell WITH on-iso corners (zero-area triangles are dropped);
 // only ids in [lo, hi) are written.  Returns the number of triangles kept.
-MC_HDN uint32_t emit_cell_triangles_z(const Params &P, const Tables &tb, unsigned b, const CellPattern &cp, unsigned zm,
+MC_COLD uint32_t emit_cell_triangles_z(const Params &P, const Tables &tb, unsigned b, const CellPattern &cp, unsigned zm,
                                       uint32_t centre_id, const uint32_t *pmask, const uint32_t *pbase, uint32_t stride,
                                       uint32_t tid, uint32_t lo, uint32_t hi, uint64_t cell)
 {

@@ -521,21 +521,18 @@ __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32
 #define VQ 256
 #define CQ 256
 #define EM_SCR 512      // per-warp scratch words: 13 ids x 32 lanes, or 8 (mask, base) pairs x 32 lanes
-#define EM_SMEM (TBL_BYTES + EM_WARPS * (VQ + CQ + EM_SCR) * 4)
+#define EMV_SMEM (EM_WARPS * VQ * 4)
+#define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR) * 4)
 
+// (the two halves are separate kernels: fused, the hot code no longer fitted the
+// instruction cache and 70 % of the warp stalls were instruction fetches)
 template <typename Sample>
-__global__ void __launch_bounds__(256, 3) k_emit(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256) k_emit_vertices(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
-	extern __shared__ __align__(128) unsigned char smem[];
-	const Tables tb = load_tables(smem);
+	__shared__ uint32_t s_vq[EM_WARPS * VQ];
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	uint32_t *vq = (uint32_t *)(smem + TBL_BYTES) + wid * VQ;
-	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * VQ + wid * CQ;
-	uint32_t *scr = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (VQ + CQ) + wid * EM_SCR;
+	uint32_t *vq = s_vq + wid * VQ;
 	const bool anyz = P.totals->anyZ != 0;
-	const uint32_t nShared = P.totals->nShared;
-	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
-	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
 	const uint32_t npass = (P.Q + 31) / 32;
 
 	for (uint32_t g = blockIdx.x * EM_WARPS + wid; g < ngroups; g += gridDim.x * EM_WARPS) {
@@ -584,7 +581,7 @@ __global__ void __launch_bounds__(256, 3) k_emit(Params P, uint32_t row_begin, u
 						quad_word(P, q00, q10, q01, q10, k, w, false, rec, c);
 					} else {
 						CellWords cw;
-						if (w < P.W) word_masks(P, z, y, w, true, rec, cw); else { rec.X = rec.Y = rec.Z = 0; }
+						if (w < P.W) word_masks_generic(P, z, y, w, rec, cw); else { rec.X = rec.Y = rec.Z = 0; }
 					}
 					const uint32_t zw = (zrow && w < P.W) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
 #pragma unroll
@@ -611,6 +608,26 @@ __global__ void __launch_bounds__(256, 3) k_emit(Params P, uint32_t row_begin, u
 			}
 			__syncwarp();
 		}
+	}
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(256) k_emit_cells(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	const Tables tb = load_tables(smem);
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + wid * CQ;
+	uint32_t *scr = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * CQ + wid * EM_SCR;
+	const bool anyz = P.totals->anyZ != 0;
+	const uint32_t nShared = P.totals->nShared;
+	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
+	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
+	const uint32_t npass = (P.Q + 31) / 32;
+
+	for (uint32_t g = blockIdx.x * EM_WARPS + wid; g < ngroups; g += gridDim.x * EM_WARPS) {
+		const uint32_t lr0 = row_begin + g * P.G, lrE = min(lr0 + P.G, row_end);
+		const bool gz = group_has_oniso(P, anyz, lr0, lane);
 		// ======================= cells =======================
 		const uint32_t tbase = P.rowBT[lr0], cloc0 = nShared + P.rowBC[lr0];
 		uint32_t runT = 0, runC = 0;                             // triangles / centres of the group so far
@@ -640,7 +657,7 @@ __global__ void __launch_bounds__(256, 3) k_emit(Params P, uint32_t row_begin, u
 							for (int k = 0; k < 4; k++) {
 								if (4 * q + k < P.WC) {
 									WordRec rec; CellWords cw;
-									word_masks(P, z, y, 4 * q + k, true, rec, cw);
+									word_masks_generic(P, z, y, 4 * q + k, rec, cw);
 									act[k] = rec.act;
 								}
 							}
@@ -694,7 +711,7 @@ __global__ void __launch_bounds__(256, 3) k_emit(Params P, uint32_t row_begin, u
 							pat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
 						} else {
 							WordRec rec; CellWords cw; CellPairs cp;
-							word_masks(P, z, y, x >> 5, true, rec, cw);
+							word_masks_generic(P, z, y, x >> 5, rec, cw);
 							cell_pairs(P, z, y, x >> 5, true, rec, cw, cp);
 #pragma unroll
 							for (int k = 0; k < 8; k++) { scr[k * 32 + lane] = cp.mask[k]; scr[256 + k * 32 + lane] = cp.base[k]; }
@@ -831,7 +848,7 @@ static int set_geom(mc33cu_ctx *c, const mc33cu_desc *d);
 template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 {
 	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES)));
-	CU(cudaFuncSetAttribute(k_emit<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM));
+	CU(cudaFuncSetAttribute(k_emit_cells<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
 	return MC33CU_OK;
 }
 
@@ -1081,15 +1098,24 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
 	{
-		// rows whose vertices (pz0..pz1) and cells (cz0..cz1, a prefix of them) this slab owns
+		// rows whose vertices this slab owns
 		const uint32_t rb = (P.pz0 - P.zlo) * P.NY, re = (P.pz1 - P.zlo) * P.NY;
 		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
-		uint32_t grid = (uint32_t)c->n_sm * 5;
+		uint32_t grid = (uint32_t)c->n_sm * 6;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		k_emit<Sample><<<grid, 256, EM_SMEM, s>>>(P, rb, re, ngroups);
+		k_emit_vertices<Sample><<<grid, 256, 0, s>>>(P, rb, re, ngroups);
 		c->launches++;
 	}
-	if (c->timing) { CU(cudaEventRecord(c->ev[4], s)); CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
+	if (c->timing) CU(cudaEventRecord(c->ev[4], s));
+	{
+		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (P.cz1 - P.zlo) * P.NY;
+		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
+		uint32_t grid = (uint32_t)c->n_sm * 6;
+		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
+		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups);
+		c->launches++;
+	}
+	if (c->timing) { CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
 	CU(cudaGetLastError());
 	return MC33CU_OK;
 }
