@@ -149,7 +149,8 @@ struct Params {
 	uint32_t Lrows;               // (zhi-zlo)*NY
 	uint32_t mQ, mNY;             // floor(2^32/Q), floor(2^32/NY) for fastdiv
 	uint32_t *S, *Z;              // bitmaps [Lrows][WP]; words >= W of a row are zero
-	uint8_t *rowZ;                // [Lrows] any Z bit in the row
+	uint32_t *rowZ;               // [Lrows] hint: == zepoch when the row has an on-iso sample in this extraction
+	uint32_t zepoch;
 	uint64_t *wpreV;              // [Lrows][WP] X | Y<<21 | Z<<42: row-local index of each plane's first vertex
 	                              // in word k (entries W..4Q: one past the plane's last vertex)
 	uint32_t *rowBV, *rowBT, *rowBC;   // [Lrows+1] slab-local exclusive bases: vertices, triangles, centres
@@ -171,11 +172,22 @@ struct Params {
 #define MC_CY(c) ((0x66 >> (c)) & 1)
 #define MC_CZ(c) ((0xCC >> (c)) & 1)
 
+// samples are never written by the kernels: read-only (non-coherent) loads, which
+// the compiler may hoist above the mesh stores
+template <typename Sample>
+MC_HD Sample ldro(const Sample *p)
+{
+#if defined(__CUDA_ARCH__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
 template <typename Sample>
 MC_HD Sample ld_sample(const Params &P, uint32_t x, uint32_t y, uint32_t z)
 {
 	const Sample *F = (const Sample *)P.data;
-	return F[((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x];
+	return ldro(F + ((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x);
 }
 template <typename Sample>
 MC_HD typename Traits<Sample>::Real ld_val(const Params &P, typename Traits<Sample>::Real iso, uint32_t x, uint32_t y, uint32_t z)
@@ -401,8 +413,8 @@ MC_COLD void word_masks_z(const Params &P, uint32_t z, uint32_t y, uint32_t w, W
 	const bool hasY = y < P.ny, hasZ = z < P.nz;
 	const uint32_t dY = hasY ? P.WP : 0u, dZ = hasZ ? P.NY * P.WP : 0u;
 	const uint32_t i00 = lr * P.WP + w, i10 = i00 + dY, i01 = i00 + dZ, i11 = i01 + dY;
-	const unsigned f00 = P.rowZ[lr], f10 = hasY ? P.rowZ[lr + 1] : 0u, f01 = hasZ ? P.rowZ[lr + P.NY] : 0u;
-	const unsigned f11 = (hasY && hasZ) ? P.rowZ[lr + P.NY + 1] : 0u;
+	const bool f00 = P.rowZ[lr] == P.zepoch, f10 = hasY && P.rowZ[lr + 1] == P.zepoch;
+	const bool f01 = hasZ && P.rowZ[lr + P.NY] == P.zepoch, f11 = hasY && hasZ && P.rowZ[lr + P.NY + 1] == P.zepoch;
 	if (!(f00 | f10 | f01 | f11)) return;
 	const uint32_t s00 = cw.c[0], x00 = cw.c[4], s10 = cw.c[1], s01 = cw.c[3];
 	const uint32_t z00 = P.Z[i00], z10 = hasY ? P.Z[i10] : 0u, z01 = hasZ ? P.Z[i01] : 0u;
@@ -626,6 +638,47 @@ MC_HDN uint64_t count_cells(const Params &P, const Tables &tb, uint32_t z, uint3
 	return (uint64_t)nt | ((uint64_t)nc << 32);
 }
 
+// the active cells of the four words of a quad in ONE loop (a separate loop per
+// word would make a warp pay the longest word four times); no on-iso samples.
+// Each iteration takes the lowest active cell of the lowest non-empty word.
+template <typename Sample>
+MC_HDN uint64_t count_cells_quad(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t q, const uint32_t *act,
+                                 const Quad &q00, const Quad &q10, const Quad &q01, const Quad &q11)
+{
+	uint32_t nt = 0, nc = 0;
+	uint32_t a0 = act[0], a1 = act[1], a2 = act[2], a3 = act[3];
+	while (a0 | a1 | a2 | a3) {
+		const int k = a0 ? 0 : (a1 ? 1 : (a2 ? 2 : 3));
+		const uint32_t m = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
+		const int b = ffs32(m);
+		const uint32_t cl = m & (m - 1);
+		if (k == 0) a0 = cl; else if (k == 1) a1 = cl; else if (k == 2) a2 = cl; else a3 = cl;
+		// the cell's 2 x 4 corner bits: bit b of word k and bit b+1 (bit 0 of word k+1 when b == 31)
+		const uint64_t t00 = ((uint64_t)(k == 0 ? q00.s[1] : (k == 1 ? q00.s[2] : (k == 2 ? q00.s[3] : q00.s[4]))) << 32) |
+		                     (k == 0 ? q00.s[0] : (k == 1 ? q00.s[1] : (k == 2 ? q00.s[2] : q00.s[3])));
+		const uint64_t t10 = ((uint64_t)(k == 0 ? q10.s[1] : (k == 1 ? q10.s[2] : (k == 2 ? q10.s[3] : q10.s[4]))) << 32) |
+		                     (k == 0 ? q10.s[0] : (k == 1 ? q10.s[1] : (k == 2 ? q10.s[2] : q10.s[3])));
+		const uint64_t t01 = ((uint64_t)(k == 0 ? q01.s[1] : (k == 1 ? q01.s[2] : (k == 2 ? q01.s[3] : q01.s[4]))) << 32) |
+		                     (k == 0 ? q01.s[0] : (k == 1 ? q01.s[1] : (k == 2 ? q01.s[2] : q01.s[3])));
+		const uint64_t t11 = ((uint64_t)(k == 0 ? q11.s[1] : (k == 1 ? q11.s[2] : (k == 2 ? q11.s[3] : q11.s[4]))) << 32) |
+		                     (k == 0 ? q11.s[0] : (k == 1 ? q11.s[1] : (k == 2 ? q11.s[2] : q11.s[3])));
+		const uint32_t p00 = (uint32_t)(t00 >> b) & 3u, p10 = (uint32_t)(t10 >> b) & 3u;
+		const uint32_t p01 = (uint32_t)(t01 >> b) & 3u, p11 = (uint32_t)(t11 >> b) & 3u;
+		// corners 0..3 at x: rows 00 10 11 01 -> index bits 7..4; corners 4..7 at x+1 -> bits 3..0
+		const unsigned idx = ((p00 & 1u) << 7) | ((p10 & 1u) << 6) | ((p11 & 1u) << 5) | ((p01 & 1u) << 4) |
+		                     ((p00 >> 1) << 3) | ((p10 >> 1) << 2) | ((p11 >> 1) << 1) | (p01 >> 1);
+		const unsigned e = tb.simple256[idx];
+		if (e != 0xFFFFu) {
+			nt += e >> 12;
+		} else {
+			CellPattern cp = cell_pattern_slow<Sample>(P, tb, (((q << 2) + (uint32_t)k) << 5) + (uint32_t)b, y, z, idx, 0u);
+			nt += cp.ntri;
+			nc += cp.centre;
+		}
+	}
+	return (uint64_t)nt | ((uint64_t)nc << 32);
+}
+
 // generic form (any grid, on-iso samples included) straight from the bitmaps
 template <typename Sample>
 MC_COLD void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,
@@ -717,7 +770,7 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 	const int64_t sy = (int64_t)P.NX, sz = (int64_t)P.NX * P.NY;
 	const Sample *p0 = (const Sample *)P.data + ((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x;
 	const Sample *p1 = p0 + (a == 0 ? (int64_t)1 : (a == 1 ? sy : sz));
-	const Real va = rsub(iso, (Real)p0[0]), vb = rsub(iso, (Real)p1[0]);
+	const Real va = rsub(iso, (Real)ldro(p0)), vb = rsub(iso, (Real)ldro(p1));
 	const Real t = rdiv(va, rsub(va, vb));
 	const Real one_t = rsub((Real)1, t);
 	Real r[6];
@@ -733,16 +786,16 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 			r[c] = (Real)q;
 			if (q != 0 && q != nq) {
 				// central difference on raw samples (e.g. c:993-994)
-				const Real e0 = rawdiff(p0[-sc], p0[sc]), e1 = rawdiff(p1[-sc], p1[sc]);
+				const Real e0 = rawdiff(ldro(p0 - sc), ldro(p0 + sc)), e1 = rawdiff(ldro(p1 - sc), ldro(p1 + sc));
 				r[3 + c] = rmul((Real)0.5f, radd(rmul(e0, one_t), rmul(e1, t)));
 			} else {
 				Real d0, d1;
 				if (q == 0) {   // forward difference of the iso-subtracted values (e.g. c:813)
-					d0 = rsub(rsub(iso, (Real)p0[sc]), va);
-					d1 = rsub(rsub(iso, (Real)p1[sc]), vb);
+					d0 = rsub(rsub(iso, (Real)ldro(p0 + sc)), va);
+					d1 = rsub(rsub(iso, (Real)ldro(p1 + sc)), vb);
 				} else {        // backward (e.g. c:995 else-branch)
-					d0 = rsub(va, rsub(iso, (Real)p0[-sc]));
-					d1 = rsub(vb, rsub(iso, (Real)p1[-sc]));
+					d0 = rsub(va, rsub(iso, (Real)ldro(p0 - sc)));
+					d1 = rsub(vb, rsub(iso, (Real)ldro(p1 - sc)));
 				}
 				r[3 + c] = radd(rmul(d0, one_t), rmul(d1, t));
 			}

@@ -165,7 +165,7 @@ __device__ __forceinline__ ClsChunk cls_chunk(const Params &P, const ClsPlan &pl
 	return k;
 }
 
-template <typename Sample>
+template <typename Sample, bool FLAT>
 __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -215,58 +215,58 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 		const int s = (int)(k % CLS_STAGES);
 		const uint32_t c = blockIdx.x + k * gridDim.x;
 		const ClsChunk ck = cls_chunk<Sample>(P, pl, c);
-		const bool whole = pl.nwchunk == 1;
-		// the row's old on-iso flag is fetched before waiting for the samples
-		const uint32_t rr0 = wid;
-		uint32_t zold_next = rr0 < ck.nrows ? P.rowZ[ck.lr0 + rr0] : 0u;
 		mbar_wait(&full[s], (k / CLS_STAGES) & 1);
 		const unsigned char *st = smem + (size_t)s * pl.stage_bytes + (((uint64_t)(uintptr_t)gbase + ck.b0) & 15);
-		// full (32 valid samples) words of this chunk's word range
-		const uint32_t nf = nfull > ck.w0 ? min(ck.nw, nfull - ck.w0) : 0u;
-		for (uint32_t rr = rr0; rr < ck.nrows; rr += CLS_THREADS / 32) {
-			const uint32_t lr = ck.lr0 + rr;
-			const bool zold = zold_next != 0;
-			if (rr + CLS_THREADS / 32 < ck.nrows) zold_next = P.rowZ[lr + CLS_THREADS / 32];
-			// sample x of this row sits at src[x - 32*w0]
-			const Sample *src = (const Sample *)st + (size_t)rr * P.NX + lane;
-			uint32_t *Sr = P.S + (uint64_t)lr * P.WP + ck.w0;    // 16-byte aligned (WP, w0 multiples of 4)
-			bool zl = false;                                  // this lane saw an on-iso sample
-			const Sample *q = src;
-			uint32_t g = 0;
-			for (; g + 4 <= nf; g += 4, q += 128) {
-				const Sample f0 = q[0], f1 = q[32], f2 = q[64], f3 = q[96];
-				uint4 b;
+		if (FLAT) {
+			// rows are a whole number of quads (NX % 128 == 0): the chunk is a flat run of
+			// 4-word groups; group gi holds samples 128*gi .. 128*gi+127 of the chunk
+			const uint32_t ngroups = ck.nrows * P.Q;
+			for (uint32_t gi = wid; gi < ngroups; gi += CLS_THREADS / 32) {
+				const uint32_t rr = fastdiv(gi, P.Q, P.mQ), q = gi - rr * P.Q;
+				const Sample *src = (const Sample *)st + ((size_t)gi << 7) + lane;
+				const Sample f0 = src[0], f1 = src[32], f2 = src[64], f3 = src[96];
+				uint4 b, e;
 				b.x = __ballot_sync(0xFFFFFFFFu, cls.gt(f0)); b.y = __ballot_sync(0xFFFFFFFFu, cls.gt(f1));
 				b.z = __ballot_sync(0xFFFFFFFFu, cls.gt(f2)); b.w = __ballot_sync(0xFFFFFFFFu, cls.gt(f3));
-				zl = zl || cls.eq(f0) || cls.eq(f1) || cls.eq(f2) || cls.eq(f3);
-				if (lane == 0) *reinterpret_cast<uint4 *>(Sr + g) = b;
-			}
-			for (; g < nf; g++, q += 32) {
-				const Sample f = q[0];
-				const uint32_t b = __ballot_sync(0xFFFFFFFFu, cls.gt(f));
-				zl = zl || cls.eq(f);
-				if (lane == 0) Sr[g] = b;
-			}
-			if (tail && g < ck.nw && ck.w0 + g == nfull) {     // the partial last word of the row
-				const bool ok = lane < tail;
-				const Sample f = ok ? q[0] : (Sample)0;
-				const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok && cls.gt(f));
-				zl = zl || (ok && cls.eq(f));
-				if (lane == 0) Sr[g] = b;
-			}
-			const bool zany = __any_sync(0xFFFFFFFFu, zl);
-			if (zany || zold || !whole) {                    // rare: (re)write this row's Z words
-				uint32_t *Zr = P.Z + (uint64_t)lr * P.WP + ck.w0;
-				for (uint32_t w = 0; w < ck.nw; w++) {
-					const uint32_t x = ((ck.w0 + w) << 5) + lane;
-					const bool ok = x < P.NX;
-					const Sample f = ok ? src[(size_t)w << 5] : (Sample)0;
-					const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok && cls.eq(f));
-					if (lane == 0) Zr[w] = b;
+				e.x = __ballot_sync(0xFFFFFFFFu, cls.eq(f0)); e.y = __ballot_sync(0xFFFFFFFFu, cls.eq(f1));
+				e.z = __ballot_sync(0xFFFFFFFFu, cls.eq(f2)); e.w = __ballot_sync(0xFFFFFFFFu, cls.eq(f3));
+				if (lane == 0) {
+					const uint64_t o = (uint64_t)(ck.lr0 + rr) * P.WP + 4 * q;
+					*reinterpret_cast<uint4 *>(P.S + o) = b;
+					*reinterpret_cast<uint4 *>(P.Z + o) = e;
+					if (e.x | e.y | e.z | e.w) { P.rowZ[ck.lr0 + rr] = P.zepoch; P.totals->anyZ = 1u; }
 				}
-				// pieces of one long row share the flag: it is only ever raised there
-				if (lane == 0 && (whole || zany)) P.rowZ[lr] = zany;
-				if (lane == 0 && zany) P.totals->anyZ = 1u;
+			}
+		} else {
+			// general shape: one warp per row (or piece of a long row), partial last word
+			const uint32_t nf = nfull > ck.w0 ? min(ck.nw, nfull - ck.w0) : 0u;   // words with 32 valid samples
+			for (uint32_t rr = wid; rr < ck.nrows; rr += CLS_THREADS / 32) {
+				const uint32_t lr = ck.lr0 + rr;
+				// sample x of this row sits at src[x - 32*w0]
+				const Sample *q = (const Sample *)st + (size_t)rr * P.NX + lane;
+				uint32_t *Sr = P.S + (uint64_t)lr * P.WP + ck.w0;    // 16-byte aligned (WP, w0 multiples of 4)
+				uint32_t *Zr = P.Z + (uint64_t)lr * P.WP + ck.w0;
+				uint32_t zacc = 0;
+				uint32_t g = 0;
+				for (; g + 4 <= nf; g += 4, q += 128) {
+					const Sample f0 = q[0], f1 = q[32], f2 = q[64], f3 = q[96];
+					uint4 b, e;
+					b.x = __ballot_sync(0xFFFFFFFFu, cls.gt(f0)); b.y = __ballot_sync(0xFFFFFFFFu, cls.gt(f1));
+					b.z = __ballot_sync(0xFFFFFFFFu, cls.gt(f2)); b.w = __ballot_sync(0xFFFFFFFFu, cls.gt(f3));
+					e.x = __ballot_sync(0xFFFFFFFFu, cls.eq(f0)); e.y = __ballot_sync(0xFFFFFFFFu, cls.eq(f1));
+					e.z = __ballot_sync(0xFFFFFFFFu, cls.eq(f2)); e.w = __ballot_sync(0xFFFFFFFFu, cls.eq(f3));
+					zacc |= e.x | e.y | e.z | e.w;
+					if (lane == 0) { *reinterpret_cast<uint4 *>(Sr + g) = b; *reinterpret_cast<uint4 *>(Zr + g) = e; }
+				}
+				for (; g < ck.nw; g++, q += 32) {             // remaining words, the last one maybe partial
+					const bool ok = g < nf || lane < tail;     // (g >= nf happens only for the row's partial last word)
+					const Sample f = ok ? q[0] : (Sample)0;
+					const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok && cls.gt(f));
+					const uint32_t e = __ballot_sync(0xFFFFFFFFu, ok && cls.eq(f));
+					zacc |= e;
+					if (lane == 0) { Sr[g] = b; Zr[g] = e; }
+				}
+				if (lane == 0 && zacc) { P.rowZ[lr] = P.zepoch; P.totals->anyZ = 1u; }
 			}
 		}
 		__syncthreads();                                     // every warp is done with stage s
@@ -315,7 +315,7 @@ __device__ __forceinline__ bool group_has_oniso(const Params &P, bool any, uint3
 	for (uint32_t i = lane; i < 3 * n; i += 32) {
 		const uint32_t dz = i / n, dy = i - dz * n;
 		const uint64_t row = (uint64_t)lr0 + dy + (uint64_t)dz * P.NY;
-		if (row < P.Lrows) f = f || P.rowZ[row] != 0;
+		if (row < P.Lrows) f = f || P.rowZ[row] == P.zepoch;
 	}
 	return __any_sync(0xFFFFFFFFu, f);
 }
@@ -346,13 +346,17 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const bool anyz = P.totals->anyZ != 0;
-	const uint32_t RB = CNT_WARPS * P.G;
+	const uint32_t GW = 32 / P.G;                    // groups per warp and block iteration: 32 rows per warp
+	const uint32_t RB = CNT_WARPS * GW * P.G;
 	const uint32_t npass = (P.Q + 31) / 32;
 
 	for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
 		s_row[0][threadIdx.x] = 0; s_row[1][threadIdx.x] = 0; s_row[2][threadIdx.x] = 0;
 		__syncthreads();
-		const uint32_t row0 = blk * RB + wid * P.G;
+	  for (uint32_t sub = 0; sub < GW; sub++) {
+		const uint32_t srow = (wid * GW + sub) * P.G;      // first row of the group within the block
+		const uint32_t row0 = blk * RB + srow;
+		if (row0 >= P.Lrows) break;
 		const bool gz = group_has_oniso(P, anyz, row0, lane);
 		uint64_t carryV = 0, carryT = 0;
 		for (uint32_t pass = 0; pass < npass; pass++) {
@@ -373,6 +377,7 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 						const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
 						const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
 						uint64_t pv[4];
+						uint32_t act[4];
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
 							WordRec rec;
@@ -380,9 +385,10 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 							quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c && hasZ, rec, c);
 							if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
 							pv[k] = pack_planes(rec);
-							if (rec.act) tt += count_cells<Sample>(P, tb, z, y, 4 * q + k, rec.act, c, c, 0u);
+							act[k] = rec.act;
 						}
 						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
+						if (act[0] | act[1] | act[2] | act[3]) tt = count_cells_quad<Sample>(P, tb, z, y, q, act, q00, q10, q01, q11);
 					} else {
 						uint64_t pv[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -425,9 +431,9 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 				if (q == P.Q - 1) {
 					const uint64_t rowT = carryT + it - rst;
 					pw[4] = lv + tv;
-					s_row[0][wid * P.G + r] = P.Q <= 32 ? fldV(lv + tv, 2) : sumV(lv + tv);
-					s_row[1][wid * P.G + r] = (uint32_t)rowT;
-					s_row[2][wid * P.G + r] = (uint32_t)(rowT >> 32);
+					s_row[0][srow + r] = P.Q <= 32 ? fldV(lv + tv, 2) : sumV(lv + tv);
+					s_row[1][srow + r] = (uint32_t)rowT;
+					s_row[2][srow + r] = (uint32_t)(rowT >> 32);
 				}
 			}
 			if (P.Q > 32) { carryV += __shfl_sync(0xFFFFFFFFu, iv, 31); carryT += __shfl_sync(0xFFFFFFFFu, it, 31); }
@@ -437,6 +443,7 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 			const uint64_t add = plane_offsets(carryV);
 			for (uint32_t i = lane; i <= 4 * P.Q; i += 32) P.wpreV[(uint64_t)row0 * P.WP + i] += add;
 		}
+	  }
 		__syncthreads();
 		// CTA-relative row bases
 		{
@@ -458,7 +465,7 @@ __global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t
 // and turns the CTA-relative row bases into slab-local ones: the implicit running
 // M->nV++ / nT++ of the reference (marching_cubes_33.c:487, :1245).
 // ---------------------------------------------------------------------------
-#define RS_BLOCKS 32     // k_count blocks per k_rowscan CTA
+#define RS_BLOCKS 4      // k_count blocks per k_rowscan CTA
 
 __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32_t RB, const uint32_t *blkSum, uint32_t owned_end_row)
 {
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(256) k_emit_vertices(Params P, uint32_t row_be
 					q10 = y < P.ny ? load_quad(P.S, i00 + P.WP) : q00;
 					q01 = z < P.nz ? load_quad(P.S, i00 + (uint64_t)P.NY * P.WP) : q00;
 				}
-				const bool zrow = gz && P.rowZ[lr];
+				const bool zrow = gz && P.rowZ[lr] == P.zepoch;
 				const uint64_t pk[4] = {pa.x, pa.y, pc.x, pc.y};
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
@@ -600,6 +607,7 @@ __global__ void __launch_bounds__(256) k_emit_vertices(Params P, uint32_t row_be
 			}
 			__syncwarp();
 			const uint32_t nt = min((uint32_t)VQ, vend - win0);
+#pragma unroll 2
 			for (uint32_t t = lane; t < nt; t += 32) {
 				const uint32_t e = vq[t];
 				const uint32_t lr = lr0 + (e >> 19);
@@ -847,7 +855,8 @@ static int set_geom(mc33cu_ctx *c, const mc33cu_desc *d);
 
 template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 {
-	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES)));
+	CU((cudaFuncSetAttribute(k_classify<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES))));
+	CU((cudaFuncSetAttribute(k_classify<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES))));
 	CU(cudaFuncSetAttribute(k_emit_cells<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
 	return MC33CU_OK;
 }
@@ -901,7 +910,7 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	c->sample_size = ssz[d->dtype];
 	c->real_size = d->dtype == MC33CU_F64 ? 8 : 4;
 	c->n_samples = (uint64_t)P.Lrows * P.NX;
-	c->nblk = (P.Lrows + CNT_WARPS * P.G - 1) / (CNT_WARPS * P.G);
+	c->nblk = (P.Lrows + CNT_WARPS * (32 / P.G) * P.G - 1) / (CNT_WARPS * (32 / P.G) * P.G);
 	{
 		// classify chunks: ~16 KB of whole rows (a multiple of the CTA's warp count
 		// when possible), or 16 KB pieces of one long row (a multiple of 4 words)
@@ -938,7 +947,8 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	TRY(dalloc(&P.S, bm)); TRY(dalloc(&P.Z, bm));
 	TRYCU(cudaMemsetAsync(P.S, 0, bm * 4, c->stream)); TRYCU(cudaMemsetAsync(P.Z, 0, bm * 4, c->stream));
 	TRY(dalloc(&P.rowZ, (size_t)P.Lrows));
-	TRYCU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows, c->stream));
+	TRYCU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows * 4, c->stream));
+	P.zepoch = 0;
 	TRY(dalloc(&P.wpreV, (size_t)P.Lrows * P.WP));
 	TRYCU(cudaMemsetAsync(P.wpreV, 0, (size_t)P.Lrows * P.WP * 8, c->stream));
 	TRY(dalloc(&P.rowBV, ((size_t)P.Lrows + 1) * 3));
@@ -1061,8 +1071,9 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 {
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
-	// re-arm the totals (overflow / on-iso flags)
+	// re-arm the totals (overflow / on-iso flags); a new epoch invalidates the per-row on-iso hints
 	CU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), s));
+	if (++P.zepoch == 0) { CU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows * 4, s)); P.zepoch = 1; }
 	if (c->timing) CU(cudaEventRecord(c->ev[0], s));
 	{
 		const ClsPlan &pl = c->cls;
@@ -1072,7 +1083,8 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 		if (per_sm > 8) per_sm = 8;
 		uint32_t grid = (uint32_t)c->n_sm * per_sm;
 		if (grid > pl.nchunks) grid = pl.nchunks;
-		k_classify<Sample><<<grid, CLS_THREADS, smem, s>>>(P, pl);
+		if (pl.nwchunk == 1 && P.NX % 128 == 0) k_classify<Sample, true><<<grid, CLS_THREADS, smem, s>>>(P, pl);
+		else k_classify<Sample, false><<<grid, CLS_THREADS, smem, s>>>(P, pl);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
@@ -1085,7 +1097,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 	if (c->timing) CU(cudaEventRecord(c->ev[2], s));
 	{
 		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
-		k_rowscan<<<(c->nblk + RS_BLOCKS - 1) / RS_BLOCKS, 256, 0, s>>>(P, c->nblk, CNT_WARPS * P.G, c->blk_sum, owned_end);
+		k_rowscan<<<(c->nblk + RS_BLOCKS - 1) / RS_BLOCKS, 256, 0, s>>>(P, c->nblk, CNT_WARPS * (32 / P.G) * P.G, c->blk_sum, owned_end);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[3], s));

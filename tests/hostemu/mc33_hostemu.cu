@@ -42,7 +42,7 @@ static void run(Params &P, bool emit)
 			P.Z[(uint64_t)lr * P.WP + w] = z;
 			anyz |= z != 0;
 		}
-		P.rowZ[lr] = anyz;
+		P.rowZ[lr] = anyz ? P.zepoch : 0u;
 		if (anyz) P.totals->anyZ = 1;
 	}
 	const bool gz = P.totals->anyZ != 0;
@@ -76,7 +76,17 @@ static void run(Params &P, bool emit)
 					if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
 					if (!own_c) rec.act = 0;
 					cv = pack_planes(rec);
-					cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
+					if (gz) {
+						cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
+					} else {
+						// the kernel's merged walk over the quad: give it this word's cells only
+						uint32_t act4[4] = {0, 0, 0, 0};
+						act4[w & 3] = rec.act;
+						const bool hasY = y < P.ny, hasZ = z < P.nz;
+						const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u, i00 = (uint64_t)lr * P.WP + (w & ~3u);
+						cc = count_cells_quad<Sample>(P, tb, z, y, w >> 2, act4, load_quad(P.S, i00), load_quad(P.S, i00 + dY),
+						                              load_quad(P.S, i00 + dZ), load_quad(P.S, i00 + dY + dZ));
+					}
 				}
 				P.wpreV[(uint64_t)lr * P.WP + w] = av;
 				av += cv; ac += cc;
@@ -98,7 +108,7 @@ static void run(Params &P, bool emit)
 		for (uint32_t w = 0; w < P.W; w++) {
 			WordRec rec; CellWords cw;
 			word_rec(z, y, w, rec, cw);
-			const uint32_t zw = (gz && P.rowZ[lr]) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
+			const uint32_t zw = (gz && P.rowZ[lr] == P.zepoch) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
 			for (int a = 0; a < 3; a++) {
 				uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
 				uint32_t id = plane_base_local(P, lr, w, a);
@@ -188,7 +198,8 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	for (int i = 0; i < 9; i++) { P.geom.A[i] = d->A[i]; P.geom.Ai[i] = d->Ai[i]; }
 	P.iso = d->dtype == MC33CU_F64 ? iso + 0.0 : (double)((float)iso + 0.0f);
 	std::vector<uint32_t> S((size_t)P.Lrows * P.WP, 0), Z((size_t)P.Lrows * P.WP, 0), rb(((size_t)P.Lrows + 1) * 3);
-	std::vector<uint8_t> rz(P.Lrows);
+	std::vector<uint32_t> rz(P.Lrows);
+	P.zepoch = 1;
 	std::vector<uint64_t> wv((size_t)P.Lrows * P.WP);
 	Totals tot;
 	memset(&tot, 0, sizeof tot);
