@@ -296,7 +296,7 @@ def run_ours(args):
             kt += np.array(ex.kernel_times())
     ex.timing(False)
     kt /= reps * len(ISOS)
-    knames = ["classify", "count", "rowscan", "emit_vertices", "emit_cells"]
+    knames = ["classify", "count", "rowscan", "emit_cells", "emit_vertices"]
     dom = int(np.argmax(kt))
 
     # ---- algorithmic bytes: grid read once + mesh written once -------

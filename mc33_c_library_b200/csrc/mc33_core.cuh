@@ -745,8 +745,13 @@ MC_HD void store_vertex(const Params &P, Real *r, uint32_t id)
 		for (int i = 0; i < 3; i++) p[i] = radd(rmul(r[i], (Real)g.D[i]), (Real)g.O[i]);
 	}
 	Real s = radd(radd(rmul(r[3], r[3]), rmul(r[4], r[4])), rmul(r[5], r[5]));
-	// exact 1/sqrt: the reference's rsqrtss is only good to 3e-4
+	// the reference's rsqrtss is only good to 3e-4; the device uses the
+	// hardware reciprocal square root (2 ulp), the host emulation the exact quotient
+#if defined(__CUDA_ARCH__)
+	float t = rsqrtf((float)s);
+#else
 	float t = rdiv(1.0f, sqrtf((float)s));
+#endif
 	if (g.normal_neg) t = -t;
 	Real *V = (Real *)P.V + 3 * (uint64_t)id;
 	float *N = P.N + 3 * (uint64_t)id;

@@ -165,7 +165,7 @@ __device__ __forceinline__ ClsChunk cls_chunk(const Params &P, const ClsPlan &pl
 	return k;
 }
 
-template <typename Sample, bool FLAT>
+template <typename Sample>
 __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -215,29 +215,12 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 		const int s = (int)(k % CLS_STAGES);
 		const uint32_t c = blockIdx.x + k * gridDim.x;
 		const ClsChunk ck = cls_chunk<Sample>(P, pl, c);
-		mbar_wait(&full[s], (k / CLS_STAGES) & 1);
+		// one warp polls the barrier, the others sleep at the CTA barrier (256 polling
+		// threads were taking issue slots from the warps still classifying)
+		if (wid == 0) mbar_wait(&full[s], (k / CLS_STAGES) & 1);
+		__syncthreads();
 		const unsigned char *st = smem + (size_t)s * pl.stage_bytes + (((uint64_t)(uintptr_t)gbase + ck.b0) & 15);
-		if (FLAT) {
-			// rows are a whole number of quads (NX % 128 == 0): the chunk is a flat run of
-			// 4-word groups; group gi holds samples 128*gi .. 128*gi+127 of the chunk
-			const uint32_t ngroups = ck.nrows * P.Q;
-			for (uint32_t gi = wid; gi < ngroups; gi += CLS_THREADS / 32) {
-				const uint32_t rr = fastdiv(gi, P.Q, P.mQ), q = gi - rr * P.Q;
-				const Sample *src = (const Sample *)st + ((size_t)gi << 7) + lane;
-				const Sample f0 = src[0], f1 = src[32], f2 = src[64], f3 = src[96];
-				uint4 b, e;
-				b.x = __ballot_sync(0xFFFFFFFFu, cls.gt(f0)); b.y = __ballot_sync(0xFFFFFFFFu, cls.gt(f1));
-				b.z = __ballot_sync(0xFFFFFFFFu, cls.gt(f2)); b.w = __ballot_sync(0xFFFFFFFFu, cls.gt(f3));
-				e.x = __ballot_sync(0xFFFFFFFFu, cls.eq(f0)); e.y = __ballot_sync(0xFFFFFFFFu, cls.eq(f1));
-				e.z = __ballot_sync(0xFFFFFFFFu, cls.eq(f2)); e.w = __ballot_sync(0xFFFFFFFFu, cls.eq(f3));
-				if (lane == 0) {
-					const uint64_t o = (uint64_t)(ck.lr0 + rr) * P.WP + 4 * q;
-					*reinterpret_cast<uint4 *>(P.S + o) = b;
-					*reinterpret_cast<uint4 *>(P.Z + o) = e;
-					if (e.x | e.y | e.z | e.w) { P.rowZ[ck.lr0 + rr] = P.zepoch; P.totals->anyZ = 1u; }
-				}
-			}
-		} else {
+		{
 			// general shape: one warp per row (or piece of a long row), partial last word
 			const uint32_t nf = nfull > ck.w0 ? min(ck.nw, nfull - ck.w0) : 0u;   // words with 32 valid samples
 			for (uint32_t rr = wid; rr < ck.nrows; rr += CLS_THREADS / 32) {
@@ -268,6 +251,104 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 				}
 				if (lane == 0 && zacc) { P.rowZ[lr] = P.zepoch; P.totals->anyZ = 1u; }
 			}
+		}
+		__syncthreads();                                     // every warp is done with stage s
+		if (k + CLS_STAGES < nmine) issue(blockIdx.x + (k + CLS_STAGES) * gridDim.x, s);
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K1, vector form: rows of whole NW-word groups and 16-byte aligned samples (the
+// common power-of-two grids).  Same TMA ring; a lane reads 16 bytes = NS
+// consecutive samples per load and turns them into NS bits, the LW = 32/NS lanes
+// whose bits make up one bitmap word OR them together with log2(LW) butterfly
+// shuffles, and a warp iteration covers NW words (f32: 128 samples with a single
+// LDS.128).  Every warp takes a contiguous run of its chunk's iterations.
+// ---------------------------------------------------------------------------
+template <typename Sample>
+__global__ void __launch_bounds__(CLS_THREADS) k_classify_vec(Params P, uint32_t rows, uint32_t nchunks, uint32_t stage_bytes)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ uint64_t full[CLS_STAGES];
+	constexpr int NS = 16 / (int)sizeof(Sample);       // samples per 16-byte load
+	constexpr int NL = NS >= 4 ? 1 : 4 / NS;            // loads per iteration (f64: 2)
+	constexpr int NW = NS * NL;                         // words per iteration
+	constexpr int LW = 32 / NS;                         // lanes per word
+	const Cls<Sample> cls(P);
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const char *gbase = (const char *)P.data;
+	const uint32_t rowb = P.NX * (uint32_t)sizeof(Sample), chunkb = rows * rowb;
+	const uint32_t gpr = P.W / NW;                      // iterations per row
+	const uint32_t ipw = (rows * gpr + CLS_THREADS / 32 - 1) / (CLS_THREADS / 32);   // iterations per warp and chunk
+	const uint32_t i0 = wid * ipw, r0 = i0 / gpr, g0 = i0 - r0 * gpr;
+	const unsigned sh = NS * (lane % LW);
+	uint32_t *const Sb = P.S, *const Zb = P.Z;
+	const uint32_t WP = P.WP, Lrows = P.Lrows;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < CLS_STAGES; s++) mbar_init(&full[s], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+	auto issue = [&](uint32_t c, int s) {
+		if (threadIdx.x == 0) {
+			const uint32_t lr0 = c * rows;
+			const uint32_t bytes = (lr0 + rows <= Lrows ? rows : Lrows - lr0) * rowb;
+			mbar_arrive_expect_tx(&full[s], bytes);
+			bulk_g2s(smem + (size_t)s * stage_bytes, gbase + (uint64_t)c * chunkb, bytes, &full[s]);
+		}
+	};
+	const uint32_t nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	for (uint32_t k = 0; k < CLS_STAGES && k < nmine; k++) issue(blockIdx.x + k * gridDim.x, (int)k);
+
+	for (uint32_t k = 0; k < nmine; k++) {
+		const int s = (int)(k % CLS_STAGES);
+		const uint32_t lr0 = (blockIdx.x + k * gridDim.x) * rows;
+		const uint32_t nit = (lr0 + rows <= Lrows ? rows : Lrows - lr0) * gpr;
+		mbar_wait(&full[s], (k / CLS_STAGES) & 1);
+		const uint4 *src = reinterpret_cast<const uint4 *>(smem + (size_t)s * stage_bytes) + (size_t)i0 * (32 * NL) + lane;
+		uint32_t gq = g0, o = (lr0 + r0) * WP + g0 * NW;
+		const uint32_t i1 = min(i0 + ipw, nit);
+		for (uint32_t it = i0; it < i1; it++, src += 32 * NL) {
+			uint32_t wS[NL];
+			bool eqa = false;
+			uint4 raw[NL];
+#pragma unroll
+			for (int j = 0; j < NL; j++) raw[j] = src[32 * j];
+#pragma unroll
+			for (int j = 0; j < NL; j++) {
+				const Sample *f = reinterpret_cast<const Sample *>(&raw[j]);
+				uint32_t nb = 0;
+#pragma unroll
+				for (int i = 0; i < NS; i++) { nb |= (uint32_t)cls.gt(f[i]) << i; eqa = eqa || cls.eq(f[i]); }
+				uint32_t v = nb << sh;
+#pragma unroll
+				for (int d = LW / 2; d; d >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+				wS[j] = v;
+			}
+			// lane l holds word (l / LW) of load j: the first lane of each segment stores it
+			if (lane % LW == 0) {
+#pragma unroll
+				for (int j = 0; j < NL; j++) Sb[o + j * NS + lane / LW] = wS[j];
+			}
+			if (__any_sync(0xFFFFFFFFu, eqa)) {
+#pragma unroll
+				for (int j = 0; j < NL; j++) {
+					const Sample *f = reinterpret_cast<const Sample *>(&raw[j]);
+					uint32_t nb = 0;
+#pragma unroll
+					for (int i = 0; i < NS; i++) nb |= (uint32_t)cls.eq(f[i]) << i;
+					uint32_t v = nb << sh;
+#pragma unroll
+					for (int d = LW / 2; d; d >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+					if (lane % LW == 0) Zb[o + j * NS + lane / LW] = v;
+				}
+				if (lane == 0) { P.rowZ[o / WP] = P.zepoch; P.totals->anyZ = 1u; }
+			} else if (lane < NW) {
+				Zb[o + lane] = 0u;
+			}
+			o += NW;
+			if (++gq == gpr) { gq = 0; o += WP - gpr * NW; }
 		}
 		__syncthreads();                                     // every warp is done with stage s
 		if (k + CLS_STAGES < nmine) issue(blockIdx.x + (k + CLS_STAGES) * gridDim.x, s);
@@ -338,7 +419,7 @@ __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32
 #define CNT_WARPS 8
 
 template <typename Sample>
-__global__ void __launch_bounds__(256) k_count(Params P, uint32_t nblk, uint32_t *blkSum)
+__global__ void __launch_bounds__(256, 4) k_count(Params P, uint32_t nblk, uint32_t *blkSum)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
@@ -534,7 +615,7 @@ __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32
 // (the two halves are separate kernels: fused, the hot code no longer fitted the
 // instruction cache and 70 % of the warp stalls were instruction fetches)
 template <typename Sample>
-__global__ void __launch_bounds__(256) k_emit_vertices(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, 4) k_emit_vertices(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
 	__shared__ uint32_t s_vq[EM_WARPS * VQ];
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -620,7 +701,7 @@ __global__ void __launch_bounds__(256) k_emit_vertices(Params P, uint32_t row_be
 }
 
 template <typename Sample>
-__global__ void __launch_bounds__(256) k_emit_cells(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, 4) k_emit_cells(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const Tables tb = load_tables(smem);
@@ -788,6 +869,8 @@ struct mc33cu_ctx {
 	int device;
 	int n_sm;
 	cudaStream_t own_stream, stream;
+	cudaStream_t side_stream;            // emit_cells runs beside emit_vertices
+	cudaEvent_t ev_fork, ev_join;
 	Params P;
 	ClsPlan cls;
 	size_t sample_size, real_size;
@@ -847,6 +930,9 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	if (c->pinned) cudaFreeHost(c->pinned);
 	if (c->h_totals) cudaFreeHost(c->h_totals);
 	for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	free(c);
 }
@@ -855,8 +941,8 @@ static int set_geom(mc33cu_ctx *c, const mc33cu_desc *d);
 
 template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 {
-	CU((cudaFuncSetAttribute(k_classify<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES))));
-	CU((cudaFuncSetAttribute(k_classify<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES))));
+	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES)));
+	CU(cudaFuncSetAttribute(k_classify_vec<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES)));
 	CU(cudaFuncSetAttribute(k_emit_cells<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
 	return MC33CU_OK;
 }
@@ -943,6 +1029,9 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	return fail(e_ == cudaErrorMemoryAllocation ? MC33CU_ERR_NOMEM : MC33CU_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
 	TRYCU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
+	TRYCU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+	TRYCU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	TRYCU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	const size_t bm = (size_t)P.Lrows * P.WP;
 	TRY(dalloc(&P.S, bm)); TRY(dalloc(&P.Z, bm));
 	TRYCU(cudaMemsetAsync(P.S, 0, bm * 4, c->stream)); TRYCU(cudaMemsetAsync(P.Z, 0, bm * 4, c->stream));
@@ -1067,6 +1156,26 @@ extern "C" int mc33cu_grid_upload_rows(mc33cu_ctx *c, const void *const *const *
 }
 
 // ---------------------------------------------------------------------------
+template <typename Sample> static int launch_classify(mc33cu_ctx *c)
+{
+	Params &P = c->P;
+	cudaStream_t s = c->stream;
+	const ClsPlan &pl = c->cls;
+	const size_t smem = (size_t)pl.stage_bytes * CLS_STAGES;
+	uint32_t per_sm = (uint32_t)((220u << 10) / (smem + 1024));
+	if (per_sm < 1) per_sm = 1;
+	if (per_sm > 8) per_sm = 8;
+	uint32_t grid = (uint32_t)c->n_sm * per_sm;
+	if (grid > pl.nchunks) grid = pl.nchunks;
+	// vector path: rows of whole NW-word groups, 16-byte aligned samples
+	const uint32_t nwv = sizeof(Sample) >= 4 ? 4u : 16u / (uint32_t)sizeof(Sample);
+	if (pl.nwchunk == 1 && P.NX % (32 * nwv) == 0 && ((uintptr_t)P.data & 15) == 0)
+		k_classify_vec<Sample><<<grid, CLS_THREADS, smem, s>>>(P, pl.rows, pl.nchunks, pl.stage_bytes);
+	else k_classify<Sample><<<grid, CLS_THREADS, smem, s>>>(P, pl);
+	c->launches++;
+	return MC33CU_OK;
+}
+
 template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 {
 	Params &P = c->P;
@@ -1075,18 +1184,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 	CU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), s));
 	if (++P.zepoch == 0) { CU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows * 4, s)); P.zepoch = 1; }
 	if (c->timing) CU(cudaEventRecord(c->ev[0], s));
-	{
-		const ClsPlan &pl = c->cls;
-		const size_t smem = (size_t)pl.stage_bytes * CLS_STAGES;
-		uint32_t per_sm = (uint32_t)((220u << 10) / (smem + 1024));
-		if (per_sm < 1) per_sm = 1;
-		if (per_sm > 8) per_sm = 8;
-		uint32_t grid = (uint32_t)c->n_sm * per_sm;
-		if (grid > pl.nchunks) grid = pl.nchunks;
-		if (pl.nwchunk == 1 && P.NX % 128 == 0) k_classify<Sample, true><<<grid, CLS_THREADS, smem, s>>>(P, pl);
-		else k_classify<Sample, false><<<grid, CLS_THREADS, smem, s>>>(P, pl);
-		c->launches++;
-	}
+	launch_classify<Sample>(c);
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
 	{
 		uint32_t grid = (uint32_t)c->n_sm * 8;
@@ -1109,24 +1207,33 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 {
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
+	// The two emit kernels only depend on the count phase, and they stall on different
+	// things (vertices: sample gathers; cells: instruction issue), so they run side by
+	// side: cells on the side stream, forked and joined with events.  With per-kernel
+	// timing enabled they run one after the other instead.
+	const bool fork = !c->timing;
+	cudaStream_t sc = fork ? c->side_stream : s;
+	if (fork) { CU(cudaEventRecord(c->ev_fork, s)); CU(cudaStreamWaitEvent(sc, c->ev_fork, 0)); }
 	{
-		// rows whose vertices this slab owns
-		const uint32_t rb = (P.pz0 - P.zlo) * P.NY, re = (P.pz1 - P.zlo) * P.NY;
+		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (P.cz1 - P.zlo) * P.NY;
 		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
-		uint32_t grid = (uint32_t)c->n_sm * 6;
+		// (side by side: two resident CTAs of each kernel per SM, so that both really co-run)
+		uint32_t grid = (uint32_t)c->n_sm * 4;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		k_emit_vertices<Sample><<<grid, 256, 0, s>>>(P, rb, re, ngroups);
+		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, sc>>>(P, rb, re, ngroups);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[4], s));
 	{
-		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (P.cz1 - P.zlo) * P.NY;
+		// rows whose vertices this slab owns
+		const uint32_t rb = (P.pz0 - P.zlo) * P.NY, re = (P.pz1 - P.zlo) * P.NY;
 		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
-		uint32_t grid = (uint32_t)c->n_sm * 6;
+		uint32_t grid = (uint32_t)c->n_sm * 4;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups);
+		k_emit_vertices<Sample><<<grid, 256, 0, s>>>(P, rb, re, ngroups);
 		c->launches++;
 	}
+	if (fork) { CU(cudaEventRecord(c->ev_join, sc)); CU(cudaStreamWaitEvent(s, c->ev_join, 0)); }
 	if (c->timing) { CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
 	CU(cudaGetLastError());
 	return MC33CU_OK;
@@ -1343,6 +1450,20 @@ extern "C" int mc33cu_kernel_times(mc33cu_ctx *c, float ms[5])
 	CU(cudaEventSynchronize(c->ev[5]));
 	for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
 	return MC33CU_OK;
+}
+
+// measurement hook (tools/ only, not declared in include/mc33cu.h): the classify kernel alone
+extern "C" int mc33cu_debug_classify(mc33cu_ctx *c, double iso)
+{
+	if (!c || !c->P.data) return MC33CU_ERR_ARG;
+	set_iso(c, iso);
+	switch (c->d.dtype) {
+	case MC33CU_F32: return launch_classify<float>(c);
+	case MC33CU_F64: return launch_classify<double>(c);
+	case MC33CU_U8:  return launch_classify<uint8_t>(c);
+	case MC33CU_U16: return launch_classify<uint16_t>(c);
+	default:         return launch_classify<uint32_t>(c);
+	}
 }
 
 extern "C" uint64_t mc33cu_launch_count(const mc33cu_ctx *c) { return c ? c->launches : 0; }
