@@ -139,8 +139,10 @@ int  mc33cu_emit_host(mc33cu_ctx *ctx, void *V, float *N, int32_t *color, uint32
                       int32_t color_value);
 
 /* per-kernel device times of the most recent extraction, in milliseconds:
- * [0] classify [1] count [2] scan [3] emit vertices [4] emit triangles.
- * Only measured while timing is enabled (adds event records between kernels). */
+ * [0] classify [1] count [2] row scan [3] emit cells (triangles + centre vertices)
+ * [4] emit vertices.  Only measured while timing is enabled: event records between
+ * the kernels, and the two emit kernels then run one after the other instead of
+ * side by side on two streams. */
 int  mc33cu_enable_timing(mc33cu_ctx *ctx, int on);
 int  mc33cu_kernel_times(mc33cu_ctx *ctx, float ms[5]);
 /* number of kernel launches issued by this context so far */

@@ -102,6 +102,86 @@ def test_sparse_on_iso_samples_mix_fast_and_generic_paths():
     _same(oracle_extract(d, float(iso), "f64"), gpu_extract(d, float(iso), "f64"))
 
 
+@pytest.mark.parametrize("variant,shape,iso,scale", [("f32", (5, 9, 128), 0.0, 0), ("f32", (4, 6, 512), 0.1, 0),
+                                                      ("f64", (5, 7, 128), 0.0, 0), ("u16", (5, 6, 256), 500.5, 1000),
+                                                      ("u16", (4, 5, 512), 3.0, 7), ("u8", (4, 5, 512), 2.5, 6),
+                                                      ("u8", (3, 4, 1024), 3.0, 6)])
+def test_vector_classify_shapes(variant, shape, iso, scale):
+    """row lengths that take the 16-byte vector classify kernel (whole NW-word groups)"""
+    a = noise_grid(0, variant, scale=scale, shape=shape)
+    _same(oracle_extract(a, iso, variant), gpu_extract(a, iso, variant))
+
+
+@pytest.mark.parametrize("variant,shape,iso,scale", [("f32", (3, 4, 4200), 0.0, 0), ("u8", (3, 3, 4500), 2.0, 5),
+                                                      ("f32", (3, 3, 5000), 0.2, 0), ("f64", (2, 3, 4224), 0.0, 0)])
+def test_long_rows(variant, shape, iso, scale):
+    """rows of more than 128 words (a warp walks them in passes) and rows longer than a classify chunk"""
+    a = noise_grid(0, variant, scale=scale, shape=shape)
+    _same(oracle_extract(a, iso, variant), gpu_extract(a, iso, variant))
+
+
+def test_cfg5_like_inclined_noise():
+    """BASELINE config 5 in small: white noise (every ambiguous sub-case) on an inclined grid"""
+    a = noise_grid(0, "f32", shape=(40, 37, 128))
+    g = inclined_geom()
+    _same(oracle_extract(a, 0.0, "f32", g), gpu_extract(a, 0.0, "f32", g))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("variant,iso,scale,shape", [("f32", 0.0, 0, (37, 20, 128)), ("u8", 2.0, 4, (23, 9, 40))])
+def test_zslabs_on_gpu_match_single_extraction(world, variant, iso, scale, shape):
+    """BASELINE config 4's decomposition in small: every z-slab through its own context
+    (halo slices, ids of the seam slice in the next slab's space), merged == oracle"""
+    import torch
+    from mc33_c_library_b200 import slabs
+    from mc33_c_library_b200.device import Extractor
+    from support import merge_slab_meshes
+    a = noise_grid(0, variant, scale=scale, shape=shape)
+    whole = oracle_extract(a, iso, variant)
+    parts = [s for s in slabs.partition(a.shape[0] - 1, world) if s is not None]
+    exs, counts = [], []
+    for s in parts:
+        ex = Extractor(make_desc(a.shape, variant, None, s))
+        ex.upload(np.ascontiguousarray(a[s.z_lo:s.z_hi]))
+        exs.append(ex)
+        counts.append(ex.count(iso))
+    bases = slabs.bases([(int(k.nV), int(k.nT)) for k in counts])
+    meshes = []
+    for ex, k, (vb, vbn) in zip(exs, counts, bases):
+        b = ex.alloc(int(k.nV), int(k.nT), keys=True)
+        ex.emit(b, vbase=vb, vbase_next=vbn)
+        ex.sync()
+        nV, nT = int(k.nV), int(k.nT)
+        meshes.append(Mesh(b["V"][:nV].cpu().numpy(), b["N"][:nV].cpu().numpy(), b["T"][:nT].cpu().numpy().view(np.uint32),
+                           vkey=b["vkey"][:nV].cpu().numpy().astype(np.uint64), tcell=b["tcell"][:nT].cpu().numpy().astype(np.uint64),
+                           nShared=int(k.nShared), nCentre=int(k.nCentre)))
+        ex.close()
+    m = merge_slab_meshes(meshes)
+    assert (m.nV, m.nT) == (whole.nV, whole.nT)
+    assert np.array_equal(m.tcell, whole.tcell)
+    om, ow = np.argsort(m.vkey, kind="stable"), np.argsort(whole.vkey, kind="stable")
+    assert np.array_equal(m.vkey[om], whole.vkey[ow])
+    inv = np.empty(m.nV, np.int64); inv[om] = ow
+    assert np.array_equal(inv[m.T.astype(np.int64)], whole.T.astype(np.int64))
+    assert np.array_equal(m.V[om], whole.V[ow])
+    fa, fb = np.isfinite(m.N[om]), np.isfinite(whole.N[ow])        # zero gradients give NaN normals on both sides
+    assert np.array_equal(fa, fb)
+    assert np.abs(np.where(fa, m.N[om], 0) - np.where(fb, whole.N[ow], 0)).max() <= 1e-6
+
+
+def test_repeated_extractions_reuse_state():
+    """iso sweep on one context: bitmaps, on-iso hints and prefixes of an earlier isovalue must not leak"""
+    from mc33_c_library_b200.device import Extractor
+    a = noise_grid(0, "u8", scale=5, shape=(20, 21, 128))
+    ex = Extractor(make_desc(a.shape, "u8"))
+    ex.upload(a)
+    for iso in (2.0, 2.5, 1.0, 3.5, 2.0, 0.5):
+        r = ex.extract(iso, keys=True)
+        g = Mesh(r["V"], r["N"], r["T"], color=r["color"], vkey=r["vkey"], tcell=r["tcell"])
+        _same(oracle_extract(a, iso, "u8"), g)
+    ex.close()
+
+
 def test_plateaus_and_empty():
     rng = np.random.default_rng(3)
     a = rng.integers(0, 3, size=(20, 22, 67)).astype(np.uint8)
