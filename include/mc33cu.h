@@ -17,6 +17,7 @@
  */
 #ifndef MC33CU_H
 #define MC33CU_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -137,6 +138,13 @@ int  mc33cu_get_counts(mc33cu_ctx *ctx, mc33cu_counts *counts);
  * counts.nV / counts.nT entries (device staging is owned by the context). */
 int  mc33cu_emit_host(mc33cu_ctx *ctx, void *V, float *N, int32_t *color, uint32_t *T,
                       int32_t color_value);
+
+/* Page-locked host memory for result arrays, pooled across calls (device-to-host
+ * copies into it run at PCIe speed).  mc33cu_host_free returns MC33CU_ERR_ARG for a
+ * pointer that did not come from mc33cu_host_alloc, so a caller holding arrays of
+ * either origin can fall back to free(). */
+int  mc33cu_host_alloc(size_t bytes, void **out);
+int  mc33cu_host_free(void *p);
 
 /* per-kernel device times of the most recent extraction, in milliseconds:
  * [0] classify [1] count [2] row scan [3] emit cells (triangles + centre vertices)

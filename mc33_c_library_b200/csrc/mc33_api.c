@@ -216,10 +216,27 @@ _GRD *generate_grid_from_fn(double xi, double yi, double zi, double xf, double y
 /* ------------------------------------------------------------------------- */
 /* surfaces: reference marching_cubes_33.c:84-127                             */
 /* ------------------------------------------------------------------------- */
+/* Result arrays come from the C-ABI's pool of page-locked memory (so that the
+ * device-to-host copies run at PCIe speed) with plain malloc as the fallback;
+ * either kind is released here.  The reference's contract is kept: the arrays are
+ * ordinary writable host memory owned by the library and released through
+ * free_surface_memory. */
+static void *result_alloc(size_t bytes)
+{
+	void *p = 0;
+	if (!getenv("MC33_B200_NO_PIN") && mc33cu_host_alloc(bytes, &p) == MC33CU_OK && p) return p;
+	return malloc(bytes ? bytes : 1);
+}
+
+static void result_free(void *p)
+{
+	if (p && mc33cu_host_free(p) != MC33CU_OK) free(p);
+}
+
 void free_surface_memory(surface *S)
 {
 	if (!S) return;
-	free(S->T); free(S->V); free(S->N); free(S->color);
+	result_free(S->T); result_free(S->V); result_free(S->N); result_free(S->color);
 	free(S);
 }
 
@@ -228,7 +245,7 @@ static int shrink(void **p, size_t bytes)
 	void *q = malloc(bytes ? bytes : 1);
 	if (!q) return -1;
 	memcpy(q, *p, bytes);
-	free(*p);
+	result_free(*p);
 	*p = q;
 	return 0;
 }
@@ -385,10 +402,10 @@ surface *calculate_isosurface(MC33 *M, MC33_real iso)
 	S->nV = (unsigned int)k.nV; S->nT = (unsigned int)k.nT;
 	S->capv = S->nV; S->capt = S->nT ? S->nT : 1;
 	S->iso = iso;
-	S->T = (unsigned int (*)[3])malloc((size_t)S->capt * 3 * sizeof(int));
-	S->V = (MC33_real (*)[3])malloc((size_t)S->capv * 3 * sizeof(MC33_real));
-	S->N = (float (*)[3])malloc((size_t)S->capv * 3 * sizeof(float));
-	S->color = (int *)malloc((size_t)S->capv * sizeof(int));
+	S->T = (unsigned int (*)[3])result_alloc((size_t)S->capt * 3 * sizeof(int));
+	S->V = (MC33_real (*)[3])result_alloc((size_t)S->capv * 3 * sizeof(MC33_real));
+	S->N = (float (*)[3])result_alloc((size_t)S->capv * 3 * sizeof(float));
+	S->color = (int *)result_alloc((size_t)S->capv * sizeof(int));
 	if (!S->T || !S->V || !S->N || !S->color) goto fail;
 	rc = mc33cu_emit_host(p->ctx, S->V, (float *)S->N, S->color, (unsigned int *)S->T, DefaultColorMC);
 	if (rc != MC33CU_OK) goto fail;

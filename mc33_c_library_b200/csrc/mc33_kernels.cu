@@ -876,6 +876,8 @@ struct mc33cu_ctx {
 	size_t sample_size, real_size;
 	uint64_t n_samples;
 	void *grid_owned;        // device copy made by the upload calls
+	const void *up_host;     // host block of the previous contiguous upload
+	void *up_registered;     // ... page-locked by us (cudaHostRegister) from its second upload on
 	void *pinned; size_t pinned_bytes;   // staging for row-wise uploads
 	// k_count blocks (CNT_WARPS * G rows each) and their (V, T, C) sums
 	uint32_t *blk_sum; uint32_t nblk;
@@ -926,6 +928,7 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaFree(P.rowBV); cudaFree(P.totals);
 	cudaFree(c->blk_sum);
 	cudaFree(c->grid_owned);
+	if (c->up_registered) cudaHostUnregister(c->up_registered);
 	cudaFree(c->oV); cudaFree(c->oN); cudaFree(c->oC); cudaFree(c->oT);
 	if (c->pinned) cudaFreeHost(c->pinned);
 	if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -1101,8 +1104,79 @@ extern "C" int mc33cu_grid_upload(mc33cu_ctx *c, const void *host)
 	if (!c || !host) return fail(MC33CU_ERR_ARG, "null argument");
 	int rc = ensure_grid(c);
 	if (rc) return rc;
-	CU(cudaMemcpyAsync(c->grid_owned, host, c->n_samples * c->sample_size, cudaMemcpyHostToDevice, c->stream));
+	const size_t bytes = c->n_samples * c->sample_size;
+	// An iso sweep uploads the same host block again and again (the reference reads the
+	// samples at calculate time, so the drop-in may not keep them): from the second
+	// upload on, the block is page-locked so that the copy runs at PCIe speed instead of
+	// through the driver's staging buffers.  MC33_B200_NO_PIN=1 turns this off.
+	if (host == c->up_host) {
+		if (!c->up_registered && !getenv("MC33_B200_NO_PIN")) {
+			if (cudaHostRegister(const_cast<void *>(host), bytes, cudaHostRegisterDefault) == cudaSuccess)
+				c->up_registered = const_cast<void *>(host);
+			else
+				cudaGetLastError();
+		}
+	} else {
+		if (c->up_registered) { cudaHostUnregister(c->up_registered); c->up_registered = nullptr; }
+		c->up_host = host;
+	}
+	CU(cudaMemcpyAsync(c->grid_owned, host, bytes, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
+	return MC33CU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pooled page-locked host memory for result arrays (the drop-in hands them to the
+// caller as surface.V/N/T/color and gets them back in free_surface_memory)
+// ---------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+namespace {
+struct HostBlock { void *p; size_t cap; bool used; };
+std::mutex g_pool_mx;
+std::vector<HostBlock> g_pool;
+const size_t POOL_MAX_FREE = 16;
+}
+
+extern "C" int mc33cu_host_alloc(size_t bytes, void **out)
+{
+	if (!out) return fail(MC33CU_ERR_ARG, "null argument");
+	*out = nullptr;
+	if (!bytes) bytes = 1;
+	std::lock_guard<std::mutex> lk(g_pool_mx);
+	int best = -1;
+	for (size_t i = 0; i < g_pool.size(); i++)
+		if (!g_pool[i].used && g_pool[i].cap >= bytes && g_pool[i].cap <= bytes + bytes / 2 + (1u << 20) &&
+		    (best < 0 || g_pool[i].cap < g_pool[(size_t)best].cap)) best = (int)i;
+	if (best >= 0) { g_pool[(size_t)best].used = true; *out = g_pool[(size_t)best].p; return MC33CU_OK; }
+	const size_t cap = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(MC33CU_ERR_NOMEM, "cudaHostAlloc failed");
+	}
+	g_pool.push_back({p, cap, true});
+	*out = p;
+	return MC33CU_OK;
+}
+
+extern "C" int mc33cu_host_free(void *p)
+{
+	if (!p) return MC33CU_OK;
+	std::lock_guard<std::mutex> lk(g_pool_mx);
+	size_t nfree = 0;
+	int found = -1;
+	for (size_t i = 0; i < g_pool.size(); i++) {
+		if (g_pool[i].p == p) found = (int)i;
+		else if (!g_pool[i].used) nfree++;
+	}
+	if (found < 0) return MC33CU_ERR_ARG;               // not ours: the caller frees it with free()
+	if (nfree >= POOL_MAX_FREE) {
+		cudaFreeHost(p);
+		g_pool.erase(g_pool.begin() + found);
+	} else {
+		g_pool[(size_t)found].used = false;
+	}
 	return MC33CU_OK;
 }
 
