@@ -773,39 +773,46 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 	typedef typename Traits<Sample>::Real Real;
 	const Real iso = (Real)P.iso;
 	const int64_t sy = (int64_t)P.NX, sz = (int64_t)P.NX * P.NY;
+	// rotated axes: a along the edge, b = a+1, c = a+2 (mod 3) across it
+	const int64_t sa = a == 0 ? (int64_t)1 : (a == 1 ? sy : sz);
+	const int64_t sb = a == 0 ? sy : (a == 1 ? sz : (int64_t)1);
+	const int64_t sc = a == 0 ? sz : (a == 1 ? (int64_t)1 : sy);
+	const uint32_t qa = a == 0 ? x : (a == 1 ? y : z), qb = a == 0 ? y : (a == 1 ? z : x), qc = a == 0 ? z : (a == 1 ? x : y);
+	const uint32_t nb = a == 0 ? P.ny : (a == 1 ? P.nz : P.nx), nc = a == 0 ? P.nz : (a == 1 ? P.nx : P.ny);
 	const Sample *p0 = (const Sample *)P.data + ((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x;
-	const Sample *p1 = p0 + (a == 0 ? (int64_t)1 : (a == 1 ? sy : sz));
+	const Sample *p1 = p0 + sa;
 	const Real va = rsub(iso, (Real)ldro(p0)), vb = rsub(iso, (Real)ldro(p1));
 	const Real t = rdiv(va, rsub(va, vb));
 	const Real one_t = rsub((Real)1, t);
-	Real r[6];
+	Real g[2];
 #pragma unroll
-	for (int c = 0; c < 3; c++) {
-		const int64_t sc = c == 0 ? (int64_t)1 : (c == 1 ? sy : sz);
-		const uint32_t q = c == 0 ? x : (c == 1 ? y : z);
-		const uint32_t nq = c == 0 ? P.nx : (c == 1 ? P.ny : P.nz);
-		if (c == a) {
-			r[c] = radd((Real)q, t);
-			r[3 + c] = rsub(vb, va);
+	for (int k = 0; k < 2; k++) {
+		const int64_t s = k ? sc : sb;
+		const uint32_t q = k ? qc : qb, n = k ? nc : nb;
+		if (q != 0 && q != n) {
+			// central difference on raw samples (e.g. c:993-994)
+			const Real e0 = rawdiff(ldro(p0 - s), ldro(p0 + s)), e1 = rawdiff(ldro(p1 - s), ldro(p1 + s));
+			g[k] = rmul((Real)0.5f, radd(rmul(e0, one_t), rmul(e1, t)));
 		} else {
-			r[c] = (Real)q;
-			if (q != 0 && q != nq) {
-				// central difference on raw samples (e.g. c:993-994)
-				const Real e0 = rawdiff(ldro(p0 - sc), ldro(p0 + sc)), e1 = rawdiff(ldro(p1 - sc), ldro(p1 + sc));
-				r[3 + c] = rmul((Real)0.5f, radd(rmul(e0, one_t), rmul(e1, t)));
-			} else {
-				Real d0, d1;
-				if (q == 0) {   // forward difference of the iso-subtracted values (e.g. c:813)
-					d0 = rsub(rsub(iso, (Real)ldro(p0 + sc)), va);
-					d1 = rsub(rsub(iso, (Real)ldro(p1 + sc)), vb);
-				} else {        // backward (e.g. c:995 else-branch)
-					d0 = rsub(va, rsub(iso, (Real)ldro(p0 - sc)));
-					d1 = rsub(vb, rsub(iso, (Real)ldro(p1 - sc)));
-				}
-				r[3 + c] = radd(rmul(d0, one_t), rmul(d1, t));
+			Real d0, d1;
+			if (q == 0) {   // forward difference of the iso-subtracted values (e.g. c:813)
+				d0 = rsub(rsub(iso, (Real)ldro(p0 + s)), va);
+				d1 = rsub(rsub(iso, (Real)ldro(p1 + s)), vb);
+			} else {        // backward (e.g. c:995 else-branch)
+				d0 = rsub(va, rsub(iso, (Real)ldro(p0 - s)));
+				d1 = rsub(vb, rsub(iso, (Real)ldro(p1 - s)));
 			}
+			g[k] = radd(rmul(d0, one_t), rmul(d1, t));
 		}
 	}
+	const Real ga = rsub(vb, va), pa = radd((Real)qa, t);
+	Real r[6];
+	r[0] = a == 0 ? pa : (Real)x;
+	r[1] = a == 1 ? pa : (Real)y;
+	r[2] = a == 2 ? pa : (Real)z;
+	r[3] = a == 0 ? ga : (a == 1 ? g[1] : g[0]);
+	r[4] = a == 0 ? g[0] : (a == 1 ? ga : g[1]);
+	r[5] = a == 0 ? g[1] : (a == 1 ? g[0] : ga);
 	store_vertex<Real>(P, r, id);
 }
 

@@ -28,30 +28,24 @@ using namespace mc33;
 // case tables in device memory (copied to shared memory by the kernels that
 // index them divergently)
 // ---------------------------------------------------------------------------
-__device__ uint16_t d_case256[256];
-__device__ uint16_t d_simple256[256];
-__device__ uint16_t d_tri[MC33_NTRI_WORDS];
-__device__ uint8_t d_pat[MC33_NTRI_WORDS];
-
 #define TBL_TRI_BYTES ((MC33_NTRI_WORDS * 2 + 15) / 16 * 16)
 #define TBL_PAT_BYTES ((MC33_NTRI_WORDS + 15) / 16 * 16)
 #define TBL_BYTES (512 + 512 + TBL_TRI_BYTES + TBL_PAT_BYTES)
 
+// one image: case256 | simple256 | tri | pat, copied to shared memory with 16-byte loads
+__device__ __align__(16) unsigned char d_tables[TBL_BYTES];
+
 __device__ __forceinline__ Tables load_tables(unsigned char *smem)
 {
-	uint16_t *c = (uint16_t *)smem;
-	uint16_t *s = c + 256;
-	uint16_t *t = s + 256;
-	uint8_t *p = (uint8_t *)t + TBL_TRI_BYTES;
-	for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-		((uint32_t *)c)[i] = ((const uint32_t *)d_case256)[i];
-		((uint32_t *)s)[i] = ((const uint32_t *)d_simple256)[i];
-	}
-	for (int i = threadIdx.x; i < MC33_NTRI_WORDS / 2; i += blockDim.x) ((uint32_t *)t)[i] = ((const uint32_t *)d_tri)[i];
-	for (int i = threadIdx.x; i < MC33_NTRI_WORDS; i += blockDim.x) p[i] = d_pat[i];
+	const uint4 *src = reinterpret_cast<const uint4 *>(d_tables);
+	uint4 *dst = reinterpret_cast<uint4 *>(smem);
+	for (int i = threadIdx.x; i < TBL_BYTES / 16; i += blockDim.x) dst[i] = src[i];
 	__syncthreads();
 	Tables tb;
-	tb.case256 = c; tb.simple256 = s; tb.tri = t; tb.pat = p;
+	tb.case256 = (const uint16_t *)smem;
+	tb.simple256 = tb.case256 + 256;
+	tb.tri = tb.simple256 + 256;
+	tb.pat = (const uint8_t *)tb.tri + TBL_TRI_BYTES;
 	return tb;
 }
 
@@ -818,22 +812,41 @@ __global__ void __launch_bounds__(256, 4) k_emit_cells(Params P, uint32_t row_be
 						if (lane >= (unsigned)d) iv += xs;
 					}
 					const uint32_t ex = iv - v, tot = __shfl_sync(0xFFFFFFFFu, iv, 31);
-					if (on) {
-						const uint32_t tid = tbase + runT + (ex & 0xFFFFu), cl = cloc0 + runC + (ex >> 16);
-						const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
-						if (pat.centre) {
-							if (cl < P.capV) {
-								emit_centre_vertex<Sample>(P, x, y, z, cl);
-								if (P.vkey) P.vkey[cl] = cell * 4 + 3;
-							} else {
-								P.totals->overflow = 1;
-							}
+					const uint32_t tid = tbase + runT + (ex & 0xFFFFu), cl = cloc0 + runC + (ex >> 16);
+					const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
+					if (on && pat.centre) {
+						if (cl < P.capV) {
+							emit_centre_vertex<Sample>(P, x, y, z, cl);
+							if (P.vkey) P.vkey[cl] = cell * 4 + 3;
+						} else {
+							P.totals->overflow = 1;
 						}
-						if (!gz) {
+					}
+					if (!gz) {
+						// Triangles of this round, one lane per TRIANGLE: each owner lane marks its
+						// slots in the round's triangle range, then lane t fetches the owner's pattern
+						// by shuffle and its three vertex ids from the owner's column of the scratch;
+						// consecutive lanes write consecutive triangles.
+						uint8_t *own = reinterpret_cast<uint8_t *>(scr + 13 * 32);
+						const uint32_t e0 = ex & 0xFFFFu, ntot = tot & 0xFFFFu;
+						if (on) {
 							scr[12 * 32 + lane] = vb + cl;
-							for (uint32_t j = 0; j < pat.ntri; j++)
-								emit_triangle_fast(P, tb.tri[pat.start + j], pat.m, scr + lane, 32, tid + j, cell);
-						} else if (zm) {
+							for (uint32_t j = 0; j < pat.ntri; j++) own[e0 + j] = (uint8_t)lane;
+						}
+						__syncwarp();
+						const uint32_t sm = pat.start | (pat.m << 12);
+						for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
+							const uint32_t t = t0 + lane;
+							const bool act = t < ntot;
+							const int c = act ? (int)own[t] : 0;
+							const uint32_t csm = __shfl_sync(0xFFFFFFFFu, sm, c), ce0 = __shfl_sync(0xFFFFFFFFu, e0, c);
+							uint64_t ccell = 0;
+							if (P.tcell) ccell = __shfl_sync(0xFFFFFFFFu, cell, c);
+							if (act) emit_triangle_fast(P, tb.tri[(csm & 0xFFFu) + (t - ce0)], csm >> 12, scr + c, 32, tbase + runT + t, ccell);
+						}
+						__syncwarp();
+					} else if (on) {
+						if (zm) {
 							emit_cell_triangles_z(P, tb, b, pat, zm, vb + cl, scr + lane, scr + 256 + lane, 32, tid, 0u, 0xFFFFFFFFu, cell);
 						} else {
 							for (uint32_t j = 0; j < pat.ntri; j++)
@@ -902,12 +915,14 @@ extern "C" int mc33cu_device_count(void)
 
 static int upload_tables()
 {
-	uint8_t pat[MC33_NTRI_WORDS];
+	static unsigned char img[TBL_BYTES];
+	memset(img, 0, sizeof img);
+	memcpy(img, MC33_CASE256, 512);
+	memcpy(img + 512, MC33_SIMPLE256, 512);
+	memcpy(img + 1024, MC33_TRI, sizeof(MC33_TRI));
+	unsigned char *pat = img + 1024 + TBL_TRI_BYTES;
 	for (int i = 0; i < MC33_NTRI_WORDS; i++) pat[i] = (uint8_t)(MC33_PAT_NTRI[i] | (MC33_PAT_CENTRE[i] << 7));
-	CU(cudaMemcpyToSymbol(d_case256, MC33_CASE256, sizeof(MC33_CASE256)));
-	CU(cudaMemcpyToSymbol(d_simple256, MC33_SIMPLE256, sizeof(MC33_SIMPLE256)));
-	CU(cudaMemcpyToSymbol(d_tri, MC33_TRI, sizeof(MC33_TRI)));
-	CU(cudaMemcpyToSymbol(d_pat, pat, sizeof(pat)));
+	CU(cudaMemcpyToSymbol(d_tables, img, sizeof img));
 	return MC33CU_OK;
 }
 
