@@ -253,6 +253,77 @@ def test_full_size_properties():
     ex.close()
 
 
+def _mesh_properties(r, nV, nT, nShared, NX, check_used=True):
+    T = r["T"].astype(np.int64)
+    assert T.shape == (nT, 3) and T.min() == 0 and T.max() == nV - 1
+    assert (T[:, 0] != T[:, 1]).all() and (T[:, 1] != T[:, 2]).all() and (T[:, 0] != T[:, 2]).all()
+    assert (np.diff(r["tcell"]) >= 0).all()                                  # sweep (cell-major) order
+    assert (np.diff(r["vkey"][:nShared] // 4 // NX) >= 0).all()              # shared vertices in point-row order
+    assert (np.diff(r["vkey"][nShared:]) > 0).all()                          # centre vertices in cell order
+    if check_used:
+        assert np.bincount(T.reshape(-1), minlength=nV).min() >= 1
+    n = r["N"].astype(np.float64)
+    ln = np.sqrt((n * n).sum(1))
+    ok = np.isfinite(ln)
+    assert np.abs(ln[ok] - 1).max() < 1e-5
+
+
+def test_cfg3_like_large_u16_volume():
+    """BASELINE config 3 at 1024 x 1024 x 160 uint16 (GRD_INTEGER, GRD_TYPE_SIZE 2): CT-like blobs + noise,
+    integer isovalue (on-iso samples everywhere -> generic path) and half-integer (fast path);
+    counts against the compiled reference's size_of_isosurface, size-independent mesh properties"""
+    import torch
+    from mc33_c_library_b200.device import Extractor
+    NZ, NY, NX = 160, 1024, 1024
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    ax = torch.linspace(-1, 1, NX, device=dev)
+    az = torch.linspace(-0.3, 0.3, NZ, device=dev)
+    v = torch.full((NZ, NY, NX), 1000.0, device=dev)
+    for c0, c1, c2, sg in ((0.1, -0.2, 0.05, 0.3), (-0.4, 0.3, -0.1, 0.25), (0.5, 0.5, 0.1, 0.2)):
+        v += 2500.0 / 3 * torch.exp(-((ax[None, None, :] - c0) ** 2 + (ax[None, :, None] - c1) ** 2 + (az[:, None, None] - c2) ** 2) / (2 * sg * sg))
+    v += torch.randint(0, 16, v.shape, device=dev, generator=g)
+    vol = v.clamp(0, 65535).to(torch.int32).to(torch.uint16)
+    del v
+    host = vol.cpu().numpy()
+    ex = Extractor(make_desc(host.shape, "u16"))
+    ex.bind(vol)
+    for iso in (1500.0, 1500.5):
+        r = ex.extract(iso, keys=True)
+        k = r["counts"]
+        nV, nT = int(k.nV), int(k.nT)
+        if have_ref("u16"):
+            _, rV, rT = ref_lib("u16").size(host, iso)
+            assert (nV, nT) == (rV, rT)
+        assert nV > 100000
+        _mesh_properties(r, nV, nT, int(k.nShared), NX, check_used=False)
+    ex.close()
+
+
+def test_cfg5_like_large_inclined_noise():
+    """BASELINE config 5 at 320^3: float white noise on an inclined grid (dense: ~1.5 vertices and ~3.5
+    triangles per voxel, half the cells through a face / interior test)"""
+    import torch
+    from mc33_c_library_b200.device import Extractor
+    n = 320
+    a = noise_grid(n, "f32")
+    geom = inclined_geom()
+    ex = Extractor(make_desc(a.shape, "f32", geom))
+    ex.upload(a)
+    r = ex.extract(0.0, keys=True)
+    k = r["counts"]
+    nV, nT = int(k.nV), int(k.nT)
+    assert 1.4 < nV / n ** 3 < 1.7 and 3.2 < nT / n ** 3 < 3.7
+    if have_ref("f32"):
+        _, rV, rT = ref_lib("f32").size(a, 0.0, geom)
+        assert (nV, nT) == (rV, rT)
+    _mesh_properties(r, nV, nT, int(k.nShared), n)
+    # a 40-slice sub-volume against the oracle, vertex by vertex
+    sub = np.ascontiguousarray(a[:40])
+    _same(oracle_extract(sub, 0.0, "f32", geom), gpu_extract(sub, 0.0, "f32", geom))
+    ex.close()
+
+
 # ---- the drop-in C API (include/marching_cubes_33.h) --------------------------
 def dropin(variant):
     return MC33Lib(LIBDIR / f"libMC33_b200_{variant}.so", variant)
