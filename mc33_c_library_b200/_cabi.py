@@ -54,10 +54,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    import os
+    path = Path(os.environ.get("MC33_B200_LIB", LIB_PATH))    # A/B builds of the same C-ABI (tools/)
+    if not path.exists():
+        raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     vp, i32, u64 = C.c_void_p, C.c_int32, C.c_uint64
     lib.mc33cu_last_error.restype = C.c_char_p
     lib.mc33cu_device_count.restype = C.c_int

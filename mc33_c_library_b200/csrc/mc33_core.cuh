@@ -784,24 +784,27 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 	const Real va = rsub(iso, (Real)ldro(p0)), vb = rsub(iso, (Real)ldro(p1));
 	const Real t = rdiv(va, rsub(va, vb));
 	const Real one_t = rsub((Real)1, t);
+	// Across-axis differences.  The four neighbours of each end point are loaded
+	// unconditionally with the step clamped at the grid faces, so that all ten loads of a
+	// vertex are in flight together (a branch around them serialised two round trips):
+	// at a face one of the two samples is the end point itself and
+	// (iso - F(+)) - (iso - F(-)) is exactly the reference's one-sided difference of the
+	// iso-subtracted values (forward e.g. c:813, backward e.g. c:995 else-branch).
 	Real g[2];
 #pragma unroll
 	for (int k = 0; k < 2; k++) {
 		const int64_t s = k ? sc : sb;
 		const uint32_t q = k ? qc : qb, n = k ? nc : nb;
-		if (q != 0 && q != n) {
+		const bool face = q == 0 || q == n;
+		const int64_t sm = q == 0 ? (int64_t)0 : s, sp = q == n ? (int64_t)0 : s;
+		const Sample f0m = ldro(p0 - sm), f0p = ldro(p0 + sp), f1m = ldro(p1 - sm), f1p = ldro(p1 + sp);
+		if (!face) {
 			// central difference on raw samples (e.g. c:993-994)
-			const Real e0 = rawdiff(ldro(p0 - s), ldro(p0 + s)), e1 = rawdiff(ldro(p1 - s), ldro(p1 + s));
+			const Real e0 = rawdiff(f0m, f0p), e1 = rawdiff(f1m, f1p);
 			g[k] = rmul((Real)0.5f, radd(rmul(e0, one_t), rmul(e1, t)));
 		} else {
-			Real d0, d1;
-			if (q == 0) {   // forward difference of the iso-subtracted values (e.g. c:813)
-				d0 = rsub(rsub(iso, (Real)ldro(p0 + s)), va);
-				d1 = rsub(rsub(iso, (Real)ldro(p1 + s)), vb);
-			} else {        // backward (e.g. c:995 else-branch)
-				d0 = rsub(va, rsub(iso, (Real)ldro(p0 - s)));
-				d1 = rsub(vb, rsub(iso, (Real)ldro(p1 - s)));
-			}
+			const Real d0 = rsub(rsub(iso, (Real)f0p), rsub(iso, (Real)f0m));
+			const Real d1 = rsub(rsub(iso, (Real)f1p), rsub(iso, (Real)f1m));
 			g[k] = radd(rmul(d0, one_t), rmul(d1, t));
 		}
 	}

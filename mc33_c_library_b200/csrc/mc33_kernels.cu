@@ -604,12 +604,18 @@ __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32
 #define CQ 256
 #define EM_SCR 512      // per-warp scratch words: 13 ids x 32 lanes, or 8 (mask, base) pairs x 32 lanes
 #define EMV_SMEM (EM_WARPS * VQ * 4)
+#ifndef EMV_MINB
+#define EMV_MINB 4      // resident CTAs per SM the emit kernels are compiled for (register cap)
+#endif
+#ifndef EMC_MINB
+#define EMC_MINB 4
+#endif
 #define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR) * 4)
 
 // (the two halves are separate kernels: fused, the hot code no longer fitted the
 // instruction cache and 70 % of the warp stalls were instruction fetches)
 template <typename Sample>
-__global__ void __launch_bounds__(256, 4) k_emit_vertices(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
 	__shared__ uint32_t s_vq[EM_WARPS * VQ];
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -695,7 +701,7 @@ __global__ void __launch_bounds__(256, 4) k_emit_vertices(Params P, uint32_t row
 }
 
 template <typename Sample>
-__global__ void __launch_bounds__(256, 4) k_emit_cells(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const Tables tb = load_tables(smem);
@@ -902,6 +908,9 @@ struct mc33cu_ctx {
 	// timing
 	bool timing; cudaEvent_t ev[6]; bool ev_valid;
 	uint64_t launches;
+	// resident CTAs per SM given to each emit kernel (they co-run on two streams and share
+	// the register file: 4 CTAs of 256 threads x 64 registers fill an SM)
+	uint32_t emc_per_sm, emv_per_sm;
 };
 
 extern "C" const char *mc33cu_last_error(void) { return g_err; }
@@ -990,6 +999,9 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	if (!c) return fail(MC33CU_ERR_NOMEM, "calloc");
 	c->d = *d;
 	c->device = device;
+	c->emc_per_sm = EMC_MINB; c->emv_per_sm = EMV_MINB;
+	if (const char *e = getenv("MC33_B200_EMC_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emc_per_sm = (uint32_t)v; }
+	if (const char *e = getenv("MC33_B200_EMV_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emv_per_sm = (uint32_t)v; }
 	int rc = upload_tables();
 	if (rc) { free(c); return rc; }
 	if (cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->n_sm <= 0) c->n_sm = 148;
@@ -1307,7 +1319,7 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (P.cz1 - P.zlo) * P.NY;
 		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
 		// (side by side: two resident CTAs of each kernel per SM, so that both really co-run)
-		uint32_t grid = (uint32_t)c->n_sm * 4;
+		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
 		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, sc>>>(P, rb, re, ngroups);
 		c->launches++;
@@ -1317,7 +1329,7 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		// rows whose vertices this slab owns
 		const uint32_t rb = (P.pz0 - P.zlo) * P.NY, re = (P.pz1 - P.zlo) * P.NY;
 		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
-		uint32_t grid = (uint32_t)c->n_sm * 4;
+		uint32_t grid = (uint32_t)c->n_sm * c->emv_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
 		k_emit_vertices<Sample><<<grid, 256, 0, s>>>(P, rb, re, ngroups);
 		c->launches++;
