@@ -116,7 +116,16 @@ struct Geom {
 	int store, normal_neg, tsa, pad_;
 	double O[3], D[3], ca, cb;   // values already narrowed to Real by the caller
 	double A[9], Ai[9];          // scaled matrices of create_MC33 (c:1763-1769)
+	float Of[3], Df[3], caf, cbf;   // the same O, D, ca, cb as float (Real == float builds: no conversion per vertex)
 };
+MC_HD float  geomO(const Geom &g, int i, float)  { return g.Of[i]; }
+MC_HD double geomO(const Geom &g, int i, double) { return g.O[i]; }
+MC_HD float  geomD(const Geom &g, int i, float)  { return g.Df[i]; }
+MC_HD double geomD(const Geom &g, int i, double) { return g.D[i]; }
+MC_HD float  geomCa(const Geom &g, float)  { return g.caf; }
+MC_HD double geomCa(const Geom &g, double) { return g.ca; }
+MC_HD float  geomCb(const Geom &g, float)  { return g.cbf; }
+MC_HD double geomCb(const Geom &g, double) { return g.cb; }
 
 struct Totals {                   // written by the scan kernel
 	uint32_t nShared;             // shared vertices owned by this slab
@@ -161,6 +170,7 @@ struct Params {
 	// outputs (device)
 	void *V; float *N; int32_t *color; uint32_t *T;
 	uint64_t *vkey, *tcell;       // optional canonical keys (tests)
+	uint64_t *vtask;              // [capV] vertex tasks left by the cell kernel for the vertex kernel
 	uint32_t capV, capT;
 	uint32_t vbase, vbase_next;   // global vertex id of this / the next slab's first vertex (0 on one GPU)
 	const uint32_t *dbases;       // optional device copy {vbase, vbase_next}: overrides the two above
@@ -697,13 +707,16 @@ MC_COLD void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t 
 // vertex store: MC33_spn0/A/B/C (marching_cubes_33.c:485-621,
 // MC33_util_grd.c:87-112); r[0..2] index-space position, r[3..5] = -grad F
 // ---------------------------------------------------------------------------
-// inclined grids, MC33_spnC (marching_cubes_33.c:595-621): p = _A r + O, n = A_^T n in double
+// inclined grids, MC33_spnC (marching_cubes_33.c:595-621): p = _A r + O, n = A_^T n in double.
+// Six values in, six out, all by value: the hot caller keeps them in registers.
+template <typename Real> struct Vtx { Real p0, p1, p2, n0, n1, n2; };
+
 template <typename Real>
-MC_COLD void store_spnc(const Geom &g, Real *r, Real *p)
+MC_COLD Vtx<Real> store_spnc(const Geom &g, Vtx<Real> v)
 {
 	const double *A = g.A, *B = g.Ai;
 	Real c0, c1, c2;
-	double r0 = r[0], r1 = r[1], r2 = r[2];
+	const double r0 = v.p0, r1 = v.p1, r2 = v.p2;
 	if (g.tsa) {
 		c0 = (Real)radd(radd(rmul(A[0], r0), rmul(A[1], r1)), rmul(A[2], r2));
 		c1 = (Real)radd(rmul(A[4], r1), rmul(A[5], r2));
@@ -713,8 +726,9 @@ MC_COLD void store_spnc(const Geom &g, Real *r, Real *p)
 		c1 = (Real)radd(radd(rmul(A[3], r0), rmul(A[4], r1)), rmul(A[5], r2));
 		c2 = (Real)radd(radd(rmul(A[6], r0), rmul(A[7], r1)), rmul(A[8], r2));
 	}
-	p[0] = radd(c0, (Real)g.O[0]); p[1] = radd(c1, (Real)g.O[1]); p[2] = radd(c2, (Real)g.O[2]);
-	double n0 = r[3], n1 = r[4], n2 = r[5];
+	Vtx<Real> o;
+	o.p0 = radd(c0, (Real)g.O[0]); o.p1 = radd(c1, (Real)g.O[1]); o.p2 = radd(c2, (Real)g.O[2]);
+	const double n0 = v.n0, n1 = v.n1, n2 = v.n2;
 	if (g.tsa) {
 		c2 = (Real)radd(radd(rmul(B[2], n0), rmul(B[5], n1)), rmul(B[8], n2));
 		c1 = (Real)radd(rmul(B[1], n0), rmul(B[4], n1));
@@ -724,27 +738,28 @@ MC_COLD void store_spnc(const Geom &g, Real *r, Real *p)
 		c1 = (Real)radd(radd(rmul(B[1], n0), rmul(B[4], n1)), rmul(B[7], n2));
 		c2 = (Real)radd(radd(rmul(B[2], n0), rmul(B[5], n1)), rmul(B[8], n2));
 	}
-	r[3] = c0; r[4] = c1; r[5] = c2;
+	o.n0 = c0; o.n1 = c1; o.n2 = c2;
+	return o;
 }
 
 template <typename Real>
-MC_HD void store_vertex(const Params &P, Real *r, uint32_t id)
+MC_HD void store_vertex(const Params &P, const Real *r, uint32_t id)
 {
 	const Geom &g = P.geom;
-	Real p[3];
-	if (g.store == STORE_SPN0) {
-		p[0] = r[0]; p[1] = r[1]; p[2] = r[2];
-	} else if (g.store == STORE_SPNC) {
-		store_spnc<Real>(g, r, p);
-	} else {
+	Vtx<Real> v;
+	v.p0 = r[0]; v.p1 = r[1]; v.p2 = r[2]; v.n0 = r[3]; v.n1 = r[4]; v.n2 = r[5];
+	if (g.store == STORE_SPNC) {
+		v = store_spnc<Real>(g, v);
+	} else if (g.store != STORE_SPN0) {
 		if (g.store == STORE_SPNB) {
-			r[3] = rmul(r[3], (Real)g.ca);
-			r[4] = rmul(r[4], (Real)g.cb);
+			v.n0 = rmul(v.n0, geomCa(g, Real()));
+			v.n1 = rmul(v.n1, geomCb(g, Real()));
 		}
-#pragma unroll
-		for (int i = 0; i < 3; i++) p[i] = radd(rmul(r[i], (Real)g.D[i]), (Real)g.O[i]);
+		v.p0 = radd(rmul(v.p0, geomD(g, 0, Real())), geomO(g, 0, Real()));
+		v.p1 = radd(rmul(v.p1, geomD(g, 1, Real())), geomO(g, 1, Real()));
+		v.p2 = radd(rmul(v.p2, geomD(g, 2, Real())), geomO(g, 2, Real()));
 	}
-	Real s = radd(radd(rmul(r[3], r[3]), rmul(r[4], r[4])), rmul(r[5], r[5]));
+	const Real s = radd(radd(rmul(v.n0, v.n0), rmul(v.n1, v.n1)), rmul(v.n2, v.n2));
 	// the reference's rsqrtss is only good to 3e-4; the device uses the
 	// hardware reciprocal square root (2 ulp), the host emulation the exact quotient
 #if defined(__CUDA_ARCH__)
@@ -755,8 +770,8 @@ MC_HD void store_vertex(const Params &P, Real *r, uint32_t id)
 	if (g.normal_neg) t = -t;
 	Real *V = (Real *)P.V + 3 * (uint64_t)id;
 	float *N = P.N + 3 * (uint64_t)id;
-	V[0] = p[0]; V[1] = p[1]; V[2] = p[2];
-	N[0] = rmul(t, (float)r[3]); N[1] = rmul(t, (float)r[4]); N[2] = rmul(t, (float)r[5]);
+	V[0] = v.p0; V[1] = v.p1; V[2] = v.p2;
+	N[0] = rmul(t, (float)v.n0); N[1] = rmul(t, (float)v.n1); N[2] = rmul(t, (float)v.n2);
 	P.color[id] = P.color_value;
 }
 
@@ -772,11 +787,13 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 {
 	typedef typename Traits<Sample>::Real Real;
 	const Real iso = (Real)P.iso;
-	const int64_t sy = (int64_t)P.NX, sz = (int64_t)P.NX * P.NY;
+	// offsets within +-1 slice of the point fit 32 bits (a slice holds < 2^31 samples, checked
+	// at context creation): one 64-bit row address, then 32-bit element offsets
+	const int32_t sy = (int32_t)P.NX, sz = (int32_t)(P.NX * P.NY);
 	// rotated axes: a along the edge, b = a+1, c = a+2 (mod 3) across it
-	const int64_t sa = a == 0 ? (int64_t)1 : (a == 1 ? sy : sz);
-	const int64_t sb = a == 0 ? sy : (a == 1 ? sz : (int64_t)1);
-	const int64_t sc = a == 0 ? sz : (a == 1 ? (int64_t)1 : sy);
+	const int32_t sa = a == 0 ? 1 : (a == 1 ? sy : sz);
+	const int32_t sb = a == 0 ? sy : (a == 1 ? sz : 1);
+	const int32_t sc = a == 0 ? sz : (a == 1 ? 1 : sy);
 	const uint32_t qa = a == 0 ? x : (a == 1 ? y : z), qb = a == 0 ? y : (a == 1 ? z : x), qc = a == 0 ? z : (a == 1 ? x : y);
 	const uint32_t nb = a == 0 ? P.ny : (a == 1 ? P.nz : P.nx), nc = a == 0 ? P.nz : (a == 1 ? P.nx : P.ny);
 	const Sample *p0 = (const Sample *)P.data + ((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x;
@@ -793,11 +810,11 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 	Real g[2];
 #pragma unroll
 	for (int k = 0; k < 2; k++) {
-		const int64_t s = k ? sc : sb;
+		const int32_t s = k ? sc : sb;
 		const uint32_t q = k ? qc : qb, n = k ? nc : nb;
 		const bool face = q == 0 || q == n;
-		const int64_t sm = q == 0 ? (int64_t)0 : s, sp = q == n ? (int64_t)0 : s;
-		const Sample f0m = ldro(p0 - sm), f0p = ldro(p0 + sp), f1m = ldro(p1 - sm), f1p = ldro(p1 + sp);
+		const int32_t sm = q == 0 ? 0 : -s, sp = q == n ? 0 : s;
+		const Sample f0m = ldro(p0 + sm), f0p = ldro(p0 + sp), f1m = ldro(p0 + (sa + sm)), f1p = ldro(p0 + (sa + sp));
 		if (!face) {
 			// central difference on raw samples (e.g. c:993-994)
 			const Real e0 = rawdiff(f0m, f0p), e1 = rawdiff(f1m, f1p);
@@ -899,6 +916,46 @@ MC_HDN void emit_vertex_task(const Params &P, uint32_t x, uint32_t y, uint32_t z
 }
 
 // ---------------------------------------------------------------------------
+// Vertex tasks.  The cell kernel already knows, for the grid point at the low corner
+// of each cell it visits, which of the point's three planes carry a vertex and what
+// their ids are, so it leaves one 8-byte task per vertex in vtask[id]:
+// local row | (x | plane << 16 | is_point << 18) << 32.  The vertex kernel is then
+// dense: thread id reads task id and computes vertex id.
+// ---------------------------------------------------------------------------
+MC_HD void put_vertex_task(const Params &P, uint32_t id, uint32_t lr, uint32_t x, unsigned a, bool is_point)
+{
+	// (ids beyond the capacity: the vertex kernel raises the overflow flag)
+	if (id < P.capV) P.vtask[id] = (uint64_t)lr | ((uint64_t)(x | (a << 16) | ((uint32_t)is_point << 18)) << 32);
+}
+
+template <typename Sample>
+MC_HD void run_vertex_task(const Params &P, uint32_t id)
+{
+	const uint64_t t = P.vtask[id];
+	const uint32_t lr = (uint32_t)t, e = (uint32_t)(t >> 32);
+	const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+	emit_vertex_task<Sample>(P, e & 0xFFFFu, y, z, (int)((e >> 16) & 3u), ((e >> 18) & 1u) != 0, id);
+}
+
+// tasks of the vertices owned by grid point (x,y,z) on a grid WITH on-iso samples
+// (generic path): plane masks of the point's own row, POINT vertices flagged
+MC_COLD void put_vertex_tasks_generic(const Params &P, uint32_t x, uint32_t y, uint32_t z)
+{
+	const uint32_t lr = (z - P.zlo) * P.NY + y, w = x >> 5, b = x & 31u;
+	WordRec rec; CellWords cw;
+	word_masks_generic(P, z, y, w, rec, cw);
+	const uint32_t zw = P.rowZ[lr] == P.zepoch ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
+	const uint32_t lo = (1u << b) - 1u;
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
+		if ((m >> b) & 1u)
+			put_vertex_task(P, plane_base_local(P, lr, w, a) + (uint32_t)popc32(m & lo), lr, x, (unsigned)a,
+			                a == 0 && ((zw >> b) & 1u));
+	}
+}
+
+// ---------------------------------------------------------------------------
 // Vertex ids referenced by the cells of word w of cell row (z,y): eight
 // (plane mask, global id of the plane's first vertex in this word) pairs
 // plane combos: 0 X00  1 Y00  2 Z00  3 X10  4 Z10  5 X01  6 Y01  7 X11
@@ -955,17 +1012,21 @@ MC_HD void write_triangle(const Params &P, uint32_t tid, const uint32_t *ti, uns
 }
 
 // ---------------------------------------------------------------------------
-// Fast path for a cell of a grid WITHOUT on-iso samples: the 8-bit case index and
+// Fast path for a cell of a grid WITHOUT on-iso samples: the 8-bit case index,
+// which vertices its low corner point owns, and
 // the global ids of the vertices on its 12 edges, straight from the sign bitmap,
 // the word prefixes and the row bases.  Every edge is evaluated (no dependence on
 // the pattern), ids of edges that carry no vertex are meaningless and never read.
 // g0 / g1: what turns a slab-local id of slice z / z+1 into a global one.
 // ---------------------------------------------------------------------------
-MC_HDN unsigned cell_fast(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t g0, uint32_t g1, uint32_t *id)
+MC_HDN unsigned cell_fast(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t g0, uint32_t g1, uint32_t *id, unsigned &own)
 {
 	const uint32_t w = x >> 5, b = x & 31u;
-	const uint32_t l00 = (z - P.zlo) * P.NY + y, l10 = l00 + 1, l01 = l00 + P.NY, l11 = l01 + 1;
-	const uint64_t i00 = (uint64_t)l00 * P.WP + w, i10 = i00 + P.WP, i01 = (uint64_t)l01 * P.WP + w, i11 = i01 + P.WP;
+	// (the point rows of the grid's high faces are visited for the vertices they own: a row
+	// that does not exist is replaced by the row itself, which empties the plane towards it)
+	const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? P.NY : 0u;
+	const uint32_t l00 = (z - P.zlo) * P.NY + y, l10 = l00 + uy, l01 = l00 + uz, l11 = l01 + uy;
+	const uint64_t i00 = (uint64_t)l00 * P.WP + w, i10 = (uint64_t)l10 * P.WP + w, i01 = (uint64_t)l01 * P.WP + w, i11 = (uint64_t)l11 * P.WP + w;
 	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
 	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
 	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
@@ -991,6 +1052,8 @@ MC_HDN unsigned cell_fast(const Params &P, uint32_t x, uint32_t y, uint32_t z, u
 	id[9] = bX10 + (uint32_t)popc32(mX10 & lo0);
 	id[10] = bX11 + (uint32_t)popc32(mX11 & lo0);
 	id[11] = bX01 + (uint32_t)popc32(mX01 & lo0);
+	// planes of the point (x,y,z) itself that carry a vertex: bit 0 X (id[8]), 1 Y (id[0]), 2 Z (id[3])
+	own = ((mX00 >> b) & 1u) | (((mY00 >> b) & 1u) << 1) | (((mZ00 >> b) & 1u) << 2);
 	// corner k -> index bit 7-k (corners 0..3 at x: rows 00 10 11 01; 4..7 at x+1)
 	return (((s00 >> b) & 1u) << 7) | (((s10 >> b) & 1u) << 6) | (((s11 >> b) & 1u) << 5) | (((s01 >> b) & 1u) << 4) |
 	       (((x00 >> b) & 1u) << 3) | (((x10 >> b) & 1u) << 2) | (((x11 >> b) & 1u) << 1) | ((x01 >> b) & 1u);

@@ -7,9 +7,9 @@
 //                 and centre vertices of the 32 cells -> row-local word prefixes;
 //                 fused single-pass decoupled look-back scan over the batches
 //                 -> per-row vertex / triangle / centre bases
-//   K3 emit V     vertex tasks compacted per tile in shared memory, one thread
-//                 per vertex, consecutive threads write consecutive vertices
-//   K4 emit T     triangle tasks compacted the same way, one thread per triangle
+//   K4 emit T     active cells compacted per row group, one lane per cell (vertex
+//                 ids, pattern, vertex tasks), then one lane per triangle
+//   K3 emit V     dense: one thread per vertex id runs the task K4 left for it
 //
 // Replaces: reference source/marching_cubes_33.c:1816-1889 (calculate_isosurface),
 // :673-1253 (MC33_findCase), :485-649 (store / surfint).  No CPU fallback.
@@ -160,7 +160,7 @@ __device__ __forceinline__ ClsChunk cls_chunk(const Params &P, const ClsPlan &pl
 }
 
 template <typename Sample>
-__global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
+__global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant__ Params P, ClsPlan pl)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint64_t full[CLS_STAGES];
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(Params P, ClsPlan pl)
 // LDS.128).  Every warp takes a contiguous run of its chunk's iterations.
 // ---------------------------------------------------------------------------
 template <typename Sample>
-__global__ void __launch_bounds__(CLS_THREADS) k_classify_vec(Params P, uint32_t rows, uint32_t nchunks, uint32_t stage_bytes)
+__global__ void __launch_bounds__(CLS_THREADS) k_classify_vec(const __grid_constant__ Params P, uint32_t rows, uint32_t nchunks, uint32_t stage_bytes)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint64_t full[CLS_STAGES];
@@ -413,7 +413,7 @@ __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32
 #define CNT_WARPS 8
 
 template <typename Sample>
-__global__ void __launch_bounds__(256, 4) k_count(Params P, uint32_t nblk, uint32_t *blkSum)
+__global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t *blkSum)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(256, 4) k_count(Params P, uint32_t nblk, uint3
 // ---------------------------------------------------------------------------
 #define RS_BLOCKS 4      // k_count blocks per k_rowscan CTA
 
-__global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32_t RB, const uint32_t *blkSum, uint32_t owned_end_row)
+__global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params P, uint32_t nblk, uint32_t RB, const uint32_t *blkSum, uint32_t owned_end_row)
 {
 	__shared__ uint64_t s_w[2][8];
 	__shared__ uint64_t s_base[3][RS_BLOCKS];
@@ -583,27 +583,22 @@ __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32
 }
 
 // ---------------------------------------------------------------------------
-// K3: emit.  Warp-synchronous, one warp per group of G rows, no block barrier:
+// K3 / K4: emit.
 //
-// vertices  the group's vertices are the id range [rowBV[first row], rowBV[last+1]).
-//           Fill: a lane whose quad owns vertices (known from the word prefixes)
-//           recomputes its plane masks and drops one task per vertex into the
-//           warp's queue at slot id - window start.  Drain: lane t computes vertex
-//           window start + t, so consecutive lanes write consecutive V / N / color.
-//           task word: x | plane << 16 | is_point << 18 | (row in group) << 19
-// cells     Fill: the active cells are compacted in sweep order (shuffle scan of
-//           the popcounts).  Drain: one lane per ACTIVE CELL picks the MC33 pattern,
-//           builds the eight (plane mask, first id) pairs its vertex ids are read
-//           from, and after a shuffle scan of the triangle counts writes its
-//           triangles (and centre vertex) at the ids the reference's sweep order
-//           gives them.
-// Groups with more vertices / cells than a queue holds take several windows.
+// cells     (K4, k_emit_cells) warp-synchronous, one warp per group of G rows, no block
+//           barrier.  Fill: the active cells -- and the grid points that own a vertex --
+//           are compacted in sweep order (shuffle scan of the popcounts).  Drain: one lane
+//           per visited CELL gets the ids of its 12 edge vertices from bitmaps + prefixes,
+//           leaves a task for each vertex its low corner point owns, picks the MC33
+//           pattern, and after a shuffle scan of the triangle counts the triangles (and
+//           centre vertices) are written at the ids the reference's sweep order gives them.
+// vertices  (K3, k_emit_vertices) dense over the vertex ids: thread id runs the task left
+//           in slot id, so consecutive threads write consecutive V / N / color.
+// Groups with more cells than a queue holds take several windows.
 // ---------------------------------------------------------------------------
 #define EM_WARPS 8
-#define VQ 256
 #define CQ 256
 #define EM_SCR 512      // per-warp scratch words: 13 ids x 32 lanes, or 8 (mask, base) pairs x 32 lanes
-#define EMV_SMEM (EM_WARPS * VQ * 4)
 #ifndef EMV_MINB
 #define EMV_MINB 4      // resident CTAs per SM the emit kernels are compiled for (register cap)
 #endif
@@ -612,96 +607,19 @@ __global__ void __launch_bounds__(256) k_rowscan(Params P, uint32_t nblk, uint32
 #endif
 #define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR) * 4)
 
-// (the two halves are separate kernels: fused, the hot code no longer fitted the
-// instruction cache and 70 % of the warp stalls were instruction fetches)
+// K3, dense: thread id computes vertex id from the task the cell kernel left in the
+// vertex's own slot of N (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
+// threads write consecutive V / N / color.
 template <typename Sample>
-__global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_constant__ Params P)
 {
-	__shared__ uint32_t s_vq[EM_WARPS * VQ];
-	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	uint32_t *vq = s_vq + wid * VQ;
-	const bool anyz = P.totals->anyZ != 0;
-	const uint32_t npass = (P.Q + 31) / 32;
-
-	for (uint32_t g = blockIdx.x * EM_WARPS + wid; g < ngroups; g += gridDim.x * EM_WARPS) {
-		const uint32_t lr0 = row_begin + g * P.G, lrE = min(lr0 + P.G, row_end);
-		const bool gz = group_has_oniso(P, anyz, lr0, lane);
-		// ======================= vertices =======================
-		const uint32_t vfirst = P.rowBV[lr0], vend = P.rowBV[lrE];
-		for (uint32_t win0 = vfirst; win0 < vend; win0 += VQ) {
-			for (uint32_t pass = 0; pass < npass; pass++) {
-				uint32_t r, q;
-				lane_item(P, lane, pass, r, q);
-				const uint32_t lr = lr0 + r;
-				if (!(r < P.G && q < P.Q && lr < lrE)) continue;
-				const uint64_t *pw = P.wpreV + (uint64_t)lr * P.WP + 4 * q;
-				const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(pw), pc = *reinterpret_cast<const ulonglong2 *>(pw + 2);
-				const uint64_t p4 = pw[4];
-				if (p4 == pa.x) continue;                    // no vertex in this quad
-				const uint32_t rb = P.rowBV[lr];
-				{
-					// does any of the quad's three id ranges meet the window?
-					const uint32_t wl = win0 - rb, wh = wl + VQ;     // window in row-local ids (may wrap: unsigned compares below)
-					bool hit = false;
-#pragma unroll
-					for (int a = 0; a < 3; a++) {
-						const uint32_t i0 = fldV(pa.x, a), i1 = fldV(p4, a);
-						hit = hit || (i1 > i0 && (int32_t)(i0 - wh) < 0 && (int32_t)(i1 - wl) > 0);
-					}
-					if (!hit) continue;
-				}
-				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
-				Quad q00, q10, q01;
-				if (!gz) {
-					const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
-					q00 = load_quad(P.S, i00);
-					q10 = y < P.ny ? load_quad(P.S, i00 + P.WP) : q00;
-					q01 = z < P.nz ? load_quad(P.S, i00 + (uint64_t)P.NY * P.WP) : q00;
-				}
-				const bool zrow = gz && P.rowZ[lr] == P.zepoch;
-				const uint64_t pk[4] = {pa.x, pa.y, pc.x, pc.y};
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const uint32_t w = 4 * q + k;
-					WordRec rec;
-					if (!gz) {
-						uint32_t c[8];
-						quad_word(P, q00, q10, q01, q10, k, w, false, rec, c);
-					} else {
-						CellWords cw;
-						if (w < P.W) word_masks_generic(P, z, y, w, rec, cw); else { rec.X = rec.Y = rec.Z = 0; }
-					}
-					const uint32_t zw = (zrow && w < P.W) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
-#pragma unroll
-					for (int a = 0; a < 3; a++) {
-						uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
-						uint32_t slot = rb + fldV(pk[k], a) - win0;
-						while (m) {
-							const int b = __ffs((int)m) - 1;
-							m &= m - 1;
-							if (slot < VQ)
-								vq[slot] = ((w << 5) + b) | ((uint32_t)a << 16) | ((a == 0 ? (zw >> b) & 1u : 0u) << 18) | (r << 19);
-							slot++;
-						}
-					}
-				}
-			}
-			__syncwarp();
-			const uint32_t nt = min((uint32_t)VQ, vend - win0);
-#pragma unroll 2
-			for (uint32_t t = lane; t < nt; t += 32) {
-				const uint32_t e = vq[t];
-				const uint32_t lr = lr0 + (e >> 19);
-				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
-				emit_vertex_task<Sample>(P, e & 0xFFFFu, y, z, (int)((e >> 16) & 3u), ((e >> 18) & 1u) != 0, win0 + t);
-			}
-			__syncwarp();
-		}
-	}
+	const uint32_t nS = P.totals->nShared, n = min(nS, P.capV);
+	if (nS > P.capV && blockIdx.x == 0 && threadIdx.x == 0) P.totals->overflow = 1;
+	for (uint32_t id = blockIdx.x * 256u + threadIdx.x; id < n; id += gridDim.x * 256u) run_vertex_task<Sample>(P, id);
 }
 
 template <typename Sample>
-__global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_constant__ Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const Tables tb = load_tables(smem);
@@ -728,26 +646,31 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(Params P, uint32_t
 				const uint32_t lr = lr0 + r;
 				if (r < P.G && q < P.Q && lr < lrE) {
 					const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
-					if (row_cells_owned(P, z, y)) {
+					// visited: active cells, and grid points that own a vertex (on the high faces
+					// of the grid those are points without a cell)
+					const bool own_c = row_cells_owned(P, z, y), own_p = row_points_owned(P, z);
+					if (own_c || own_p) {
 						uint32_t act[4] = {0, 0, 0, 0};
+						const uint32_t pm = own_p ? 0xFFFFFFFFu : 0u;
 						if (!gz) {
-							const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q, dZ = (uint64_t)P.NY * P.WP;
-							const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + P.WP);
-							const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + P.WP + dZ);
+							const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
+							const uint64_t dY = y < P.ny ? P.WP : 0u, dZ = z < P.nz ? (uint64_t)P.NY * P.WP : 0u;
+							const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
+							const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
 #pragma unroll
 							for (int k = 0; k < 4; k++) {
 								WordRec rec;
 								uint32_t c[8];
-								quad_word(P, q00, q10, q01, q11, k, 4 * q + k, true, rec, c);
-								act[k] = rec.act;
+								quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c, rec, c);
+								act[k] = rec.act | ((rec.X | rec.Y | rec.Z) & pm);
 							}
 						} else {
 #pragma unroll
 							for (int k = 0; k < 4; k++) {
-								if (4 * q + k < P.WC) {
+								if (4 * q + k < P.W) {
 									WordRec rec; CellWords cw;
 									word_masks_generic(P, z, y, 4 * q + k, rec, cw);
-									act[k] = rec.act;
+									act[k] = (own_c ? rec.act : 0u) | ((rec.X | rec.Y | rec.Z) & pm);
 								}
 							}
 						}
@@ -786,27 +709,43 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(Params P, uint32_t
 					pat.start = 0; pat.m = 0; pat.ntri = 0; pat.centre = 0;
 					unsigned zm = 0, b = 0;
 					uint32_t x = 0, y = 0, z = 0;
+					bool cellok = false;
 					if (on) {
 						const uint32_t e = cq[j0 + lane];
 						x = e & 0xFFFFu; b = x & 31u;
 						const uint32_t lr = lr0 + (e >> 16);
 						const uint32_t zl = fastdiv(lr, P.NY, P.mNY);
 						y = lr - zl * P.NY; z = zl + P.zlo;
+						const bool ownp = row_points_owned(P, z);
+						cellok = row_cells_owned(P, z, y) && x < P.nx;
 						if (!gz) {
 							uint32_t id[12];
-							const unsigned idx = cell_fast(P, x, y, z, z == P.hz ? vbn : vb, z + 1 == P.hz ? vbn : vb, id);
+							unsigned own;
+							const uint32_t g0 = z == P.hz ? vbn : vb;
+							const unsigned idx = cell_fast(P, x, y, z, g0, z + 1 == P.hz ? vbn : vb, id, own);
 #pragma unroll
 							for (int k = 0; k < 12; k++) scr[k * 32 + lane] = id[k];
-							pat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
-						} else {
+							if (cellok) pat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
+							if (ownp) {
+								if (own & 1u) put_vertex_task(P, id[8] - g0, lr, x, 0u, false);
+								if (own & 2u) put_vertex_task(P, id[0] - g0, lr, x, 1u, false);
+								if (own & 4u) put_vertex_task(P, id[3] - g0, lr, x, 2u, false);
+							}
+						} else if (ownp) {
+							put_vertex_tasks_generic(P, x, y, z);
+						}
+						if (gz && cellok) {
 							WordRec rec; CellWords cw; CellPairs cp;
 							word_masks_generic(P, z, y, x >> 5, rec, cw);
-							cell_pairs(P, z, y, x >> 5, true, rec, cw, cp);
+							// (with on-iso samples a point can own a vertex while its cell is inactive)
+							if ((rec.act >> b) & 1u) {
+								cell_pairs(P, z, y, x >> 5, true, rec, cw, cp);
 #pragma unroll
-							for (int k = 0; k < 8; k++) { scr[k * 32 + lane] = cp.mask[k]; scr[256 + k * 32 + lane] = cp.base[k]; }
-							const unsigned idx = cell_index(cw.c, 1, (int)b);
-							zm = cw.zany ? cell_zmask(cw.zc, 1, (int)b) : 0u;
-							pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
+								for (int k = 0; k < 8; k++) { scr[k * 32 + lane] = cp.mask[k]; scr[256 + k * 32 + lane] = cp.base[k]; }
+								const unsigned idx = cell_index(cw.c, 1, (int)b);
+								zm = cw.zany ? cell_zmask(cw.zc, 1, (int)b) : 0u;
+								pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
+							}
 						}
 					}
 					// triangle / centre offsets: shuffle scan in sweep order
@@ -888,8 +827,6 @@ struct mc33cu_ctx {
 	int device;
 	int n_sm;
 	cudaStream_t own_stream, stream;
-	cudaStream_t side_stream;            // emit_cells runs beside emit_vertices
-	cudaEvent_t ev_fork, ev_join;
 	Params P;
 	ClsPlan cls;
 	size_t sample_size, real_size;
@@ -908,9 +845,9 @@ struct mc33cu_ctx {
 	// timing
 	bool timing; cudaEvent_t ev[6]; bool ev_valid;
 	uint64_t launches;
-	// resident CTAs per SM given to each emit kernel (they co-run on two streams and share
-	// the register file: 4 CTAs of 256 threads x 64 registers fill an SM)
+	// resident CTAs per SM of the two emit kernels (persistent grids)
 	uint32_t emc_per_sm, emv_per_sm;
+	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
 };
 
 extern "C" const char *mc33cu_last_error(void) { return g_err; }
@@ -951,15 +888,13 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaFree(P.S); cudaFree(P.Z); cudaFree(P.rowZ); cudaFree(P.wpreV);
 	cudaFree(P.rowBV); cudaFree(P.totals);
 	cudaFree(c->blk_sum);
+	cudaFree(c->vtask);
 	cudaFree(c->grid_owned);
 	if (c->up_registered) cudaHostUnregister(c->up_registered);
 	cudaFree(c->oV); cudaFree(c->oN); cudaFree(c->oC); cudaFree(c->oT);
 	if (c->pinned) cudaFreeHost(c->pinned);
 	if (c->h_totals) cudaFreeHost(c->h_totals);
 	for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-	if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
-	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-	if (c->ev_join) cudaEventDestroy(c->ev_join);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	free(c);
 }
@@ -1018,6 +953,7 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	P.G = P.Q <= 32 ? 32 / P.Q : 1;
 	P.Lrows = (P.zhi - P.zlo) * P.NY;
 	if (P.NX > 65535) { free(c); return fail(MC33CU_ERR_ARG, "rows longer than 65535 samples are not supported"); }
+	if ((uint64_t)P.NX * P.NY > 0x7FFFFFFFull) { free(c); return fail(MC33CU_ERR_ARG, "slices of more than 2^31-1 samples are not supported"); }
 	if ((uint64_t)(P.zhi - P.zlo) * P.NY > 0x7FFFFFFFull / P.WP) { free(c); return fail(MC33CU_ERR_ARG, "too many rows"); }
 	P.mQ = P.Q >= 2 ? (uint32_t)(0x100000000ull / P.Q) : 0u;
 	P.mNY = (uint32_t)(0x100000000ull / P.NY);
@@ -1059,9 +995,6 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	return fail(e_ == cudaErrorMemoryAllocation ? MC33CU_ERR_NOMEM : MC33CU_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
 	TRYCU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
-	TRYCU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-	TRYCU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-	TRYCU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	const size_t bm = (size_t)P.Lrows * P.WP;
 	TRY(dalloc(&P.S, bm)); TRY(dalloc(&P.Z, bm));
 	TRYCU(cudaMemsetAsync(P.S, 0, bm * 4, c->stream)); TRYCU(cudaMemsetAsync(P.Z, 0, bm * 4, c->stream));
@@ -1091,6 +1024,8 @@ static int set_geom(mc33cu_ctx *c, const mc33cu_desc *d)
 	P.geom.store = d->store; P.geom.normal_neg = d->normal_neg; P.geom.tsa = d->tsa;
 	for (int i = 0; i < 3; i++) { P.geom.O[i] = d->O[i]; P.geom.D[i] = d->D[i]; }
 	P.geom.ca = d->ca; P.geom.cb = d->cb;
+	for (int i = 0; i < 3; i++) { P.geom.Of[i] = (float)d->O[i]; P.geom.Df[i] = (float)d->D[i]; }
+	P.geom.caf = (float)d->ca; P.geom.cbf = (float)d->cb;
 	for (int i = 0; i < 9; i++) { P.geom.A[i] = d->A[i]; P.geom.Ai[i] = d->Ai[i]; }
 	return MC33CU_OK;
 }
@@ -1308,33 +1243,23 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 {
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
-	// The two emit kernels only depend on the count phase, and they stall on different
-	// things (vertices: sample gathers; cells: instruction issue), so they run side by
-	// side: cells on the side stream, forked and joined with events.  With per-kernel
-	// timing enabled they run one after the other instead.
-	const bool fork = !c->timing;
-	cudaStream_t sc = fork ? c->side_stream : s;
-	if (fork) { CU(cudaEventRecord(c->ev_fork, s)); CU(cudaStreamWaitEvent(sc, c->ev_fork, 0)); }
 	{
-		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (P.cz1 - P.zlo) * P.NY;
+		// cell rows of the slab, plus the point rows above them whose vertices it owns
+		// (the grid's last slice on the last slab)
+		const uint32_t zend = P.pz1 > P.cz1 ? P.pz1 : P.cz1;
+		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (zend - P.zlo) * P.NY;
 		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
-		// (side by side: two resident CTAs of each kernel per SM, so that both really co-run)
 		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, sc>>>(P, rb, re, ngroups);
+		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[4], s));
 	{
-		// rows whose vertices this slab owns
-		const uint32_t rb = (P.pz0 - P.zlo) * P.NY, re = (P.pz1 - P.zlo) * P.NY;
-		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
-		uint32_t grid = (uint32_t)c->n_sm * c->emv_per_sm;
-		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		k_emit_vertices<Sample><<<grid, 256, 0, s>>>(P, rb, re, ngroups);
+		// dense over the vertex ids (the count is only known on the device: persistent grid)
+		k_emit_vertices<Sample><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
 		c->launches++;
 	}
-	if (fork) { CU(cudaEventRecord(c->ev_join, sc)); CU(cudaStreamWaitEvent(s, c->ev_join, 0)); }
 	if (c->timing) { CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
 	CU(cudaGetLastError());
 	return MC33CU_OK;
@@ -1390,13 +1315,24 @@ static void set_iso(mc33cu_ctx *c, double iso)
 	else { P.ieq_lo = 1; P.ieq_hi = 0; }
 }
 
-static void set_out(mc33cu_ctx *c, const mc33cu_out *o)
+static int set_out(mc33cu_ctx *c, const mc33cu_out *o)
 {
 	Params &P = c->P;
+	if (o->capV > c->vtask_cap) {
+		// (first extraction, or a larger output than any before: not on the steady-state path)
+		CU(cudaStreamSynchronize(c->stream));
+		cudaFree(c->vtask);
+		c->vtask = nullptr; c->vtask_cap = 0;
+		const uint64_t cap = (uint64_t)o->capV + o->capV / 8 + 1024;
+		CU(cudaMalloc((void **)&c->vtask, cap * sizeof(uint64_t)));
+		c->vtask_cap = cap;
+	}
+	P.vtask = c->vtask;
 	P.V = o->V; P.N = o->N; P.color = o->color; P.T = o->T; P.vkey = o->vkey; P.tcell = o->tcell;
 	P.capV = o->capV; P.capT = o->capT;
 	P.vbase = o->vbase; P.vbase_next = o->vbase_next; P.dbases = o->dev_bases;
 	P.color_value = o->color_value;
+	return MC33CU_OK;
 }
 
 static int fetch_totals(mc33cu_ctx *c)
@@ -1459,7 +1395,8 @@ extern "C" int mc33cu_emit_device(mc33cu_ctx *c, const mc33cu_out *o)
 	if (!c || !o) return fail(MC33CU_ERR_ARG, "null argument");
 	if (!c->counted) return fail(MC33CU_ERR_STATE, "mc33cu_count has not run");
 	CU(cudaSetDevice(c->device));
-	set_out(c, o);
+	int rc = set_out(c, o);
+	if (rc) return rc;
 	return dispatch_emit(c);
 }
 
@@ -1469,8 +1406,9 @@ extern "C" int mc33cu_extract_device(mc33cu_ctx *c, double iso, const mc33cu_out
 	if (!c->P.data) return fail(MC33CU_ERR_STATE, "no grid bound");
 	CU(cudaSetDevice(c->device));
 	set_iso(c, iso);
-	set_out(c, o);
-	int rc = dispatch_count(c);
+	int rc = set_out(c, o);
+	if (rc) return rc;
+	rc = dispatch_count(c);
 	if (rc) return rc;
 	rc = dispatch_emit(c);
 	if (rc) return rc;
@@ -1524,8 +1462,9 @@ extern "C" int mc33cu_emit_host(mc33cu_ctx *c, void *V, float *N, int32_t *color
 	o.V = c->oV; o.N = c->oN; o.color = c->oC; o.T = c->oT;
 	o.capV = (uint32_t)k.nV; o.capT = (uint32_t)k.nT;
 	o.color_value = color_value;
-	set_out(c, &o);
-	int rc = dispatch_emit(c);
+	int rc = set_out(c, &o);
+	if (rc) return rc;
+	rc = dispatch_emit(c);
 	if (rc) return rc;
 	cudaStream_t s = c->stream;
 	CU(cudaMemcpyAsync(T, c->oT, k.nT * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

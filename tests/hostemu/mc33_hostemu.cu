@@ -102,52 +102,47 @@ static void run(Params &P, bool emit)
 		P.totals->nCentre = (uint32_t)bc; P.totals->nT = (uint32_t)bt; P.totals->nSharedAll = (uint32_t)bv;
 	}
 	if (!emit) return;
-	// K3, vertices
-	for (uint32_t lr = (P.pz0 - P.zlo) * P.NY; lr < (P.pz1 - P.zlo) * P.NY; lr++) {
-		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
-		for (uint32_t w = 0; w < P.W; w++) {
-			WordRec rec; CellWords cw;
-			word_rec(z, y, w, rec, cw);
-			const uint32_t zw = (gz && P.rowZ[lr] == P.zepoch) ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
-			for (int a = 0; a < 3; a++) {
-				uint32_t m = a == 0 ? rec.X : (a == 1 ? rec.Y : rec.Z);
-				uint32_t id = plane_base_local(P, lr, w, a);
-				while (m) {
-					int b = ffs32(m);
-					m &= m - 1;
-					emit_vertex_task<Sample>(P, (w << 5) + b, y, z, a, a == 0 && ((zw >> b) & 1), id++);
-				}
-			}
-		}
-	}
-	// K3, cells: triangles (+ centre vertices) in sweep order
+	// K4, cells: triangles (+ centre vertices) in sweep order, vertex tasks
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
 	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - P.totals->nShared;
-	for (uint32_t lr = (P.cz0 - P.zlo) * P.NY; lr < (P.cz1 - P.zlo) * P.NY; lr++) {
+	const uint32_t zend = P.pz1 > P.cz1 ? P.pz1 : P.cz1;
+	for (uint32_t lr = (P.cz0 - P.zlo) * P.NY; lr < (zend - P.zlo) * P.NY; lr++) {
 		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
-		if (y >= P.ny) continue;
+		const bool own_c = row_cells_owned(P, z, y), own_p = row_points_owned(P, z);
+		if (!own_c && !own_p) continue;
 		uint32_t tid = P.rowBT[lr], cl = P.totals->nShared + P.rowBC[lr];
-		for (uint32_t w = 0; w < P.WC; w++) {
+		for (uint32_t w = 0; w < P.W; w++) {
 			WordRec rec; CellWords cw; CellPairs cp;
 			word_rec(z, y, w, rec, cw);
-			uint32_t act = rec.act;
+			// visited: active cells and grid points that own a vertex (as k_emit_cells does)
+			uint32_t act = (own_c ? rec.act : 0u) | (own_p ? (rec.X | rec.Y | rec.Z) : 0u);
 			if (!act) continue;
-			// the drain side: generic path with on-iso samples, else the fast per-cell path
-			if (gz) {
-				word_masks(P, z, y, w, gz, rec, cw);
-				cell_pairs(P, z, y, w, gz, rec, cw, cp);
-			}
+			bool pairs = false;
 			while (act) {
 				int b = ffs32(act);
 				act &= act - 1;
 				const uint32_t x = (w << 5) + b;
+				const bool cellok = own_c && x < P.nx;
 				uint32_t ids[13];
-				unsigned idx, zm = 0;
+				unsigned idx = 0, zm = 0;
 				if (gz) {
+					if (own_p) put_vertex_tasks_generic(P, x, y, z);
+					// (with on-iso samples a point can own a vertex while its cell is inactive)
+					if (!cellok || !((rec.act >> b) & 1u)) continue;
+					// the drain side: generic path with on-iso samples
+					if (!pairs) { word_masks(P, z, y, w, gz, rec, cw); cell_pairs(P, z, y, w, gz, rec, cw, cp); pairs = true; }
 					idx = cell_index(cw.c, 1, b);
 					zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
 				} else {
-					idx = cell_fast(P, x, y, z, z == P.hz ? vbn : vb, z + 1 == P.hz ? vbn : vb, ids);
+					unsigned own;
+					const uint32_t g0 = z == P.hz ? vbn : vb;
+					idx = cell_fast(P, x, y, z, g0, z + 1 == P.hz ? vbn : vb, ids, own);
+					if (own_p) {
+						if (own & 1u) put_vertex_task(P, ids[8] - g0, lr, x, 0u, false);
+						if (own & 2u) put_vertex_task(P, ids[0] - g0, lr, x, 1u, false);
+						if (own & 4u) put_vertex_task(P, ids[3] - g0, lr, x, 2u, false);
+					}
+					if (!cellok) continue;
 				}
 				const CellPattern cpat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
 				const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
@@ -175,6 +170,8 @@ static void run(Params &P, bool emit)
 			}
 		}
 	}
+	// K3, vertices: dense over the ids, each from the task left in its slot
+	for (uint32_t id = 0; id < P.totals->nShared && id < P.capV; id++) run_vertex_task<Sample>(P, id);
 }
 
 extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, const mc33cu_out *o,
@@ -195,6 +192,8 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.geom.store = d->store; P.geom.normal_neg = d->normal_neg; P.geom.tsa = d->tsa;
 	for (int i = 0; i < 3; i++) { P.geom.O[i] = d->O[i]; P.geom.D[i] = d->D[i]; }
 	P.geom.ca = d->ca; P.geom.cb = d->cb;
+	for (int i = 0; i < 3; i++) { P.geom.Of[i] = (float)d->O[i]; P.geom.Df[i] = (float)d->D[i]; }
+	P.geom.caf = (float)d->ca; P.geom.cbf = (float)d->cb;
 	for (int i = 0; i < 9; i++) { P.geom.A[i] = d->A[i]; P.geom.Ai[i] = d->Ai[i]; }
 	P.iso = d->dtype == MC33CU_F64 ? iso + 0.0 : (double)((float)iso + 0.0f);
 	std::vector<uint32_t> S((size_t)P.Lrows * P.WP, 0), Z((size_t)P.Lrows * P.WP, 0), rb(((size_t)P.Lrows + 1) * 3);
@@ -207,6 +206,8 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.rowBV = rb.data(); P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
 	P.totals = &tot;
 	bool emit = o != nullptr;
+	std::vector<uint64_t> vtask(emit ? (size_t)o->capV + 1 : 1);
+	P.vtask = vtask.data();
 	if (emit) {
 		P.V = o->V; P.N = o->N; P.color = o->color; P.T = o->T; P.vkey = o->vkey; P.tcell = o->tcell;
 		P.capV = o->capV; P.capT = o->capT; P.vbase = o->vbase; P.vbase_next = o->vbase_next; P.dbases = o->dev_bases;
