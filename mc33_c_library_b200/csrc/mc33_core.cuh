@@ -689,6 +689,39 @@ MC_HDN uint64_t count_cells_quad(const Params &P, const Tables &tb, uint32_t z, 
 	return (uint64_t)nt | ((uint64_t)nc << 32);
 }
 
+// ---------------------------------------------------------------------------
+// Triangles of the SIMPLE cells of a word, 32 cells at a time, without looking at any
+// cell.  The cases the reference triangulates without a test (base cases 1, 2, 5, 8, 9,
+// 11, 14 of MC33_all_tables, marching_cubes_33.c:693-696) are exactly the cells whose
+// surface is one disc, and a disc through k crossed edges has k - 2 triangles; every
+// other active cell has an ambiguous face (corner signs alternating round the face) or
+// is case 4 (two corners on a body diagonal against the other six) -- checked against
+// the table for all 256 indices in tests/test_hostemu_vs_oracle.py.  So
+//   triangles(simple cells) = sum over the 12 edges of popc(crossed & simple) - 2 popc(simple)
+// and only the complex cells (returned in cx) are walked one by one.
+// c[k] = sign word of corner k (bit b = cell b), act = active cells.
+// ---------------------------------------------------------------------------
+MC_HD uint32_t count_simple_cells(const uint32_t *c, uint32_t act, uint32_t &cx)
+{
+	const uint32_t e01 = c[0] ^ c[1], e12 = c[1] ^ c[2], e32 = c[3] ^ c[2], e03 = c[0] ^ c[3];
+	const uint32_t e45 = c[4] ^ c[5], e56 = c[5] ^ c[6], e76 = c[7] ^ c[6], e47 = c[4] ^ c[7];
+	const uint32_t e04 = c[0] ^ c[4], e15 = c[1] ^ c[5], e26 = c[2] ^ c[6], e37 = c[3] ^ c[7];
+	// ambiguous faces {0,1,5,4} {1,2,6,5} {3,2,6,7} {0,3,7,4} {0,1,2,3} {4,5,6,7}
+	uint32_t m = (e01 & e15 & e45) | (e12 & e26 & e56) | (e32 & e26 & e76) |
+	             (e03 & e37 & e47) | (e01 & e12 & e32) | (e45 & e56 & e76);
+	// case 4, diagonal {0,6} {1,7} {2,4} {3,5}: both differ from a neighbour, the other six are equal
+	m |= e01 & e26 & ~(e12 | e32 | e37 | e47 | e45);
+	m |= e01 & e37 & ~(e03 | e32 | e26 | e56 | e45);
+	m |= e12 & e04 & ~(e01 | e03 | e37 | e76 | e56);
+	m |= e03 & e15 & ~(e01 | e12 | e26 | e76 | e47);
+	cx = act & m;
+	const uint32_t sm = act & ~m;
+	const int n = popc32(e01 & sm) + popc32(e12 & sm) + popc32(e32 & sm) + popc32(e03 & sm) +
+	              popc32(e45 & sm) + popc32(e56 & sm) + popc32(e76 & sm) + popc32(e47 & sm) +
+	              popc32(e04 & sm) + popc32(e15 & sm) + popc32(e26 & sm) + popc32(e37 & sm);
+	return (uint32_t)(n - 2 * popc32(sm));
+}
+
 // generic form (any grid, on-iso samples included) straight from the bitmaps
 template <typename Sample>
 MC_COLD void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,

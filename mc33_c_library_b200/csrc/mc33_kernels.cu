@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params
 						const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
 						uint64_t pv[4];
 						uint32_t act[4];
+						uint32_t nts = 0;
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
 							WordRec rec;
@@ -460,10 +461,13 @@ __global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params
 							quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c && hasZ, rec, c);
 							if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
 							pv[k] = pack_planes(rec);
-							act[k] = rec.act;
+							// simple cells are counted 32 at a time; only the complex ones are walked
+							act[k] = 0;
+							if (rec.act) nts += count_simple_cells(c, rec.act, act[k]);
 						}
 						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
-						if (act[0] | act[1] | act[2] | act[3]) tt = count_cells_quad<Sample>(P, tb, z, y, q, act, q00, q10, q01, q11);
+						tt = nts;
+						if (act[0] | act[1] | act[2] | act[3]) tt += count_cells_quad<Sample>(P, tb, z, y, q, act, q00, q10, q01, q11);
 					} else {
 						uint64_t pv[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -600,7 +604,7 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
 #define CQ 256
 #define EM_SCR 512      // per-warp scratch words: 13 ids x 32 lanes, or 8 (mask, base) pairs x 32 lanes
 #ifndef EMV_MINB
-#define EMV_MINB 4      // resident CTAs per SM the emit kernels are compiled for (register cap)
+#define EMV_MINB 5      // resident CTAs per SM the emit kernels are compiled for (register cap)
 #endif
 #ifndef EMC_MINB
 #define EMC_MINB 4

@@ -81,11 +81,15 @@ static void run(Params &P, bool emit)
 					} else {
 						// the kernel's merged walk over the quad: give it this word's cells only
 						uint32_t act4[4] = {0, 0, 0, 0};
-						act4[w & 3] = rec.act;
+						// simple cells 32 at a time, the complex ones one by one (as k_count does)
+						uint32_t cxm = 0;
+						const uint32_t nts = rec.act ? count_simple_cells(cw.c, rec.act, cxm) : 0u;
+						act4[w & 3] = cxm;
 						const bool hasY = y < P.ny, hasZ = z < P.nz;
 						const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u, i00 = (uint64_t)lr * P.WP + (w & ~3u);
 						cc = count_cells_quad<Sample>(P, tb, z, y, w >> 2, act4, load_quad(P.S, i00), load_quad(P.S, i00 + dY),
 						                              load_quad(P.S, i00 + dZ), load_quad(P.S, i00 + dY + dZ));
+						cc += nts;
 					}
 				}
 				P.wpreV[(uint64_t)lr * P.WP + w] = av;
@@ -227,3 +231,11 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	}
 	return tot.overflow ? MC33CU_ERR_CAPACITY : 0;
 }
+
+// the bit-parallel triangle count of k_count (mc33_core.cuh count_simple_cells), for
+// the exhaustive check against the case table
+extern "C" uint32_t mc33emu_count_simple(const uint32_t *c8, uint32_t act, uint32_t *cx)
+{
+	return count_simple_cells(c8, act, *cx);
+}
+extern "C" const uint16_t *mc33emu_simple256(void) { return MC33_SIMPLE256; }

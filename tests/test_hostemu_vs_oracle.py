@@ -79,3 +79,28 @@ def test_slab_decomposition(world, variant, iso, scale):
     assert np.array_equal(inv[m.T.astype(np.int64)], whole.T.astype(np.int64))
     assert np.array_equal(m.V[order_m], whole.V[order_w])
     assert np.array_equal(m.N[order_m], whole.N[order_w], equal_nan=True)
+
+
+def test_bit_parallel_triangle_count_matches_case_table():
+    """count_simple_cells (k_count): for every one of the 256 indices, alone and packed 32
+    per word in random order, complex cells are exactly those without a fixed
+    triangulation and the simple ones sum to the table's triangle counts."""
+    import ctypes as C
+    from support import hostemu_lib
+    emu = hostemu_lib()
+    emu.mc33emu_count_simple.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
+    emu.mc33emu_count_simple.restype = C.c_uint32
+    emu.mc33emu_simple256.restype = C.POINTER(C.c_uint16)
+    simple = np.ctypeslib.as_array(emu.mc33emu_simple256(), shape=(256,)).copy()
+    rng = np.random.default_rng(3)
+    words = [np.array([i] * 32) for i in range(256)] + [rng.integers(0, 256, 32) for _ in range(400)]
+    for idx in words:
+        c = (C.c_uint32 * 8)()
+        for k in range(8):                      # corner k <-> index bit 7-k
+            c[k] = int(sum(((int(i) >> (7 - k)) & 1) << b for b, i in enumerate(idx)))
+        act = int(sum(1 << b for b, i in enumerate(idx) if i not in (0, 255)))
+        cx = C.c_uint32()
+        nt = emu.mc33emu_count_simple(c, act, C.byref(cx))
+        want_cx = int(sum(1 << b for b, i in enumerate(idx) if i not in (0, 255) and simple[i] == 0xFFFF))
+        want_nt = int(sum(int(simple[i]) >> 12 for i in idx if i not in (0, 255) and simple[i] != 0xFFFF))
+        assert cx.value == want_cx and nt == want_nt
