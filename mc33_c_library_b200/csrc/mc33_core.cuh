@@ -136,6 +136,8 @@ struct Totals {                   // written by the scan kernel
 	uint32_t nSharedAll;          // shared vertices counted (own + halo slice)
 	uint32_t range;               // 1: more than 2^32-1 vertices or triangles
 	uint32_t anyZ;                // classify: some sample is exactly on the isovalue
+	uint32_t ticket;              // next row group of the cell kernel (dynamic distribution; the vertex kernel re-arms it)
+	uint32_t pad_[3];
 };
 
 struct Tables {
@@ -158,6 +160,8 @@ struct Params {
 	uint32_t Lrows;               // (zhi-zlo)*NY
 	uint32_t mQ, mNY;             // floor(2^32/Q), floor(2^32/NY) for fastdiv
 	uint32_t *S, *Z;              // bitmaps [Lrows][WP]; words >= W of a row are zero
+	uint32_t *A;                  // [Lrows][WP] visit bitmap left by the count kernel for the cell kernel: active
+	                              // cells of the row, and grid points that own a vertex this slab emits
 	uint32_t *rowZ;               // [Lrows] hint: == zepoch when the row has an on-iso sample in this extraction
 	uint32_t zepoch;
 	uint64_t *wpreV;              // [Lrows][WP] X | Y<<21 | Z<<42: row-local index of each plane's first vertex
@@ -722,16 +726,19 @@ MC_HD uint32_t count_simple_cells(const uint32_t *c, uint32_t act, uint32_t &cx)
 	return (uint32_t)(n - 2 * popc32(sm));
 }
 
+MC_HD bool row_points_owned(const Params &P, uint32_t z);
+
 // generic form (any grid, on-iso samples included) straight from the bitmaps
 template <typename Sample>
 MC_COLD void count_word(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, bool gz,
-                       bool own_points, bool own_cells, uint64_t &cv, uint64_t &cc)
+                       bool own_points, bool own_cells, uint64_t &cv, uint64_t &cc, uint32_t &visit)
 {
 	WordRec rec;
 	CellWords cw;
 	if (gz) word_masks_generic(P, z, y, w, rec, cw); else word_masks(P, z, y, w, false, rec, cw);
 	if (!own_points) { rec.X = rec.Y = rec.Z = 0; }
 	if (!own_cells) rec.act = 0;
+	visit = rec.act | (row_points_owned(P, z) ? (rec.X | rec.Y | rec.Z) : 0u);
 	cv = pack_planes(rec);
 	cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
 }
@@ -1059,28 +1066,31 @@ MC_HDN unsigned cell_fast(const Params &P, uint32_t x, uint32_t y, uint32_t z, u
 	// that does not exist is replaced by the row itself, which empties the plane towards it)
 	const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? P.NY : 0u;
 	const uint32_t l00 = (z - P.zlo) * P.NY + y, l10 = l00 + uy, l01 = l00 + uz, l11 = l01 + uy;
-	const uint64_t i00 = (uint64_t)l00 * P.WP + w, i10 = (uint64_t)l10 * P.WP + w, i01 = (uint64_t)l01 * P.WP + w, i11 = (uint64_t)l11 * P.WP + w;
+	// word indices fit 32 bits (checked at context creation)
+	const uint32_t i00 = l00 * P.WP + w, i10 = l10 * P.WP + w, i01 = l01 * P.WP + w, i11 = l11 * P.WP + w;
 	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
 	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
 	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
 	const uint64_t p00 = P.wpreV[i00], p10 = P.wpreV[i10], p01 = P.wpreV[i01], p11 = P.wpreV[i11];
 	const uint32_t r00 = P.rowBV[l00] + g0, r10 = P.rowBV[l10] + g0, r01 = P.rowBV[l01] + g1, r11 = P.rowBV[l11] + g1;
-	const uint32_t vp = mask_le(w, P.nx), vx = mask_le(w, P.nx - 1);
-	const uint32_t lo0 = (1u << b) - 1u, lo1 = (lo0 << 1) | 1u;     // bits below x, below x+1
+	// bits beyond x = nx are zero in S, so only the X plane needs a mask: the last point has no X edge
+	const uint32_t vx = mask_le(w, P.nx - 1);
+	const uint32_t lo0 = (1u << b) - 1u;                            // bits below x
 	// plane masks (suffix = dy dz of the point row) and the id of their first vertex in word w
-	const uint32_t mX00 = (s00 ^ x00) & vx, mY00 = (s00 ^ s10) & vp, mZ00 = (s00 ^ s01) & vp;
-	const uint32_t mX10 = (s10 ^ x10) & vx, mZ10 = (s10 ^ s11) & vp;
-	const uint32_t mX01 = (s01 ^ x01) & vx, mY01 = (s01 ^ s11) & vp;
+	const uint32_t mX00 = (s00 ^ x00) & vx, mY00 = s00 ^ s10, mZ00 = s00 ^ s01;
+	const uint32_t mX10 = (s10 ^ x10) & vx, mZ10 = s10 ^ s11;
+	const uint32_t mX01 = (s01 ^ x01) & vx, mY01 = s01 ^ s11;
 	const uint32_t mX11 = (s11 ^ x11) & vx;
 	const uint32_t bX00 = r00 + fldV(p00, 0), bY00 = r00 + fldV(p00, 1), bZ00 = r00 + fldV(p00, 2);
 	const uint32_t bX10 = r10 + fldV(p10, 0), bZ10 = r10 + fldV(p10, 2);
 	const uint32_t bX01 = r01 + fldV(p01, 0), bY01 = r01 + fldV(p01, 1);
 	const uint32_t bX11 = r11 + fldV(p11, 0);
 	// edges: 0:(0,1)y 1:(1,2)z 2:(3,2)y 3:(0,3)z 4:(4,5)y 5:(5,6)z 6:(7,6)y 7:(4,7)z 8:(0,4)x 9:(1,5)x 10:(2,6)x 11:(3,7)x
-	id[0] = bY00 + (uint32_t)popc32(mY00 & lo0);  id[4] = bY00 + (uint32_t)popc32(mY00 & lo1);
-	id[1] = bZ10 + (uint32_t)popc32(mZ10 & lo0);  id[5] = bZ10 + (uint32_t)popc32(mZ10 & lo1);
-	id[2] = bY01 + (uint32_t)popc32(mY01 & lo0);  id[6] = bY01 + (uint32_t)popc32(mY01 & lo1);
-	id[3] = bZ00 + (uint32_t)popc32(mZ00 & lo0);  id[7] = bZ00 + (uint32_t)popc32(mZ00 & lo1);
+	// (the edge at x+1 follows the one at x in the same plane: one more if the point x carries a vertex)
+	id[0] = bY00 + (uint32_t)popc32(mY00 & lo0);  id[4] = id[0] + ((mY00 >> b) & 1u);
+	id[1] = bZ10 + (uint32_t)popc32(mZ10 & lo0);  id[5] = id[1] + ((mZ10 >> b) & 1u);
+	id[2] = bY01 + (uint32_t)popc32(mY01 & lo0);  id[6] = id[2] + ((mY01 >> b) & 1u);
+	id[3] = bZ00 + (uint32_t)popc32(mZ00 & lo0);  id[7] = id[3] + ((mZ00 >> b) & 1u);
 	id[8] = bX00 + (uint32_t)popc32(mX00 & lo0);
 	id[9] = bX10 + (uint32_t)popc32(mX10 & lo0);
 	id[10] = bX11 + (uint32_t)popc32(mX11 & lo0);

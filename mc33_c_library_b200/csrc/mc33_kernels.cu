@@ -452,13 +452,15 @@ __global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params
 						const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
 						const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
 						uint64_t pv[4];
-						uint32_t act[4];
+						uint32_t act[4], vis[4];
 						uint32_t nts = 0;
+						const uint32_t pm = row_points_owned(P, z) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
 							WordRec rec;
 							uint32_t c[8];
 							quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c && hasZ, rec, c);
+							vis[k] = rec.act | ((rec.X | rec.Y | rec.Z) & pm);
 							if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
 							pv[k] = pack_planes(rec);
 							// simple cells are counted 32 at a time; only the complex ones are walked
@@ -466,19 +468,22 @@ __global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params
 							if (rec.act) nts += count_simple_cells(c, rec.act, act[k]);
 						}
 						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
+						*reinterpret_cast<uint4 *>(P.A + i00) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
 						tt = nts;
 						if (act[0] | act[1] | act[2] | act[3]) tt += count_cells_quad<Sample>(P, tb, z, y, q, act, q00, q10, q01, q11);
 					} else {
 						uint64_t pv[4] = {0, 0, 0, 0};
+						uint32_t vis[4] = {0, 0, 0, 0};
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
 							const uint32_t w = 4 * q + k;
 							if (w < P.W) {
 								uint64_t cc;
-								count_word<Sample>(P, tb, z, y, w, true, own_p, own_c, pv[k], cc);
+								count_word<Sample>(P, tb, z, y, w, true, own_p, own_c, pv[k], cc, vis[k]);
 								tt += cc;
 							}
 						}
+						*reinterpret_cast<uint4 *>(P.A + (uint64_t)lr * P.WP + 4 * q) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
 						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
 					}
 				}
@@ -609,7 +614,8 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
 #ifndef EMC_MINB
 #define EMC_MINB 4
 #endif
-#define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR) * 4)
+#define EM_ROWT 64      // per-warp row table words: (y, z) of the group's rows (G <= 32)
+#define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR + EM_ROWT) * 4)
 
 // K3, dense: thread id computes vertex id from the task the cell kernel left in the
 // vertex's own slot of N (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
@@ -618,7 +624,10 @@ template <typename Sample>
 __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_constant__ Params P)
 {
 	const uint32_t nS = P.totals->nShared, n = min(nS, P.capV);
-	if (nS > P.capV && blockIdx.x == 0 && threadIdx.x == 0) P.totals->overflow = 1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		if (nS > P.capV) P.totals->overflow = 1;
+		P.totals->ticket = 0;                  // re-arm the cell kernel's group counter (it has finished: stream order)
+	}
 	for (uint32_t id = blockIdx.x * 256u + threadIdx.x; id < n; id += gridDim.x * 256u) run_vertex_task<Sample>(P, id);
 }
 
@@ -630,15 +639,28 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + wid * CQ;
 	uint32_t *scr = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * CQ + wid * EM_SCR;
+	uint2 *rowt = reinterpret_cast<uint2 *>((uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (CQ + EM_SCR) + wid * EM_ROWT);
 	const bool anyz = P.totals->anyZ != 0;
 	const uint32_t nShared = P.totals->nShared;
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
 	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
 	const uint32_t npass = (P.Q + 31) / 32;
 
-	for (uint32_t g = blockIdx.x * EM_WARPS + wid; g < ngroups; g += gridDim.x * EM_WARPS) {
+	// Row groups are handed out by a ticket counter: the work of a group follows the surface,
+	// and with a fixed assignment the slowest warp set the kernel time (a quarter of the warp
+	// slots sat empty on the gyroid).  The next ticket is fetched while the current group runs.
+	uint32_t g = 0, gnext = 0;
+	if (lane == 0) g = atomicAdd(&P.totals->ticket, 1u);
+	g = __shfl_sync(0xFFFFFFFFu, g, 0);
+	for (; g < ngroups; g = __shfl_sync(0xFFFFFFFFu, gnext, 0)) {
+		if (lane == 0) gnext = atomicAdd(&P.totals->ticket, 1u);
 		const uint32_t lr0 = row_begin + g * P.G, lrE = min(lr0 + P.G, row_end);
 		const bool gz = group_has_oniso(P, anyz, lr0, lane);
+		if (lane < P.G) {
+			const uint32_t lr = lr0 + lane, zl = fastdiv(lr, P.NY, P.mNY);
+			rowt[lane] = make_uint2(lr - zl * P.NY, zl + P.zlo);
+		}
+		__syncwarp();
 		// ======================= cells =======================
 		const uint32_t tbase = P.rowBT[lr0], cloc0 = nShared + P.rowBC[lr0];
 		uint32_t runT = 0, runC = 0;                             // triangles / centres of the group so far
@@ -649,37 +671,11 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 			{
 				const uint32_t lr = lr0 + r;
 				if (r < P.G && q < P.Q && lr < lrE) {
-					const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
-					// visited: active cells, and grid points that own a vertex (on the high faces
-					// of the grid those are points without a cell)
-					const bool own_c = row_cells_owned(P, z, y), own_p = row_points_owned(P, z);
-					if (own_c || own_p) {
-						uint32_t act[4] = {0, 0, 0, 0};
-						const uint32_t pm = own_p ? 0xFFFFFFFFu : 0u;
-						if (!gz) {
-							const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
-							const uint64_t dY = y < P.ny ? P.WP : 0u, dZ = z < P.nz ? (uint64_t)P.NY * P.WP : 0u;
-							const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
-							const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
-#pragma unroll
-							for (int k = 0; k < 4; k++) {
-								WordRec rec;
-								uint32_t c[8];
-								quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c, rec, c);
-								act[k] = rec.act | ((rec.X | rec.Y | rec.Z) & pm);
-							}
-						} else {
-#pragma unroll
-							for (int k = 0; k < 4; k++) {
-								if (4 * q + k < P.W) {
-									WordRec rec; CellWords cw;
-									word_masks_generic(P, z, y, 4 * q + k, rec, cw);
-									act[k] = (own_c ? rec.act : 0u) | ((rec.X | rec.Y | rec.Z) & pm);
-								}
-							}
-						}
-						act0 = act[0]; act1 = act[1]; act2 = act[2]; act3 = act[3];
-					}
+					// visited: active cells, and grid points that own a vertex (on the high faces of
+					// the grid those are points without a cell); the count kernel left the mask,
+					// rows this slab neither has cells nor emits vertices for stay zero
+					const uint4 a = *reinterpret_cast<const uint4 *>(P.A + (uint64_t)lr * P.WP + 4 * q);
+					act0 = a.x; act1 = a.y; act2 = a.z; act3 = a.w;
 				}
 			}
 			const uint32_t na = (uint32_t)(__popc(act0) + __popc(act1) + __popc(act2) + __popc(act3));
@@ -718,8 +714,8 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 						const uint32_t e = cq[j0 + lane];
 						x = e & 0xFFFFu; b = x & 31u;
 						const uint32_t lr = lr0 + (e >> 16);
-						const uint32_t zl = fastdiv(lr, P.NY, P.mNY);
-						y = lr - zl * P.NY; z = zl + P.zlo;
+						const uint2 yz = rowt[e >> 16];
+						y = yz.x; z = yz.y;
 						const bool ownp = row_points_owned(P, z);
 						cellok = row_cells_owned(P, z, y) && x < P.nx;
 						if (!gz) {
@@ -889,7 +885,7 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	Params &P = c->P;
-	cudaFree(P.S); cudaFree(P.Z); cudaFree(P.rowZ); cudaFree(P.wpreV);
+	cudaFree(P.S); cudaFree(P.Z); cudaFree(P.A); cudaFree(P.rowZ); cudaFree(P.wpreV);
 	cudaFree(P.rowBV); cudaFree(P.totals);
 	cudaFree(c->blk_sum);
 	cudaFree(c->vtask);
@@ -1002,6 +998,8 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	const size_t bm = (size_t)P.Lrows * P.WP;
 	TRY(dalloc(&P.S, bm)); TRY(dalloc(&P.Z, bm));
 	TRYCU(cudaMemsetAsync(P.S, 0, bm * 4, c->stream)); TRYCU(cudaMemsetAsync(P.Z, 0, bm * 4, c->stream));
+	TRY(dalloc(&P.A, bm));
+	TRYCU(cudaMemsetAsync(P.A, 0, bm * 4, c->stream));
 	TRY(dalloc(&P.rowZ, (size_t)P.Lrows));
 	TRYCU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows * 4, c->stream));
 	P.zepoch = 0;

@@ -75,6 +75,8 @@ static void run(Params &P, bool emit)
 					word_rec(z, y, w, rec, cw);
 					if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
 					if (!own_c) rec.act = 0;
+					// visit mask for the cell kernel: active cells, points owning a vertex emitted here
+					P.A[(uint64_t)lr * P.WP + w] = rec.act | (row_points_owned(P, z) ? (rec.X | rec.Y | rec.Z) : 0u);
 					cv = pack_planes(rec);
 					if (gz) {
 						cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
@@ -118,8 +120,8 @@ static void run(Params &P, bool emit)
 		for (uint32_t w = 0; w < P.W; w++) {
 			WordRec rec; CellWords cw; CellPairs cp;
 			word_rec(z, y, w, rec, cw);
-			// visited: active cells and grid points that own a vertex (as k_emit_cells does)
-			uint32_t act = (own_c ? rec.act : 0u) | (own_p ? (rec.X | rec.Y | rec.Z) : 0u);
+			// visited: active cells and grid points that own a vertex (the mask k_count left)
+			uint32_t act = P.A[(uint64_t)lr * P.WP + w];
 			if (!act) continue;
 			bool pairs = false;
 			while (act) {
@@ -201,7 +203,8 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	for (int i = 0; i < 9; i++) { P.geom.A[i] = d->A[i]; P.geom.Ai[i] = d->Ai[i]; }
 	P.iso = d->dtype == MC33CU_F64 ? iso + 0.0 : (double)((float)iso + 0.0f);
 	std::vector<uint32_t> S((size_t)P.Lrows * P.WP, 0), Z((size_t)P.Lrows * P.WP, 0), rb(((size_t)P.Lrows + 1) * 3);
-	std::vector<uint32_t> rz(P.Lrows);
+	std::vector<uint32_t> rz(P.Lrows), A((size_t)P.Lrows * P.WP, 0);
+	P.A = A.data();
 	P.zepoch = 1;
 	std::vector<uint64_t> wv((size_t)P.Lrows * P.WP);
 	Totals tot;
