@@ -320,6 +320,9 @@ def run_ours(args):
               "emit_vertices": (nV_avg - nC_avg) * 28, "emit_cells": nT_avg * 12 + nC_avg * 28}
     kb = kbytes[knames[dom]]
     achieved = kb / (kt[dom] * 1e-3) * 1e-9 if kt[dom] > 0 else 0.0
+    per_kernel = {n: {"ms": float(t), "algorithmic_bytes": float(kbytes[n]),
+                      "achieved_gbs": float(kbytes[n] / (t * 1e-3) * 1e-9) if t > 0 else 0.0} for n, t in zip(knames, kt)}
+    traffic = ncu_traffic(knames[dom])
 
     out = None
     if rank == 0:
@@ -336,8 +339,10 @@ def run_ours(args):
                             "frac_of_hbm_peak": pipeline_gbs / hbm_peak, "peak_gbs": hbm_peak, "peak_source": peak_src},
                "kernel_ms": dict(zip(knames, [float(x) for x in kt])),
                "roofline": {"bound": "hbm", "kernel": knames[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                            "algorithmic_bytes_per_launch": kb},
+                            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": kb, "per_kernel": per_kernel,
+                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel in "
+                                              "profiles/r1_ncu_full_summary.csv (one ncu --set full capture, iso 0.0)"},
                "gpu_launches": int(launches), "clocks": clocks}
     # ---- e2e: the drop-in C API with host buffers (rank 0, one GPU) ----------------
     if rank == 0:
@@ -391,6 +396,24 @@ def cpu_baseline():
     return {"value": len(ISOS) * N_SIDE ** 3 / t * 1e-9, "unit": "Gvoxels/s", "cores": 1, "kind": "reference",
             "sample": f"the full 8-isovalue sweep once on one core ({t:.1f} s), reference built -Ofast -funroll-loops",
             "mtriangles_per_s": sum(r[1] for r in res) / t * 1e-6}
+
+
+def ncu_traffic(kname):
+    """DRAM bytes (read + write) of one launch of the kernel, from the committed ncu summary."""
+    import csv
+    p = ROOT / "profiles" / "r1_ncu_full_summary.csv"
+    if not p.exists():
+        return None
+    def mb(v):
+        x, u = v.split()[:2]
+        return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    for r in csv.DictReader(open(p)):
+        if ("k_" + kname) in r["kernel"]:
+            try:
+                return mb(r["dram__bytes_read.sum"]) + mb(r["dram__bytes_write.sum"])
+            except (KeyError, ValueError):
+                return None
+    return None
 
 
 def main():

@@ -169,6 +169,7 @@ struct Params {
 	uint32_t *rowBV, *rowBT, *rowBC;   // [Lrows+1] slab-local exclusive bases: vertices, triangles, centres
 	Totals *totals;
 	double iso;
+	uint32_t dbg_noz;             // measurement hook (MC33_B200_DEBUG_NOZ=1, tools/ only): classify ignores on-iso samples
 	uint32_t ithr, ieq_lo, ieq_hi, inone;   // integer grids: sample >= ithr <=> above iso; [ieq_lo,ieq_hi] on iso
 	Geom geom;
 	// outputs (device)
@@ -504,6 +505,37 @@ MC_HD Quad load_quad(const uint32_t *B, uint64_t i)   // i = word index, multipl
 #endif
 	q.s[4] = B[i + 4];
 	return q;
+}
+
+// Is there an on-iso sample among the points whose signs decide word k of a cell row:
+// the four corner rows at this word, or their first point of the next word?  When there
+// is none, the no-on-iso formulas (quad_word, cell_fast) yield exactly what the generic
+// walk yields for this word -- every mask they build only involves these points -- so the
+// slow path is taken per WORD, not per row group.
+MC_HD uint32_t quad_oniso(const Quad &z00, const Quad &z10, const Quad &z01, const Quad &z11, int k)
+{
+	return (z00.s[k] | z10.s[k] | z01.s[k] | z11.s[k]) | ((z00.s[k + 1] | z10.s[k + 1] | z01.s[k + 1] | z11.s[k + 1]) & 1u);
+}
+
+// ... for the four words of a quad at once (bit k = word k); out of line: only row groups
+// near an on-iso sample come here, and the count kernel has no registers to spare
+MC_COLD uint32_t quad_oniso_mask(const uint32_t *Zb, uint64_t i00, uint64_t dY, uint64_t dZ)
+{
+	const Quad z00 = load_quad(Zb, i00), z10 = load_quad(Zb, i00 + dY);
+	const Quad z01 = load_quad(Zb, i00 + dZ), z11 = load_quad(Zb, i00 + dY + dZ);
+	uint32_t m = 0;
+#pragma unroll
+	for (int k = 0; k < 4; k++) m |= quad_oniso(z00, z10, z01, z11, k) ? (1u << k) : 0u;
+	return m;
+}
+
+// the same predicate for word w of cell / point row (z,y), straight from the Z bitmap
+MC_HD bool word_oniso(const Params &P, uint32_t z, uint32_t y, uint32_t w)
+{
+	const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? P.NY : 0u;
+	const uint32_t l00 = (z - P.zlo) * P.NY + y;
+	const uint32_t i00 = l00 * P.WP + w, i10 = (l00 + uy) * P.WP + w, i01 = (l00 + uz) * P.WP + w, i11 = (l00 + uz + uy) * P.WP + w;
+	return ((P.Z[i00] | P.Z[i10] | P.Z[i01] | P.Z[i11]) | ((P.Z[i00 + 1] | P.Z[i10 + 1] | P.Z[i01 + 1] | P.Z[i11 + 1]) & 1u)) != 0u;
 }
 
 // word k (0..3, compile time) of quad q of row (z,y) when the grid has NO on-iso
@@ -1169,6 +1201,51 @@ MC_COLD uint32_t emit_cell_triangles_z(const Params &P, const Tables &tb, unsign
 		if (!(tw >> 12)) break;
 	}
 	return n;
+}
+
+// ---------------------------------------------------------------------------
+// One visited cell of a word that holds an on-iso sample (generic rules): the vertex
+// tasks of its low corner point and, if the cell is active, its pattern and on-iso
+// corner mask.  Without an on-iso corner its 12 edge vertex ids go to ids[e * stride]
+// exactly like cell_fast's, so it joins the dense triangle loop; with one, its own lane
+// writes the triangles afterwards (cell_slow_triangles), dropping the zero-area ones.
+// ---------------------------------------------------------------------------
+template <typename Sample>
+MC_COLD CellPattern cell_slow(const Params &P, const Tables &tb, uint32_t x, uint32_t y, uint32_t z, bool ownp, bool cellok,
+                              uint32_t *ids, uint32_t stride, unsigned &zm)
+{
+	CellPattern pat;
+	pat.start = 0; pat.m = 0; pat.ntri = 0; pat.centre = 0;
+	zm = 0;
+	if (ownp) put_vertex_tasks_generic(P, x, y, z);
+	if (!cellok) return pat;
+	const uint32_t w = x >> 5, b = x & 31u;
+	WordRec rec; CellWords cw;
+	word_masks_generic(P, z, y, w, rec, cw);
+	// (with on-iso samples a point can own a vertex while its cell is inactive)
+	if (!((rec.act >> b) & 1u)) return pat;
+	const unsigned idx = cell_index(cw.c, 1, (int)b);
+	zm = cw.zany ? cell_zmask(cw.zc, 1, (int)b) : 0u;
+	pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
+	if (!zm) {
+		CellPairs cp;
+		cell_pairs(P, z, y, w, true, rec, cw, cp);
+		for (unsigned e = 0; e < 12; e++) {
+			unsigned key;
+			ids[e * stride] = corner_vertex(cp.mask, cp.base, 1, e, b, 0u, key);
+		}
+	}
+	return pat;
+}
+
+template <typename Sample>
+MC_COLD void cell_slow_triangles(const Params &P, const Tables &tb, uint32_t x, uint32_t y, uint32_t z, const CellPattern &pat,
+                                 unsigned zm, uint32_t centre_id, uint32_t tid, uint64_t cell)
+{
+	WordRec rec; CellWords cw; CellPairs cp;
+	word_masks_generic(P, z, y, x >> 5, rec, cw);
+	cell_pairs(P, z, y, x >> 5, true, rec, cw, cp);
+	emit_cell_triangles_z(P, tb, x & 31u, pat, zm, centre_id, cp.mask, cp.base, 1, tid, 0u, 0xFFFFFFFFu, cell);
 }
 
 }  // namespace mc33

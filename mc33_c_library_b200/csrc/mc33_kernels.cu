@@ -108,9 +108,10 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // ---------------------------------------------------------------------------
 template <typename Sample> struct Cls {
 	typename Traits<Sample>::Real iso;
-	__device__ __forceinline__ Cls(const Params &P) : iso((typename Traits<Sample>::Real)P.iso) {}
+	bool noz;
+	__device__ __forceinline__ Cls(const Params &P) : iso((typename Traits<Sample>::Real)P.iso), noz(P.dbg_noz != 0) {}
 	__device__ __forceinline__ bool gt(Sample f) const { return f > iso; }
-	__device__ __forceinline__ bool eq(Sample f) const { return f == iso; }
+	__device__ __forceinline__ bool eq(Sample f) const { return f == iso && !noz; }
 };
 template <typename Sample> struct ClsInt {
 	uint32_t thr, eq_lo, eq_span;
@@ -412,8 +413,11 @@ __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32
 // ---------------------------------------------------------------------------
 #define CNT_WARPS 8
 
+#ifndef CNT_MINB
+#define CNT_MINB 4     // resident CTAs per SM k_count is compiled for
+#endif
 template <typename Sample>
-__global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t *blkSum)
+__global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t *blkSum)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
@@ -445,18 +449,21 @@ __global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params
 				const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
 				const bool own_c = row_cells_owned(P, z, y);
 				if (own_p || own_c) {
-					if (!gz) {
-						const bool hasY = y < P.ny, hasZ = z < P.nz;
-						const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u;
-						const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
-						const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
-						const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
-						uint64_t pv[4];
-						uint32_t act[4], vis[4];
-						uint32_t nts = 0;
-						const uint32_t pm = row_points_owned(P, z) ? 0xFFFFFFFFu : 0u;
+					const bool hasY = y < P.ny, hasZ = z < P.nz;
+					const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u;
+					const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
+					const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
+					const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
+					// groups near an on-iso sample: the words it touches take the generic walk
+					const uint32_t slow = gz ? quad_oniso_mask(P.Z, i00, dY, dZ) : 0u;
+					uint64_t pv[4];
+					uint32_t act[4], vis[4];
+					uint32_t nts = 0;
+					const uint32_t pm = row_points_owned(P, z) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-						for (int k = 0; k < 4; k++) {
+					for (int k = 0; k < 4; k++) {
+						act[k] = 0;
+						if (!((slow >> k) & 1u)) {
 							WordRec rec;
 							uint32_t c[8];
 							quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c && hasZ, rec, c);
@@ -464,28 +471,20 @@ __global__ void __launch_bounds__(256, 4) k_count(const __grid_constant__ Params
 							if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
 							pv[k] = pack_planes(rec);
 							// simple cells are counted 32 at a time; only the complex ones are walked
-							act[k] = 0;
 							if (rec.act) nts += count_simple_cells(c, rec.act, act[k]);
+						} else {
+							// (temporaries: the call takes references, and pv / vis must stay in registers)
+							uint64_t cc = 0, pvk = 0;
+							uint32_t visk = 0;
+							if (4 * q + k < P.W) count_word<Sample>(P, tb, z, y, 4 * q + k, true, own_p, own_c, pvk, cc, visk);
+							pv[k] = pvk; vis[k] = visk;
+							tt += cc;
 						}
-						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
-						*reinterpret_cast<uint4 *>(P.A + i00) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
-						tt = nts;
-						if (act[0] | act[1] | act[2] | act[3]) tt += count_cells_quad<Sample>(P, tb, z, y, q, act, q00, q10, q01, q11);
-					} else {
-						uint64_t pv[4] = {0, 0, 0, 0};
-						uint32_t vis[4] = {0, 0, 0, 0};
-#pragma unroll
-						for (int k = 0; k < 4; k++) {
-							const uint32_t w = 4 * q + k;
-							if (w < P.W) {
-								uint64_t cc;
-								count_word<Sample>(P, tb, z, y, w, true, own_p, own_c, pv[k], cc, vis[k]);
-								tt += cc;
-							}
-						}
-						*reinterpret_cast<uint4 *>(P.A + (uint64_t)lr * P.WP + 4 * q) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
-						pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
 					}
+					pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
+					*reinterpret_cast<uint4 *>(P.A + i00) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
+					tt += nts;
+					if (act[0] | act[1] | act[2] | act[3]) tt += count_cells_quad<Sample>(P, tb, z, y, q, act, q00, q10, q01, q11);
 				}
 			}
 			// lane-local exclusive prefix over the four words, then the warp scan
@@ -632,7 +631,8 @@ __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_co
 }
 
 template <typename Sample>
-__global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_constant__ Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups)
+__global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_constant__ Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups,
+                                                                uint32_t ncoarse, uint32_t gfine)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const Tables tb = load_tables(smem);
@@ -649,12 +649,16 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 	// Row groups are handed out by a ticket counter: the work of a group follows the surface,
 	// and with a fixed assignment the slowest warp set the kernel time (a quarter of the warp
 	// slots sat empty on the gyroid).  The next ticket is fetched while the current group runs.
-	uint32_t g = 0, gnext = 0;
-	if (lane == 0) g = atomicAdd(&P.totals->ticket, 1u);
-	g = __shfl_sync(0xFFFFFFFFu, g, 0);
+	// (every warp's first unit is its own index: no burst of same-address atomics at the start)
+	const uint32_t nwarps = gridDim.x * EM_WARPS;
+	uint32_t g = blockIdx.x * EM_WARPS + wid, gnext = 0;
+	// The first ncoarse tickets are whole groups of G rows; the rows after them are handed
+	// out gfine at a time, so that the warps which finish early at the end of the kernel still
+	// find work and the last units are short (a warp takes ~20 us over a whole group).
 	for (; g < ngroups; g = __shfl_sync(0xFFFFFFFFu, gnext, 0)) {
-		if (lane == 0) gnext = atomicAdd(&P.totals->ticket, 1u);
-		const uint32_t lr0 = row_begin + g * P.G, lrE = min(lr0 + P.G, row_end);
+		if (lane == 0) gnext = nwarps + atomicAdd(&P.totals->ticket, 1u);
+		const uint32_t lr0 = row_begin + (g < ncoarse ? g * P.G : ncoarse * P.G + (g - ncoarse) * gfine);
+		const uint32_t lrE = min(lr0 + (g < ncoarse ? P.G : gfine), row_end);
 		const bool gz = group_has_oniso(P, anyz, lr0, lane);
 		if (lane < P.G) {
 			const uint32_t lr = lr0 + lane, zl = fastdiv(lr, P.NY, P.mNY);
@@ -718,7 +722,8 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 						y = yz.x; z = yz.y;
 						const bool ownp = row_points_owned(P, z);
 						cellok = row_cells_owned(P, z, y) && x < P.nx;
-						if (!gz) {
+						// groups near an on-iso sample: only the words it touches take the generic rules
+						if (!(gz && word_oniso(P, z, y, x >> 5))) {
 							uint32_t id[12];
 							unsigned own;
 							const uint32_t g0 = z == P.hz ? vbn : vb;
@@ -731,21 +736,8 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 								if (own & 2u) put_vertex_task(P, id[0] - g0, lr, x, 1u, false);
 								if (own & 4u) put_vertex_task(P, id[3] - g0, lr, x, 2u, false);
 							}
-						} else if (ownp) {
-							put_vertex_tasks_generic(P, x, y, z);
-						}
-						if (gz && cellok) {
-							WordRec rec; CellWords cw; CellPairs cp;
-							word_masks_generic(P, z, y, x >> 5, rec, cw);
-							// (with on-iso samples a point can own a vertex while its cell is inactive)
-							if ((rec.act >> b) & 1u) {
-								cell_pairs(P, z, y, x >> 5, true, rec, cw, cp);
-#pragma unroll
-								for (int k = 0; k < 8; k++) { scr[k * 32 + lane] = cp.mask[k]; scr[256 + k * 32 + lane] = cp.base[k]; }
-								const unsigned idx = cell_index(cw.c, 1, (int)b);
-								zm = cw.zany ? cell_zmask(cw.zc, 1, (int)b) : 0u;
-								pat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
-							}
+						} else {
+							pat = cell_slow<Sample>(P, tb, x, y, z, ownp, cellok, scr + lane, 32, zm);
 						}
 					}
 					// triangle / centre offsets: shuffle scan in sweep order
@@ -767,11 +759,12 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							P.totals->overflow = 1;
 						}
 					}
-					if (!gz) {
+					{
 						// Triangles of this round, one lane per TRIANGLE: each owner lane marks its
 						// slots in the round's triangle range, then lane t fetches the owner's pattern
 						// by shuffle and its three vertex ids from the owner's column of the scratch;
-						// consecutive lanes write consecutive triangles.
+						// consecutive lanes write consecutive triangles.  (Cells with an on-iso corner
+						// write their own triangles afterwards: bit 31 of the pattern word.)
 						uint8_t *own = reinterpret_cast<uint8_t *>(scr + 13 * 32);
 						const uint32_t e0 = ex & 0xFFFFu, ntot = tot & 0xFFFFu;
 						if (on) {
@@ -779,7 +772,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							for (uint32_t j = 0; j < pat.ntri; j++) own[e0 + j] = (uint8_t)lane;
 						}
 						__syncwarp();
-						const uint32_t sm = pat.start | (pat.m << 12);
+						const uint32_t sm = pat.start | (pat.m << 12) | (zm ? 0x80000000u : 0u);
 						for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
 							const uint32_t t = t0 + lane;
 							const bool act = t < ntot;
@@ -787,16 +780,11 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							const uint32_t csm = __shfl_sync(0xFFFFFFFFu, sm, c), ce0 = __shfl_sync(0xFFFFFFFFu, e0, c);
 							uint64_t ccell = 0;
 							if (P.tcell) ccell = __shfl_sync(0xFFFFFFFFu, cell, c);
-							if (act) emit_triangle_fast(P, tb.tri[(csm & 0xFFFu) + (t - ce0)], csm >> 12, scr + c, 32, tbase + runT + t, ccell);
+							if (act && !(csm >> 31))
+								emit_triangle_fast(P, tb.tri[(csm & 0xFFFu) + (t - ce0)], (csm >> 12) & 1u, scr + c, 32, tbase + runT + t, ccell);
 						}
 						__syncwarp();
-					} else if (on) {
-						if (zm) {
-							emit_cell_triangles_z(P, tb, b, pat, zm, vb + cl, scr + lane, scr + 256 + lane, 32, tid, 0u, 0xFFFFFFFFu, cell);
-						} else {
-							for (uint32_t j = 0; j < pat.ntri; j++)
-								emit_triangle_task(P, tb.tri[pat.start + j], b, pat.m, vb + cl, scr + lane, scr + 256 + lane, 32, tid + j, cell);
-						}
+						if (zm) cell_slow_triangles<Sample>(P, tb, x, y, z, pat, zm, vb + cl, tid, cell);
 					}
 					runT += tot & 0xFFFFu; runC += tot >> 16;
 				}
@@ -847,6 +835,7 @@ struct mc33cu_ctx {
 	uint64_t launches;
 	// resident CTAs per SM of the two emit kernels (persistent grids)
 	uint32_t emc_per_sm, emv_per_sm;
+	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
 	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
 };
 
@@ -935,6 +924,10 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	c->d = *d;
 	c->device = device;
 	c->emc_per_sm = EMC_MINB; c->emv_per_sm = EMV_MINB;
+	c->P.dbg_noz = getenv("MC33_B200_DEBUG_NOZ") ? 1u : 0u;
+	c->fine_pct = 8; c->fine_rows = 4;
+	if (const char *e = getenv("MC33_B200_FINE_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) c->fine_pct = (uint32_t)v; }
+	if (const char *e = getenv("MC33_B200_FINE_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->fine_rows = (uint32_t)v; }
 	if (const char *e = getenv("MC33_B200_EMC_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emc_per_sm = (uint32_t)v; }
 	if (const char *e = getenv("MC33_B200_EMV_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emv_per_sm = (uint32_t)v; }
 	int rc = upload_tables();
@@ -1250,10 +1243,16 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		// (the grid's last slice on the last slab)
 		const uint32_t zend = P.pz1 > P.cz1 ? P.pz1 : P.cz1;
 		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (zend - P.zlo) * P.NY;
-		const uint32_t ngroups = (re - rb + P.G - 1) / P.G;
+		// work units: whole groups of G rows first, the last rows (about one group per resident
+		// warp's worth ... c->fine_pct per cent) in units of gfine rows
+		const uint32_t nrows = re - rb;
+		const uint32_t gfine = P.G >= 4 ? (c->fine_rows < P.G ? c->fine_rows : P.G) : P.G;
+		uint32_t ncoarse = (uint32_t)((uint64_t)nrows * (100u - c->fine_pct) / 100u) / P.G;
+		if (gfine == P.G) ncoarse = nrows / P.G;
+		const uint32_t ngroups = ncoarse + (nrows - ncoarse * P.G + gfine - 1) / gfine;
 		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups);
+		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[4], s));

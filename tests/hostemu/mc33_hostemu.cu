@@ -46,10 +46,10 @@ static void run(Params &P, bool emit)
 		if (anyz) P.totals->anyZ = 1;
 	}
 	const bool gz = P.totals->anyZ != 0;
-	// per-word record of row (z,y): through the quad fast path when the grid has no
-	// on-iso sample (as the kernels do), else the generic bitmap walk
+	// per-word record of row (z,y): through the quad fast path when the word has no
+	// on-iso sample among the points it depends on (as the kernels do), else the generic walk
 	auto word_rec = [&](uint32_t z, uint32_t y, uint32_t w, WordRec &rec, CellWords &cw) {
-		if (gz) { word_masks(P, z, y, w, true, rec, cw); return; }
+		if (gz && word_oniso(P, z, y, w)) { word_masks(P, z, y, w, true, rec, cw); return; }
 		const uint32_t lr = (z - P.zlo) * P.NY + y, q = w >> 2;
 		const bool hasY = y < P.ny, hasZ = z < P.nz;
 		const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u, i00 = (uint64_t)lr * P.WP + 4 * q;
@@ -78,7 +78,7 @@ static void run(Params &P, bool emit)
 					// visit mask for the cell kernel: active cells, points owning a vertex emitted here
 					P.A[(uint64_t)lr * P.WP + w] = rec.act | (row_points_owned(P, z) ? (rec.X | rec.Y | rec.Z) : 0u);
 					cv = pack_planes(rec);
-					if (gz) {
+					if (gz && word_oniso(P, z, y, w)) {
 						cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
 					} else {
 						// the kernel's merged walk over the quad: give it this word's cells only
@@ -118,39 +118,32 @@ static void run(Params &P, bool emit)
 		if (!own_c && !own_p) continue;
 		uint32_t tid = P.rowBT[lr], cl = P.totals->nShared + P.rowBC[lr];
 		for (uint32_t w = 0; w < P.W; w++) {
-			WordRec rec; CellWords cw; CellPairs cp;
-			word_rec(z, y, w, rec, cw);
 			// visited: active cells and grid points that own a vertex (the mask k_count left)
 			uint32_t act = P.A[(uint64_t)lr * P.WP + w];
 			if (!act) continue;
-			bool pairs = false;
+			const bool slow = gz && word_oniso(P, z, y, w);
 			while (act) {
 				int b = ffs32(act);
 				act &= act - 1;
 				const uint32_t x = (w << 5) + b;
 				const bool cellok = own_c && x < P.nx;
 				uint32_t ids[13];
-				unsigned idx = 0, zm = 0;
-				if (gz) {
-					if (own_p) put_vertex_tasks_generic(P, x, y, z);
-					// (with on-iso samples a point can own a vertex while its cell is inactive)
-					if (!cellok || !((rec.act >> b) & 1u)) continue;
-					// the drain side: generic path with on-iso samples
-					if (!pairs) { word_masks(P, z, y, w, gz, rec, cw); cell_pairs(P, z, y, w, gz, rec, cw, cp); pairs = true; }
-					idx = cell_index(cw.c, 1, b);
-					zm = cw.zany ? cell_zmask(cw.zc, 1, b) : 0u;
+				unsigned zm = 0;
+				CellPattern cpat;
+				cpat.start = 0; cpat.m = 0; cpat.ntri = 0; cpat.centre = 0;
+				if (slow) {
+					cpat = cell_slow<Sample>(P, tb, x, y, z, own_p, cellok, ids, 1, zm);
 				} else {
 					unsigned own;
 					const uint32_t g0 = z == P.hz ? vbn : vb;
-					idx = cell_fast(P, x, y, z, g0, z + 1 == P.hz ? vbn : vb, ids, own);
+					const unsigned idx = cell_fast(P, x, y, z, g0, z + 1 == P.hz ? vbn : vb, ids, own);
 					if (own_p) {
 						if (own & 1u) put_vertex_task(P, ids[8] - g0, lr, x, 0u, false);
 						if (own & 2u) put_vertex_task(P, ids[0] - g0, lr, x, 1u, false);
 						if (own & 4u) put_vertex_task(P, ids[3] - g0, lr, x, 2u, false);
 					}
-					if (!cellok) continue;
+					if (cellok) cpat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
 				}
-				const CellPattern cpat = cell_pattern<Sample>(P, tb, x, y, z, idx, zm);
 				const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
 				if (cpat.centre) {
 					if (cl < P.capV) {
@@ -160,18 +153,14 @@ static void run(Params &P, bool emit)
 						P.totals->overflow = 1;
 					}
 				}
-				if (!gz) {
+				if (!zm) {
 					ids[12] = vb + cl;
 					for (uint32_t j = 0; j < cpat.ntri; j++)
 						emit_triangle_fast(P, tb.tri[cpat.start + j], cpat.m, ids, 1, tid + j, cell);
-					tid += cpat.ntri;
-				} else if (zm) {
-					tid += emit_cell_triangles_z(P, tb, (unsigned)b, cpat, zm, vb + cl, cp.mask, cp.base, 1, tid, 0u, 0xFFFFFFFFu, cell);
 				} else {
-					for (uint32_t j = 0; j < cpat.ntri; j++)
-						emit_triangle_task(P, tb.tri[cpat.start + j], (unsigned)b, cpat.m, vb + cl, cp.mask, cp.base, 1, tid + j, cell);
-					tid += cpat.ntri;
+					cell_slow_triangles<Sample>(P, tb, x, y, z, cpat, zm, vb + cl, tid, cell);
 				}
+				tid += cpat.ntri;
 				cl += cpat.centre;
 			}
 		}

@@ -21,7 +21,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 tag = sys.argv[3] if len(sys.argv) > 3 else ""
 dev = torch.device("cuda", 0)
 grid = bench.gyroid_device(n, 0, n, n, dev)
-isos = bench.ISOS
+isos = [float(v) for v in os.environ["MC33_TP_ISOS"].split(",")] if os.environ.get("MC33_TP_ISOS") else bench.ISOS
 ex = Extractor(cabi.make_desc(cabi.F32, n - 1, n - 1, n - 1), 0)
 ex.bind(grid)
 s = torch.cuda.Stream()
@@ -43,12 +43,15 @@ with torch.cuda.stream(s):
     ms = e0.elapsed_time(e1) / (reps * len(isos))
     ex.timing(True)
     kt = [0.0] * 5
+    per_iso = []
     for i in isos:
         ex.extract_async(i, buf)
         torch.cuda.synchronize()
-        kt = [a + b / len(isos) for a, b in zip(kt, ex.kernel_times())]
+        one = ex.kernel_times()
+        per_iso.append([round(x, 4) for x in one])
+        kt = [a + b / len(isos) for a, b in zip(kt, one)]
     ex.timing(False)
 env = {k: v for k, v in os.environ.items() if k.startswith("MC33_B200_")}
 print(json.dumps({"tag": tag, "env": env, "n": n, "ms_per_iso": round(ms, 4),
                   "serial_kernel_ms": dict(zip(["classify", "count", "rowscan", "emit_cells", "emit_vertices"], [round(x, 4) for x in kt])),
-                  "nV": [int(c.nV) for c in ks], "nT": [int(c.nT) for c in ks]}))
+                  "per_iso_kernel_ms": per_iso, "nV": [int(c.nV) for c in ks], "nT": [int(c.nT) for c in ks]}))
