@@ -248,9 +248,7 @@ def run_ours(args):
             else:
                 ex.count_async(iso, counts_dev)
                 dist.all_gather_into_tensor(gathered, counts_dev)
-                cs = torch.cumsum(gathered[:, 0], 0, dtype=torch.int32)
-                bases_dev[1] = cs[rank]
-                bases_dev[0] = cs[rank] - gathered[rank, 0]
+                ex.slab_bases(gathered, rank, world, bases_dev)
                 ex.emit(buf, dev_bases=bases_dev)
 
     def barrier():

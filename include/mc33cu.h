@@ -126,6 +126,12 @@ int  mc33cu_count(mc33cu_ctx *ctx, double iso, mc33cu_counts *counts);
  * left in the caller's DEVICE buffer dev_counts4 (4 x uint32), ready for an
  * all-gather across slabs; follow with mc33cu_emit_device */
 int  mc33cu_count_async(mc33cu_ctx *ctx, double iso, uint32_t *dev_counts4);
+/* z-slabs: after the all-gather of every slab's dev_counts4 into the DEVICE
+ * array dev_counts_all [world][4], leave {vbase, vbase_next} of slab `rank` in the DEVICE
+ * buffer dev_bases2 (the exclusive sum of the vertex counts; asynchronous, context stream):
+ * the global running nV of the reference (marching_cubes_33.c:487) across slabs.  Pass
+ * dev_bases2 as mc33cu_out.dev_bases. */
+int  mc33cu_slab_bases(mc33cu_ctx *ctx, const uint32_t *dev_counts_all, int rank, int world, uint32_t *dev_bases2);
 /* emit the mesh of the last mc33cu_count into device buffers (asynchronous on the
  * context's stream; mc33cu_sync reports a capacity overflow). */
 int  mc33cu_emit_device(mc33cu_ctx *ctx, const mc33cu_out *out);

@@ -890,10 +890,15 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 
 static int set_geom(mc33cu_ctx *c, const mc33cu_desc *d);
 
+// (the attribute belongs to the function, not to a context: contexts of different row
+// lengths coexist, so it is set to the largest ring any plan can ask for)
+#define CLS_MAX_SMEM ((16384 + 512 + 32 + 127) / 128 * 128 * CLS_STAGES)
+
 template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 {
-	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES)));
-	CU(cudaFuncSetAttribute(k_classify_vec<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl.stage_bytes * CLS_STAGES)));
+	if ((size_t)pl.stage_bytes * CLS_STAGES > CLS_MAX_SMEM) return fail(MC33CU_ERR_ARG, "classify plan exceeds the shared memory ring");
+	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
+	CU(cudaFuncSetAttribute(k_classify_vec<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	CU(cudaFuncSetAttribute(k_emit_cells<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
 	return MC33CU_OK;
 }
@@ -1388,6 +1393,24 @@ extern "C" int mc33cu_count_async(mc33cu_ctx *c, double iso, uint32_t *dev_count
 		CU(cudaGetLastError());
 	}
 	c->counted = true;
+	return MC33CU_OK;
+}
+
+__global__ void k_slab_bases(const uint32_t *all4, int rank, uint32_t *bases2)
+{
+	uint32_t v = 0;
+	for (int r = 0; r < rank; r++) v += all4[4 * r];
+	bases2[0] = v; bases2[1] = v + all4[4 * rank];
+}
+
+extern "C" int mc33cu_slab_bases(mc33cu_ctx *c, const uint32_t *dev_counts_all, int rank, int world, uint32_t *dev_bases2)
+{
+	if (!c || !dev_counts_all || !dev_bases2) return fail(MC33CU_ERR_ARG, "null argument");
+	if (world < 1 || rank < 0 || rank >= world) return fail(MC33CU_ERR_ARG, "bad rank / world");
+	CU(cudaSetDevice(c->device));
+	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, rank, dev_bases2);
+	c->launches++;
+	CU(cudaGetLastError());
 	return MC33CU_OK;
 }
 

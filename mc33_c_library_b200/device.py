@@ -59,6 +59,12 @@ class Extractor:
         tensor dev_counts4 (no host synchronisation)."""
         cabi.check(self.lib.mc33cu_count_async(self.h, float(iso), C.c_void_p(dev_counts4.data_ptr())))
 
+    def slab_bases(self, counts_all, rank, world, bases2):
+        """{vbase, vbase_next} of this slab from the all-gathered counts (CUDA int32 tensors
+        [world, 4] and [2]); one small kernel on the context stream, no host round trip."""
+        cabi.check(self.lib.mc33cu_slab_bases(self.h, C.c_void_p(counts_all.data_ptr()), int(rank), int(world),
+                                              C.c_void_p(bases2.data_ptr())))
+
     def alloc(self, capV, capT, keys=False):
         dev = torch.device("cuda", self.device)
         b = dict(V=torch.empty((max(capV, 1), 3), dtype=self.real, device=dev),

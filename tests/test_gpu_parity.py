@@ -127,11 +127,15 @@ def test_cfg5_like_inclined_noise():
     _same(oracle_extract(a, 0.0, "f32", g), gpu_extract(a, 0.0, "f32", g))
 
 
+@pytest.mark.parametrize("device_bases", [False, True])
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("variant,iso,scale,shape", [("f32", 0.0, 0, (37, 20, 128)), ("u8", 2.0, 4, (23, 9, 40))])
-def test_zslabs_on_gpu_match_single_extraction(world, variant, iso, scale, shape):
+def test_zslabs_on_gpu_match_single_extraction(world, variant, iso, scale, shape, device_bases):
     """BASELINE config 4's decomposition in small: every z-slab through its own context
-    (halo slices, ids of the seam slice in the next slab's space), merged == oracle"""
+    (halo slices, ids of the seam slice in the next slab's space), merged == oracle.
+    device_bases: the multi-GPU flow of bench.py -- counts stay on the device
+    (mc33cu_count_async), are 'all-gathered' (here: stacked), and mc33cu_slab_bases turns
+    them into the global vertex bases without a host round trip."""
     import torch
     from mc33_c_library_b200 import slabs
     from mc33_c_library_b200.device import Extractor
@@ -146,10 +150,23 @@ def test_zslabs_on_gpu_match_single_extraction(world, variant, iso, scale, shape
         exs.append(ex)
         counts.append(ex.count(iso))
     bases = slabs.bases([(int(k.nV), int(k.nT)) for k in counts])
+    gathered = None
+    if device_bases:
+        dev = torch.device("cuda", 0)
+        per = [torch.zeros(4, dtype=torch.int32, device=dev) for _ in exs]
+        for ex, c4 in zip(exs, per):
+            ex.count_async(iso, c4)
+        torch.cuda.synchronize()
+        gathered = torch.stack(per).contiguous()
     meshes = []
-    for ex, k, (vb, vbn) in zip(exs, counts, bases):
+    for r, (ex, k, (vb, vbn)) in enumerate(zip(exs, counts, bases)):
         b = ex.alloc(int(k.nV), int(k.nT), keys=True)
-        ex.emit(b, vbase=vb, vbase_next=vbn)
+        if device_bases:
+            b2 = torch.zeros(2, dtype=torch.int32, device=gathered.device)
+            ex.slab_bases(gathered, r, len(exs), b2)
+            ex.emit(b, dev_bases=b2)
+        else:
+            ex.emit(b, vbase=vb, vbase_next=vbn)
         ex.sync()
         nV, nT = int(k.nV), int(k.nT)
         meshes.append(Mesh(b["V"][:nV].cpu().numpy(), b["N"][:nV].cpu().numpy(), b["T"][:nT].cpu().numpy().view(np.uint32),
