@@ -662,11 +662,21 @@ MC_HD uint64_t pack_planes(const WordRec &rec)
 
 // walk the active cells of word w of cell row (z,y): c[k] / zc[k] = corner sign /
 // on-iso words (zc only read when zany)
+MC_HD uint32_t count_simple_cells(const uint32_t *c, uint32_t act, uint32_t &cx);
+
 template <typename Sample>
 MC_HDN uint64_t count_cells(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t w, uint32_t act,
                             const uint32_t *c, const uint32_t *zc, uint32_t zany)
 {
-	uint32_t nt = 0, nc = 0;
+	uint32_t nc = 0;
+	// cells without an on-iso corner follow the index alone: the simple ones are counted 32 at a
+	// time, and only complex cells and cells with an on-iso corner are walked (this is the word
+	// that makes one lane of the count kernel late, so it should be short)
+	uint32_t zcells = 0;
+	if (zany) zcells = (zc[0] | zc[1] | zc[2] | zc[3] | zc[4] | zc[5] | zc[6] | zc[7]) & act;
+	uint32_t cx = 0;
+	uint32_t nt = count_simple_cells(c, act & ~zcells, cx);
+	act = cx | zcells;
 	while (act) {
 		int b = ffs32(act);
 		act &= act - 1;
@@ -687,12 +697,16 @@ MC_HDN uint64_t count_cells(const Params &P, const Tables &tb, uint32_t z, uint3
 // the active cells of the four words of a quad in ONE loop (a separate loop per
 // word would make a warp pay the longest word four times); no on-iso samples.
 // Each iteration takes the lowest active cell of the lowest non-empty word.
+// (only the COMPLEX cells come here -- the simple ones are counted 32 at a time -- so it is
+// out of line and loads the four sign quads again instead of taking them by reference, which
+// kept them in local memory in the caller's hot path)
 template <typename Sample>
-MC_HDN uint64_t count_cells_quad(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t q, const uint32_t *act,
-                                 const Quad &q00, const Quad &q10, const Quad &q01, const Quad &q11)
+MC_COLD uint64_t count_cells_quad(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t q,
+                                  uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint64_t i00, uint64_t dY, uint64_t dZ)
 {
 	uint32_t nt = 0, nc = 0;
-	uint32_t a0 = act[0], a1 = act[1], a2 = act[2], a3 = act[3];
+	const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
+	const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
 	while (a0 | a1 | a2 | a3) {
 		const int k = a0 ? 0 : (a1 ? 1 : (a2 ? 2 : 3));
 		const uint32_t m = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
@@ -1201,6 +1215,28 @@ MC_COLD uint32_t emit_cell_triangles_z(const Params &P, const Tables &tb, unsign
 		if (!(tw >> 12)) break;
 	}
 	return n;
+}
+
+// the words of a quad that hold an on-iso sample (bit k of slow), generic rules; one call per
+// quad so that the count kernel's hot loop stays free of calls
+struct QuadSlow { uint64_t pv[4]; uint64_t cc; uint32_t vis[4]; };
+
+template <typename Sample>
+MC_COLD QuadSlow count_quad_slow(const Params &P, const Tables &tb, uint32_t z, uint32_t y, uint32_t q, uint32_t slow,
+                                 bool own_points, bool own_cells)
+{
+	QuadSlow r;
+	r.cc = 0;
+	for (int k = 0; k < 4; k++) {
+		r.pv[k] = 0; r.vis[k] = 0;
+		const uint32_t w = 4 * q + (uint32_t)k;
+		if (((slow >> k) & 1u) && w < P.W) {
+			uint64_t cc;
+			count_word<Sample>(P, tb, z, y, w, true, own_points, own_cells, r.pv[k], cc, r.vis[k]);
+			r.cc += cc;
+		}
+	}
+	return r;
 }
 
 // ---------------------------------------------------------------------------

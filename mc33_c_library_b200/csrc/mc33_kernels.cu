@@ -417,7 +417,7 @@ __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32
 #define CNT_MINB 4     // resident CTAs per SM k_count is compiled for
 #endif
 template <typename Sample>
-__global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t *blkSum)
+__global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t GW, uint32_t *blkSum)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
@@ -425,10 +425,11 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const bool anyz = P.totals->anyZ != 0;
-	const uint32_t GW = 32 / P.G;                    // groups per warp and block iteration: 32 rows per warp
-	const uint32_t RB = CNT_WARPS * GW * P.G;
+	const uint32_t RB = CNT_WARPS * GW * P.G;       // rows per block: GW groups of G rows per warp
 	const uint32_t npass = (P.Q + 31) / 32;
 
+	// (one block per CTA when the grid allows: the hardware hands CTAs out as slots free up, which
+	// measured better than persistent CTAs pulling blocks by ticket, and than smaller blocks)
 	for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
 		s_row[0][threadIdx.x] = 0; s_row[1][threadIdx.x] = 0; s_row[2][threadIdx.x] = 0;
 		__syncthreads();
@@ -473,18 +474,20 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 							// simple cells are counted 32 at a time; only the complex ones are walked
 							if (rec.act) nts += count_simple_cells(c, rec.act, act[k]);
 						} else {
-							// (temporaries: the call takes references, and pv / vis must stay in registers)
-							uint64_t cc = 0, pvk = 0;
-							uint32_t visk = 0;
-							if (4 * q + k < P.W) count_word<Sample>(P, tb, z, y, 4 * q + k, true, own_p, own_c, pvk, cc, visk);
-							pv[k] = pvk; vis[k] = visk;
-							tt += cc;
+							pv[k] = 0; vis[k] = 0;
 						}
+					}
+					if (slow) {
+						const QuadSlow r = count_quad_slow<Sample>(P, tb, z, y, q, slow, own_p, own_c);
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							if ((slow >> k) & 1u) { pv[k] = r.pv[k]; vis[k] = r.vis[k]; }
+						tt += r.cc;
 					}
 					pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
 					*reinterpret_cast<uint4 *>(P.A + i00) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
 					tt += nts;
-					if (act[0] | act[1] | act[2] | act[3]) tt += count_cells_quad<Sample>(P, tb, z, y, q, act, q00, q10, q01, q11);
+					if (act[0] | act[1] | act[2] | act[3]) tt += count_cells_quad<Sample>(P, tb, z, y, q, act[0], act[1], act[2], act[3], i00, dY, dZ);
 				}
 			}
 			// lane-local exclusive prefix over the four words, then the warp scan
@@ -824,7 +827,7 @@ struct mc33cu_ctx {
 	void *up_registered;     // ... page-locked by us (cudaHostRegister) from its second upload on
 	void *pinned; size_t pinned_bytes;   // staging for row-wise uploads
 	// k_count blocks (CNT_WARPS * G rows each) and their (V, T, C) sums
-	uint32_t *blk_sum; uint32_t nblk;
+	uint32_t *blk_sum; uint32_t nblk, cnt_gw, cnt_rb;
 	// host mirror of totals
 	Totals *h_totals;
 	bool counted;
@@ -960,7 +963,13 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	c->sample_size = ssz[d->dtype];
 	c->real_size = d->dtype == MC33CU_F64 ? 8 : 4;
 	c->n_samples = (uint64_t)P.Lrows * P.NX;
-	c->nblk = (P.Lrows + CNT_WARPS * (32 / P.G) * P.G - 1) / (CNT_WARPS * (32 / P.G) * P.G);
+	{
+		uint32_t rpw = 32;                               // rows per warp and k_count block
+		if (const char *e = getenv("MC33_B200_CNT_RPW")) { int v = atoi(e); if (v >= 1 && v <= 32) rpw = (uint32_t)v; }
+		c->cnt_gw = rpw / P.G ? rpw / P.G : 1;
+		c->cnt_rb = CNT_WARPS * c->cnt_gw * P.G;
+		c->nblk = (P.Lrows + c->cnt_rb - 1) / c->cnt_rb;
+	}
 	{
 		// classify chunks: ~16 KB of whole rows (a multiple of the CTA's warp count
 		// when possible), or 16 KB pieces of one long row (a multiple of 4 words)
@@ -1225,13 +1234,13 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
 	{
 		uint32_t grid = (uint32_t)c->n_sm * 8;
 		if (grid > c->nblk) grid = c->nblk;
-		k_count<Sample><<<grid, 256, TBL_BYTES, s>>>(P, c->nblk, c->blk_sum);
+		k_count<Sample><<<grid, 256, TBL_BYTES, s>>>(P, c->nblk, c->cnt_gw, c->blk_sum);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[2], s));
 	{
 		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
-		k_rowscan<<<(c->nblk + RS_BLOCKS - 1) / RS_BLOCKS, 256, 0, s>>>(P, c->nblk, CNT_WARPS * (32 / P.G) * P.G, c->blk_sum, owned_end);
+		k_rowscan<<<(c->nblk + RS_BLOCKS - 1) / RS_BLOCKS, 256, 0, s>>>(P, c->nblk, c->cnt_rb, c->blk_sum, owned_end);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[3], s));

@@ -89,8 +89,7 @@ static void run(Params &P, bool emit)
 						act4[w & 3] = cxm;
 						const bool hasY = y < P.ny, hasZ = z < P.nz;
 						const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u, i00 = (uint64_t)lr * P.WP + (w & ~3u);
-						cc = count_cells_quad<Sample>(P, tb, z, y, w >> 2, act4, load_quad(P.S, i00), load_quad(P.S, i00 + dY),
-						                              load_quad(P.S, i00 + dZ), load_quad(P.S, i00 + dY + dZ));
+						cc = count_cells_quad<Sample>(P, tb, z, y, w >> 2, act4[0], act4[1], act4[2], act4[3], i00, dY, dZ);
 						cc += nts;
 					}
 				}
