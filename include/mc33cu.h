@@ -138,6 +138,16 @@ int  mc33cu_emit_device(mc33cu_ctx *ctx, const mc33cu_out *out);
 /* classify + count + scan + emit back to back without any host synchronisation;
  * counts (optional) are read after mc33cu_sync via mc33cu_get_counts. */
 int  mc33cu_extract_device(mc33cu_ctx *ctx, double iso, const mc33cu_out *out);
+/* Iso sweep over one grid (BASELINE config 2): the reference calls calculate_isosurface once
+ * per isovalue and re-reads every sample each time (marching_cubes_33.c:1832-1859).  Here the
+ * samples are streamed ONCE for up to 8 isovalues: mc33cu_classify_sweep leaves one set of
+ * sign / on-iso bitmaps per isovalue; mc33cu_count_set_async and mc33cu_extract_set_device are
+ * mc33cu_count_async / mc33cu_extract_device for pre-classified set `set` (0 .. n-1), in any
+ * order, until the next classify call on the context.  Results are identical to n separate
+ * extractions. */
+int  mc33cu_classify_sweep(mc33cu_ctx *ctx, const double *isos, int n);
+int  mc33cu_count_set_async(mc33cu_ctx *ctx, int set, uint32_t *dev_counts4);
+int  mc33cu_extract_set_device(mc33cu_ctx *ctx, int set, const mc33cu_out *out);
 int  mc33cu_sync(mc33cu_ctx *ctx);
 int  mc33cu_get_counts(mc33cu_ctx *ctx, mc33cu_counts *counts);
 /* emit the mesh of the last mc33cu_count into HOST arrays of at least

@@ -162,6 +162,8 @@ struct Params {
 	uint32_t *S, *Z;              // bitmaps [Lrows][WP]; words >= W of a row are zero
 	uint32_t *A;                  // [Lrows][WP] visit bitmap left by the count kernel for the cell kernel: active
 	                              // cells of the row, and grid points that own a vertex this slab emits
+	uint32_t *anyZp;              // one word: set by the classify kernel when some sample is exactly on the isovalue
+	                              // (totals->anyZ, or the slot of a pre-classified sweep set)
 	uint32_t *rowZ;               // [Lrows] hint: == zepoch when the row has an on-iso sample in this extraction
 	uint32_t zepoch;
 	uint64_t *wpreV;              // [Lrows][WP] X | Y<<21 | Z<<42: row-local index of each plane's first vertex

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
 					zacc |= e;
 					if (lane == 0) { Sr[g] = b; Zr[g] = e; }
 				}
-				if (lane == 0 && zacc) { P.rowZ[lr] = P.zepoch; P.totals->anyZ = 1u; }
+				if (lane == 0 && zacc) { P.rowZ[lr] = P.zepoch; *P.anyZp = 1u; }
 			}
 		}
 		__syncthreads();                                     // every warp is done with stage s
@@ -338,12 +338,149 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify_vec(const __grid_const
 					for (int d = LW / 2; d; d >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, d);
 					if (lane % LW == 0) Zb[o + j * NS + lane / LW] = v;
 				}
-				if (lane == 0) { P.rowZ[o / WP] = P.zepoch; P.totals->anyZ = 1u; }
+				if (lane == 0) { P.rowZ[o / WP] = P.zepoch; *P.anyZp = 1u; }
 			} else if (lane < NW) {
 				Zb[o + lane] = 0u;
 			}
 			o += NW;
 			if (++gq == gpr) { gq = 0; o += WP - gpr * NW; }
+		}
+		__syncthreads();                                     // every warp is done with stage s
+		if (k + CLS_STAGES < nmine) issue(blockIdx.x + (k + CLS_STAGES) * gridDim.x, s);
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K1, iso sweep: the samples are streamed ONCE for up to eight isovalues (same TMA ring as
+// k_classify_vec; float grids with rows of whole 128-sample groups).  A lane loads samples
+// lane, lane+32, lane+64, lane+96 of a group and packs its 4 x 8 comparison results into one
+// word (bit 4j+i: sample 32i+lane above isovalue j); a 32 x 32 bit-matrix transpose across
+// the warp (five shuffle stages) then leaves in lane 4j+i exactly bitmap word i of the group
+// for isovalue j, stored to set j.  Equality (on-iso) is accumulated in one predicate; only a
+// group that has a hit builds the Z words the same way.  Isovalues beyond n are +inf.
+// ---------------------------------------------------------------------------
+#define SWEEP_MAX 8
+struct SweepSets {
+	float iso[SWEEP_MAX];
+	uint32_t *S, *Z, *rowZ, *any;     // set j at S + j * set_words, rowZ + j * Lrows, any + j
+	uint64_t set_words;
+};
+
+// 32 x 32 bit-matrix transpose across the warp: out[l] bit s = in[s] bit l.  Five butterfly
+// stages; a stage is one shuffle, one rotate and one bit-select (the rotate amount and the
+// select mask depend on the lane only and are passed in).
+struct TransposeLane { uint32_t sh[5], m[5]; };
+__device__ __forceinline__ TransposeLane transpose_lane(unsigned lane)
+{
+	TransposeLane t;
+#pragma unroll
+	for (int i = 0; i < 5; i++) {
+		const int k = 16 >> i;
+		const uint32_t M = k == 16 ? 0xFFFF0000u : k == 8 ? 0xFF00FF00u : k == 4 ? 0xF0F0F0F0u : k == 2 ? 0xCCCCCCCCu : 0xAAAAAAAAu;
+		t.sh[i] = (lane & k) ? 32u - k : (uint32_t)k;     // rotate left by k, or right by k
+		t.m[i] = (lane & k) ? ~M : M;                     // bit positions taken from the partner
+	}
+	return t;
+}
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t w, const TransposeLane &t)
+{
+#pragma unroll
+	for (int i = 0; i < 5; i++) {
+		const uint32_t x = __shfl_xor_sync(0xFFFFFFFFu, w, 16 >> i);
+		const uint32_t r = __funnelshift_l(x, x, t.sh[i]);
+		w = (w & ~t.m[i]) | (r & t.m[i]);
+	}
+	return w;
+}
+// all ones if a == b, for building bit fields without predicates
+__device__ __forceinline__ uint32_t feq_mask(float a, float b)
+{
+	uint32_t d;
+	asm("set.eq.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b));
+	return d;
+}
+
+#ifndef SWEEP_THREADS
+#define SWEEP_THREADS 512    // more warps than the single-isovalue kernel: the transpose is a chain of shuffles
+#endif
+__global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __grid_constant__ Params P, const __grid_constant__ SweepSets ss,
+                                                                uint32_t rows, uint32_t nchunks, uint32_t stage_bytes)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ uint64_t full[CLS_STAGES];
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const char *gbase = (const char *)P.data;
+	const uint32_t rowb = P.NX * 4u, chunkb = rows * rowb;
+	const uint32_t gpr = P.W / 4;                       // 128-sample groups per row
+	const uint32_t ipw = (rows * gpr + SWEEP_THREADS / 32 - 1) / (SWEEP_THREADS / 32);
+	const uint32_t i0 = wid * ipw, r0 = i0 / gpr, g0 = i0 - r0 * gpr;
+	const uint32_t WP = P.WP, Lrows = P.Lrows;
+	const uint64_t lane_off = (uint64_t)(lane >> 2) * ss.set_words + (lane & 3u);     // set j = lane / 4, word i = lane % 4
+	uint32_t *const Sl = ss.S + lane_off, *const Zl = ss.Z + lane_off;
+	float iso[SWEEP_MAX];
+#pragma unroll
+	for (int j = 0; j < SWEEP_MAX; j++) iso[j] = ss.iso[j];
+	const TransposeLane tl = transpose_lane(lane);
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < CLS_STAGES; s++) mbar_init(&full[s], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+	auto issue = [&](uint32_t c, int s) {
+		if (threadIdx.x == 0) {
+			const uint32_t lr0 = c * rows;
+			const uint32_t bytes = (lr0 + rows <= Lrows ? rows : Lrows - lr0) * rowb;
+			mbar_arrive_expect_tx(&full[s], bytes);
+			bulk_g2s(smem + (size_t)s * stage_bytes, gbase + (uint64_t)c * chunkb, bytes, &full[s]);
+		}
+	};
+	const uint32_t nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	for (uint32_t k = 0; k < CLS_STAGES && k < nmine; k++) issue(blockIdx.x + k * gridDim.x, (int)k);
+
+	for (uint32_t k = 0; k < nmine; k++) {
+		const int s = (int)(k % CLS_STAGES);
+		const uint32_t lr0 = (blockIdx.x + k * gridDim.x) * rows;
+		const uint32_t nit = (lr0 + rows <= Lrows ? rows : Lrows - lr0) * gpr;
+		mbar_wait(&full[s], (k / CLS_STAGES) & 1);
+		const float *src = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes) + (size_t)i0 * 128 + lane;
+		uint32_t gq = g0, o = (lr0 + r0) * WP + g0 * 4;
+		const uint32_t i1 = min(i0 + ipw, nit);
+		for (uint32_t it = i0; it < i1; it++, src += 128) {
+			const float f0 = src[0], f1 = src[32], f2 = src[64], f3 = src[96];
+			// bit 4j+i = IEEE sign bit of iso_j - f_i, exactly the reference's index bit
+			// (marching_cubes_33.c:392-409, :1856-1859; no flush-to-zero, so the difference is
+			// zero only for equal operands): one subtraction and one funnel shift per bit,
+			// highest bit first
+			uint32_t w = 0;
+			bool eq = false;
+#pragma unroll
+			for (int j = SWEEP_MAX - 1; j >= 0; j--) {
+				const float d3 = __fsub_rn(iso[j], f3), d2 = __fsub_rn(iso[j], f2), d1 = __fsub_rn(iso[j], f1), d0 = __fsub_rn(iso[j], f0);
+				w = __funnelshift_l(__float_as_uint(d3), w, 1);
+				w = __funnelshift_l(__float_as_uint(d2), w, 1);
+				w = __funnelshift_l(__float_as_uint(d1), w, 1);
+				w = __funnelshift_l(__float_as_uint(d0), w, 1);
+				eq = eq || d0 == 0.0f || d1 == 0.0f || d2 == 0.0f || d3 == 0.0f;
+			}
+			Sl[o] = warp_transpose32(w, tl);
+			if (__any_sync(0xFFFFFFFFu, eq)) {
+				uint32_t e = 0;
+#pragma unroll
+				for (int j = 0; j < SWEEP_MAX; j++) {
+					e |= feq_mask(f0, iso[j]) & (1u << (4 * j));
+					e |= feq_mask(f1, iso[j]) & (2u << (4 * j));
+					e |= feq_mask(f2, iso[j]) & (4u << (4 * j));
+					e |= feq_mask(f3, iso[j]) & (8u << (4 * j));
+				}
+				e = warp_transpose32(e, tl);
+				Zl[o] = e;
+				if (e) { ss.rowZ[(uint64_t)(lane >> 2) * Lrows + o / WP] = P.zepoch; ss.any[lane >> 2] = 1u; }
+			} else {
+				Zl[o] = 0u;
+			}
+			o += 4;
+			if (++gq == gpr) { gq = 0; o += WP - gpr * 4; }
 		}
 		__syncthreads();                                     // every warp is done with stage s
 		if (k + CLS_STAGES < nmine) issue(blockIdx.x + (k + CLS_STAGES) * gridDim.x, s);
@@ -424,7 +561,7 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 	__shared__ uint64_t s_w[2][8];
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const bool anyz = P.totals->anyZ != 0;
+	const bool anyz = *P.anyZp != 0;
 	const uint32_t RB = CNT_WARPS * GW * P.G;       // rows per block: GW groups of G rows per warp
 	const uint32_t npass = (P.Q + 31) / 32;
 
@@ -643,7 +780,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + wid * CQ;
 	uint32_t *scr = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * CQ + wid * EM_SCR;
 	uint2 *rowt = reinterpret_cast<uint2 *>((uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (CQ + EM_SCR) + wid * EM_ROWT);
-	const bool anyz = P.totals->anyZ != 0;
+	const bool anyz = *P.anyZp != 0;
 	const uint32_t nShared = P.totals->nShared;
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
 	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
@@ -840,6 +977,12 @@ struct mc33cu_ctx {
 	uint32_t emc_per_sm, emv_per_sm;
 	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
 	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
+	// bitmaps of the single-isovalue path (P.S / P.Z / P.rowZ point here or into a sweep set)
+	uint32_t *S0, *Z0, *rowZ0;
+	uint32_t epoch;                        // on-iso hint epoch, bumped by every classify launch
+	// iso sweep: up to SWEEP_MAX pre-classified bitmap sets (allocated by the first sweep)
+	uint32_t *swS, *swZ, *swRowZ, *swAny;
+	double sw_iso[SWEEP_MAX]; int sw_n; uint32_t sw_epoch;
 };
 
 extern "C" const char *mc33cu_last_error(void) { return g_err; }
@@ -877,7 +1020,8 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	Params &P = c->P;
-	cudaFree(P.S); cudaFree(P.Z); cudaFree(P.A); cudaFree(P.rowZ); cudaFree(P.wpreV);
+	cudaFree(c->S0); cudaFree(c->Z0); cudaFree(P.A); cudaFree(c->rowZ0); cudaFree(P.wpreV);
+	cudaFree(c->swS); cudaFree(c->swZ); cudaFree(c->swRowZ); cudaFree(c->swAny);
 	cudaFree(P.rowBV); cudaFree(P.totals);
 	cudaFree(c->blk_sum);
 	cudaFree(c->vtask);
@@ -903,6 +1047,7 @@ template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	CU(cudaFuncSetAttribute(k_classify_vec<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	CU(cudaFuncSetAttribute(k_emit_cells<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
+	CU(cudaFuncSetAttribute(k_classify_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	return MC33CU_OK;
 }
 
@@ -1009,7 +1154,7 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	TRYCU(cudaMemsetAsync(P.A, 0, bm * 4, c->stream));
 	TRY(dalloc(&P.rowZ, (size_t)P.Lrows));
 	TRYCU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows * 4, c->stream));
-	P.zepoch = 0;
+	P.zepoch = 0; c->epoch = 0;
 	TRY(dalloc(&P.wpreV, (size_t)P.Lrows * P.WP));
 	TRYCU(cudaMemsetAsync(P.wpreV, 0, (size_t)P.Lrows * P.WP * 8, c->stream));
 	TRY(dalloc(&P.rowBV, ((size_t)P.Lrows + 1) * 3));
@@ -1022,6 +1167,8 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	TRYCU(cudaStreamSynchronize(c->stream));
 #undef TRY
 #undef TRYCU
+	c->S0 = P.S; c->Z0 = P.Z; c->rowZ0 = P.rowZ;
+	P.anyZp = &P.totals->anyZ;
 	*out = c;
 	return MC33CU_OK;
 }
@@ -1221,15 +1368,37 @@ template <typename Sample> static int launch_classify(mc33cu_ctx *c)
 	return MC33CU_OK;
 }
 
-template <typename Sample> static int launch_count_phase(mc33cu_ctx *c)
+// a new epoch invalidates the per-row on-iso hints of every bitmap set
+static int next_epoch(mc33cu_ctx *c, uint32_t *e)
+{
+	if (++c->epoch == 0) {
+		CU(cudaMemsetAsync(c->rowZ0, 0, (size_t)c->P.Lrows * 4, c->stream));
+		if (c->swRowZ) CU(cudaMemsetAsync(c->swRowZ, 0, (size_t)c->P.Lrows * 4 * SWEEP_MAX, c->stream));
+		c->epoch = 1;
+	}
+	*e = c->epoch;
+	return MC33CU_OK;
+}
+
+// set < 0: classify the single-isovalue bitmaps now; set >= 0: use pre-classified sweep set
+template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 {
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
-	// re-arm the totals (overflow / on-iso flags); a new epoch invalidates the per-row on-iso hints
+	// re-arm the totals (overflow / on-iso flags)
 	CU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), s));
-	if (++P.zepoch == 0) { CU(cudaMemsetAsync(P.rowZ, 0, (size_t)P.Lrows * 4, s)); P.zepoch = 1; }
 	if (c->timing) CU(cudaEventRecord(c->ev[0], s));
-	launch_classify<Sample>(c);
+	if (set < 0) {
+		P.S = c->S0; P.Z = c->Z0; P.rowZ = c->rowZ0; P.anyZp = &P.totals->anyZ;
+		int rc = next_epoch(c, &P.zepoch);
+		if (rc) return rc;
+		launch_classify<Sample>(c);
+	} else {
+		const size_t bm = (size_t)P.Lrows * P.WP;
+		P.S = c->swS + (size_t)set * bm; P.Z = c->swZ + (size_t)set * bm; P.rowZ = c->swRowZ + (size_t)set * P.Lrows;
+		P.anyZp = c->swAny + set;
+		P.zepoch = c->sw_epoch;
+	}
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
 	{
 		uint32_t grid = (uint32_t)c->n_sm * 8;
@@ -1280,14 +1449,14 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 	return MC33CU_OK;
 }
 
-static int dispatch_count(mc33cu_ctx *c)
+static int dispatch_count(mc33cu_ctx *c, int set = -1)
 {
 	switch (c->d.dtype) {
-	case MC33CU_F32: return launch_count_phase<float>(c);
-	case MC33CU_F64: return launch_count_phase<double>(c);
-	case MC33CU_U8:  return launch_count_phase<uint8_t>(c);
-	case MC33CU_U16: return launch_count_phase<uint16_t>(c);
-	default:         return launch_count_phase<uint32_t>(c);
+	case MC33CU_F32: return launch_count_phase<float>(c, set);
+	case MC33CU_F64: return launch_count_phase<double>(c, set);
+	case MC33CU_U8:  return launch_count_phase<uint8_t>(c, set);
+	case MC33CU_U16: return launch_count_phase<uint16_t>(c, set);
+	default:         return launch_count_phase<uint32_t>(c, set);
 	}
 }
 static int dispatch_emit(mc33cu_ctx *c)
@@ -1442,6 +1611,118 @@ extern "C" int mc33cu_extract_device(mc33cu_ctx *c, double iso, const mc33cu_out
 	int rc = set_out(c, o);
 	if (rc) return rc;
 	rc = dispatch_count(c);
+	if (rc) return rc;
+	rc = dispatch_emit(c);
+	if (rc) return rc;
+	c->counted = true;
+	return MC33CU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// iso sweep: classify once for up to SWEEP_MAX isovalues, then count / emit per set
+// ---------------------------------------------------------------------------
+template <typename Sample> static int classify_one_into_set(mc33cu_ctx *c, int j)
+{
+	// general shapes / element types: the single-isovalue kernel, once per set
+	Params &P = c->P;
+	const size_t bm = (size_t)P.Lrows * P.WP;
+	P.S = c->swS + (size_t)j * bm; P.Z = c->swZ + (size_t)j * bm; P.rowZ = c->swRowZ + (size_t)j * P.Lrows;
+	P.anyZp = c->swAny + j;
+	P.zepoch = c->sw_epoch;
+	return launch_classify<Sample>(c);
+}
+
+extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
+{
+	if (!c || !isos) return fail(MC33CU_ERR_ARG, "null argument");
+	if (n < 1 || n > SWEEP_MAX) return fail(MC33CU_ERR_ARG, "a sweep holds 1..8 isovalues");
+	if (!c->P.data) return fail(MC33CU_ERR_STATE, "no grid bound");
+	CU(cudaSetDevice(c->device));
+	Params &P = c->P;
+	cudaStream_t s = c->stream;
+	const size_t bm = (size_t)P.Lrows * P.WP;
+	if (!c->swS) {
+		// (first sweep on this context: not on the steady-state path)
+		CU(cudaStreamSynchronize(s));
+		CU(cudaMalloc((void **)&c->swS, bm * 4 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swZ, bm * 4 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swRowZ, (size_t)P.Lrows * 4 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swAny, 4 * SWEEP_MAX));
+		CU(cudaMemsetAsync(c->swS, 0, bm * 4 * SWEEP_MAX, s));
+		CU(cudaMemsetAsync(c->swZ, 0, bm * 4 * SWEEP_MAX, s));
+		CU(cudaMemsetAsync(c->swRowZ, 0, (size_t)P.Lrows * 4 * SWEEP_MAX, s));
+	}
+	CU(cudaMemsetAsync(c->swAny, 0, 4 * SWEEP_MAX, s));
+	int rc = next_epoch(c, &c->sw_epoch);
+	if (rc) return rc;
+	c->sw_n = n;
+	for (int j = 0; j < n; j++) c->sw_iso[j] = isos[j];
+	c->ev_valid = false;
+	const ClsPlan &pl = c->cls;
+	if (c->d.dtype == MC33CU_F32 && pl.nwchunk == 1 && P.NX % 128 == 0 && ((uintptr_t)P.data & 15) == 0) {
+		SweepSets ss;
+		for (int j = 0; j < SWEEP_MAX; j++) ss.iso[j] = j < n ? (float)isos[j] + 0.0f : __builtin_inff();
+		ss.S = c->swS; ss.Z = c->swZ; ss.rowZ = c->swRowZ; ss.any = c->swAny; ss.set_words = bm;
+		P.zepoch = c->sw_epoch;
+		const size_t smem = (size_t)pl.stage_bytes * CLS_STAGES;
+		uint32_t per_sm = (uint32_t)((220u << 10) / (smem + 1024));
+		if (per_sm < 1) per_sm = 1;
+		if (per_sm > 8) per_sm = 8;
+		uint32_t grid = (uint32_t)c->n_sm * per_sm;
+		if (grid > pl.nchunks) grid = pl.nchunks;
+		k_classify_sweep<<<grid, SWEEP_THREADS, smem, s>>>(P, ss, pl.rows, pl.nchunks, pl.stage_bytes);
+		c->launches++;
+	} else {
+		for (int j = 0; j < n; j++) {
+			set_iso(c, isos[j]);
+			switch (c->d.dtype) {
+			case MC33CU_F32: classify_one_into_set<float>(c, j); break;
+			case MC33CU_F64: classify_one_into_set<double>(c, j); break;
+			case MC33CU_U8:  classify_one_into_set<uint8_t>(c, j); break;
+			case MC33CU_U16: classify_one_into_set<uint16_t>(c, j); break;
+			default:         classify_one_into_set<uint32_t>(c, j); break;
+			}
+		}
+	}
+	CU(cudaGetLastError());
+	return MC33CU_OK;
+}
+
+static int check_set(mc33cu_ctx *c, int set)
+{
+	if (!c) return fail(MC33CU_ERR_ARG, "null context");
+	if (set < 0 || set >= c->sw_n) return fail(MC33CU_ERR_STATE, "no such pre-classified set: call mc33cu_classify_sweep first");
+	return MC33CU_OK;
+}
+
+extern "C" int mc33cu_count_set_async(mc33cu_ctx *c, int set, uint32_t *dev_counts4)
+{
+	int rc = check_set(c, set);
+	if (rc) return rc;
+	CU(cudaSetDevice(c->device));
+	set_iso(c, c->sw_iso[set]);
+	c->ev_valid = false;
+	rc = dispatch_count(c, set);
+	if (rc) return rc;
+	if (dev_counts4) {
+		k_export_counts<<<1, 1, 0, c->stream>>>(c->P.totals, dev_counts4);
+		c->launches++;
+		CU(cudaGetLastError());
+	}
+	c->counted = true;
+	return MC33CU_OK;
+}
+
+extern "C" int mc33cu_extract_set_device(mc33cu_ctx *c, int set, const mc33cu_out *o)
+{
+	int rc = check_set(c, set);
+	if (rc) return rc;
+	if (!o) return fail(MC33CU_ERR_ARG, "null argument");
+	CU(cudaSetDevice(c->device));
+	set_iso(c, c->sw_iso[set]);
+	rc = set_out(c, o);
+	if (rc) return rc;
+	rc = dispatch_count(c, set);
 	if (rc) return rc;
 	rc = dispatch_emit(c);
 	if (rc) return rc;

@@ -95,6 +95,18 @@ class Extractor:
         o = self._out(b, **kw)
         cabi.check(self.lib.mc33cu_extract_device(self.h, float(iso), C.byref(o)))
 
+    # -- iso sweep: classify once for up to 8 isovalues, then count / emit per set ----------
+    def classify_sweep(self, isos):
+        arr = (C.c_double * len(isos))(*[float(v) for v in isos])
+        cabi.check(self.lib.mc33cu_classify_sweep(self.h, arr, len(isos)))
+
+    def count_set_async(self, j, dev_counts4):
+        cabi.check(self.lib.mc33cu_count_set_async(self.h, int(j), C.c_void_p(dev_counts4.data_ptr())))
+
+    def extract_set_async(self, j, b, **kw):
+        o = self._out(b, **kw)
+        cabi.check(self.lib.mc33cu_extract_set_device(self.h, int(j), C.byref(o)))
+
     def sync(self):
         cabi.check(self.lib.mc33cu_sync(self.h))
         k = cabi.Counts()

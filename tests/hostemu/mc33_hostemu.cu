@@ -43,9 +43,9 @@ static void run(Params &P, bool emit)
 			anyz |= z != 0;
 		}
 		P.rowZ[lr] = anyz ? P.zepoch : 0u;
-		if (anyz) P.totals->anyZ = 1;
+		if (anyz) *P.anyZp = 1;
 	}
-	const bool gz = P.totals->anyZ != 0;
+	const bool gz = *P.anyZp != 0;
 	// per-word record of row (z,y): through the quad fast path when the word has no
 	// on-iso sample among the points it depends on (as the kernels do), else the generic walk
 	auto word_rec = [&](uint32_t z, uint32_t y, uint32_t w, WordRec &rec, CellWords &cw) {
@@ -200,6 +200,7 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.S = S.data(); P.Z = Z.data(); P.rowZ = rz.data(); P.wpreV = wv.data();
 	P.rowBV = rb.data(); P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
 	P.totals = &tot;
+	P.anyZp = &tot.anyZ;
 	bool emit = o != nullptr;
 	std::vector<uint64_t> vtask(emit ? (size_t)o->capV + 1 : 1);
 	P.vtask = vtask.data();

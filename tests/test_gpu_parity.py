@@ -391,3 +391,48 @@ def test_dropin_empty_surface_and_null_safety():
     L.free_surface_memory(None); L.free_MC33(None); L.free_memory_grd(None)
     assert not L.create_MC33(None)
     assert not L.grid_from_data_pointer(0, 4, 4, a.ctypes.data)
+
+
+@pytest.mark.parametrize("variant,shape,scale,isos", [
+    # float rows of whole 128-sample groups: the one-pass sweep kernel; integer-valued samples
+    # and integer isovalues put on-iso samples in every set
+    ("f32", (9, 12, 256), 6, [1.0, 2.0, 2.5, 3.0, 4.0, 0.5, 5.0, 3.5]),
+    ("f32", (7, 10, 128), 0, [-0.5, -0.2, 0.0, 0.1, 0.3]),
+    # other shapes / element types: one classify launch per set
+    ("f32", (8, 9, 70), 0, [-0.3, 0.0, 0.2]),
+    ("u8", (8, 9, 128), 6, [2.0, 2.5, 3.0]),
+])
+def test_classify_sweep_matches_single_extractions(variant, shape, scale, isos):
+    """mc33cu_classify_sweep + mc33cu_extract_set_device == one mc33cu_extract_device per isovalue
+    (== the oracle), sets taken in scrambled order, with a normal extraction in between"""
+    import torch
+    from mc33_c_library_b200.device import Extractor
+    code, sdt, real = DTYPES[variant]
+    if variant == "f32" and scale:       # integer-valued floats: many samples exactly on the integer isovalues
+        a = noise_grid(0, "u8", scale=scale, shape=shape).astype(np.float32)
+    else:
+        a = noise_grid(0, variant, scale=scale, shape=shape) if scale else noise_grid(0, variant, shape=shape)
+    ex = Extractor(make_desc(a.shape, variant, None))
+    ex.upload(np.ascontiguousarray(a, dtype=sdt))
+    ex.classify_sweep(isos)
+    order = list(range(len(isos)))[::-1]
+    for n_done, j in enumerate(order):
+        want = oracle_extract(a, isos[j], variant)
+        b = ex.alloc(want.nV + 8, want.nT + 8, keys=True)
+        ex.extract_set_async(j, b)
+        k = ex.sync()
+        nV, nT = int(k.nV), int(k.nT)
+        assert (nV, nT) == (want.nV, want.nT)
+        g = Mesh(b["V"][:nV].cpu().numpy(), b["N"][:nV].cpu().numpy(), b["T"][:nT].cpu().numpy().view(np.uint32),
+                 color=b["color"][:nV].cpu().numpy(), vkey=b["vkey"][:nV].cpu().numpy(), tcell=b["tcell"][:nT].cpu().numpy())
+        _same(want, g)
+    # the single-isovalue path still works on the same context afterwards, and the sets survive it
+    r = ex.extract(isos[0], keys=True)
+    want = oracle_extract(a, isos[0], variant)
+    assert (int(r["counts"].nV), int(r["counts"].nT)) == (want.nV, want.nT)
+    b = ex.alloc(want.nV + 8, want.nT + 8, keys=True)
+    ex.extract_set_async(0, b)
+    k = ex.sync()
+    assert (int(k.nV), int(k.nT)) == (want.nV, want.nT)
+    assert np.array_equal(b["T"][:want.nT].cpu().numpy().view(np.uint32), want.T)
+    ex.close()

@@ -1,0 +1,18 @@
+#!/usr/bin/env python3
+"""Short run for ncu: one mc33cu_classify_sweep of the cfg2 grid."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch
+import bench
+from mc33_c_library_b200 import _cabi as cabi
+from mc33_c_library_b200.device import Extractor
+n = 512
+grid = bench.gyroid_device(n, 0, n, n, torch.device("cuda", 0))
+ex = Extractor(cabi.make_desc(cabi.F32, n - 1, n - 1, n - 1), 0)
+ex.bind(grid)
+for _ in range(2):
+    ex.classify_sweep(bench.ISOS)
+torch.cuda.synchronize()
+print("ok")
