@@ -401,8 +401,12 @@ __device__ __forceinline__ uint32_t feq_mask(float a, float b)
 }
 
 #ifndef SWEEP_THREADS
-#define SWEEP_THREADS 512    // more warps than the single-isovalue kernel: the transpose is a chain of shuffles
+#define SWEEP_THREADS 128    // (A/B: 128 x unroll 2 measured best; 256 / 512 threads and unroll 1 / 4 are within 5 %)
 #endif
+#ifndef SWEEP_UNROLL
+#define SWEEP_UNROLL 2
+#endif
+constexpr int kSweepUnroll = SWEEP_UNROLL;
 __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __grid_constant__ Params P, const __grid_constant__ SweepSets ss,
                                                                 uint32_t rows, uint32_t nchunks, uint32_t stage_bytes)
 {
@@ -446,6 +450,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __gri
 		const float *src = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes) + (size_t)i0 * 128 + lane;
 		uint32_t gq = g0, o = (lr0 + r0) * WP + g0 * 4;
 		const uint32_t i1 = min(i0 + ipw, nit);
+#pragma unroll kSweepUnroll
 		for (uint32_t it = i0; it < i1; it++, src += 128) {
 			const float f0 = src[0], f1 = src[32], f2 = src[64], f3 = src[96];
 			// bit 4j+i = IEEE sign bit of iso_j - f_i, exactly the reference's index bit
