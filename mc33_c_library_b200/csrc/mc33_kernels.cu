@@ -758,6 +758,10 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
 #ifndef EMC_MINB
 #define EMC_MINB 4
 #endif
+#ifndef EMV_UNROLL
+#define EMV_UNROLL 1
+#endif
+constexpr int kEmvUnroll = EMV_UNROLL;
 #define EM_ROWT 64      // per-warp row table words: (y, z) of the group's rows (G <= 32)
 #define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR + EM_ROWT) * 4)
 
@@ -772,6 +776,7 @@ __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_co
 		if (nS > P.capV) P.totals->overflow = 1;
 		P.totals->ticket = 0;                  // re-arm the cell kernel's group counter (it has finished: stream order)
 	}
+#pragma unroll kEmvUnroll
 	for (uint32_t id = blockIdx.x * 256u + threadIdx.x; id < n; id += gridDim.x * 256u) run_vertex_task<Sample>(P, id);
 }
 
