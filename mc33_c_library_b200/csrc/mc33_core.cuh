@@ -162,6 +162,8 @@ struct Params {
 	uint32_t *S, *Z;              // bitmaps [Lrows][WP]; words >= W of a row are zero
 	uint32_t *A;                  // [Lrows][WP] visit bitmap left by the count kernel for the cell kernel: active
 	                              // cells of the row, and grid points that own a vertex this slab emits
+	uint32_t *D;                  // dirty bits of Z (k_classify_sweep: one per 128-sample group, set while the group holds a
+	                              // non-zero Z word, so that clean groups need not be rewritten with zeros)
 	uint32_t *anyZp;              // one word: set by the classify kernel when some sample is exactly on the isovalue
 	                              // (totals->anyZ, or the slot of a pre-classified sweep set)
 	uint32_t *rowZ;               // [Lrows] hint: == zepoch when the row has an on-iso sample in this extraction

@@ -340,6 +340,8 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify_vec(const __grid_const
 				}
 				if (lane == 0) { P.rowZ[o / WP] = P.zepoch; *P.anyZp = 1u; }
 			} else if (lane < NW) {
+				// (every Z word is rewritten on every launch; tracking dirty units as k_classify_sweep
+				// does measured slower here: one isovalue leaves this kernel enough slack for the zeros)
 				Zb[o + lane] = 0u;
 			}
 			o += NW;
@@ -362,8 +364,8 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify_vec(const __grid_const
 #define SWEEP_MAX 8
 struct SweepSets {
 	float iso[SWEEP_MAX];
-	uint32_t *S, *Z, *rowZ, *any;     // set j at S + j * set_words, rowZ + j * Lrows, any + j
-	uint64_t set_words;
+	uint32_t *S, *Z, *rowZ, *any, *D; // set j at S + j * set_words, rowZ + j * Lrows, any + j, D + j * dwords
+	uint64_t set_words, dwords;
 };
 
 // 32 x 32 bit-matrix transpose across the warp: out[l] bit s = in[s] bit l.  Five butterfly
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __gri
 	const uint32_t WP = P.WP, Lrows = P.Lrows;
 	const uint64_t lane_off = (uint64_t)(lane >> 2) * ss.set_words + (lane & 3u);     // set j = lane / 4, word i = lane % 4
 	uint32_t *const Sl = ss.S + lane_off, *const Zl = ss.Z + lane_off;
+	uint32_t *const Dl = ss.D + (uint64_t)(lane >> 2) * ss.dwords;
 	float iso[SWEEP_MAX];
 #pragma unroll
 	for (int j = 0; j < SWEEP_MAX; j++) iso[j] = ss.iso[j];
@@ -446,12 +449,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __gri
 		const int s = (int)(k % CLS_STAGES);
 		const uint32_t lr0 = (blockIdx.x + k * gridDim.x) * rows;
 		const uint32_t nit = (lr0 + rows <= Lrows ? rows : Lrows - lr0) * gpr;
+		// Z is only rewritten where it has to change: a 128-sample group with an on-iso sample is
+		// written and marked dirty, a clean group is zeroed only if it was dirty (writing eight
+		// sets of zeros every time cost a third of the kernel).  A warp's groups of a chunk (at most
+		// 32) span two dirty words, fetched before waiting for the samples; every lane tracks its own set.
+		const uint32_t i1 = min(i0 + ipw, nit);
+		uint32_t gi = lr0 * gpr + i0;
+		const uint32_t dw0 = gi >> 5;
+		uint64_t dd = 0;
+		if (i0 < i1) dd = (uint64_t)Dl[dw0] | ((uint64_t)Dl[dw0 + 1] << 32);
 		mbar_wait(&full[s], (k / CLS_STAGES) & 1);
 		const float *src = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes) + (size_t)i0 * 128 + lane;
 		uint32_t gq = g0, o = (lr0 + r0) * WP + g0 * 4;
-		const uint32_t i1 = min(i0 + ipw, nit);
 #pragma unroll kSweepUnroll
-		for (uint32_t it = i0; it < i1; it++, src += 128) {
+		for (uint32_t it = i0; it < i1; it++, src += 128, gi++) {
+			const bool dirty = (dd >> (gi - (dw0 << 5))) & 1u;
+			const uint32_t dbit = 1u << (gi & 31u);
 			const float f0 = src[0], f1 = src[32], f2 = src[64], f3 = src[96];
 			// bit 4j+i = IEEE sign bit of iso_j - f_i, exactly the reference's index bit
 			// (marching_cubes_33.c:392-409, :1856-1859; no flush-to-zero, so the difference is
@@ -466,7 +479,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __gri
 				w = __funnelshift_l(__float_as_uint(d2), w, 1);
 				w = __funnelshift_l(__float_as_uint(d1), w, 1);
 				w = __funnelshift_l(__float_as_uint(d0), w, 1);
-				eq = eq || d0 == 0.0f || d1 == 0.0f || d2 == 0.0f || d3 == 0.0f;
+				// any exact zero among the four?  One product (on the otherwise idle FMA pipe) and one
+				// test instead of four tests: a zero factor gives 0, or NaN against an infinite one,
+				// and both fail |p| > 0.  An underflowing product only sends the group through the
+				// exact on-iso path below for nothing.
+				eq = eq || !(fabsf(__fmul_rn(__fmul_rn(d0, d1), __fmul_rn(d2, d3))) > 0.0f);
 			}
 			Sl[o] = warp_transpose32(w, tl);
 			if (__any_sync(0xFFFFFFFFu, eq)) {
@@ -479,10 +496,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __gri
 					e |= feq_mask(f3, iso[j]) & (8u << (4 * j));
 				}
 				e = warp_transpose32(e, tl);
-				Zl[o] = e;
-				if (e) { ss.rowZ[(uint64_t)(lane >> 2) * Lrows + o / WP] = P.zepoch; ss.any[lane >> 2] = 1u; }
-			} else {
+				// the four lanes of a set agree on whether the set has a hit in this group
+				const bool hit = ((__ballot_sync(0xFFFFFFFFu, e != 0u) >> (lane & ~3u)) & 0xFu) != 0u;
+				if (hit) {
+					Zl[o] = e;
+					if (e) { ss.rowZ[(uint64_t)(lane >> 2) * Lrows + o / WP] = P.zepoch; ss.any[lane >> 2] = 1u; }
+					if (!dirty && (lane & 3u) == 0) atomicOr(&Dl[gi >> 5], dbit);
+				} else if (dirty) {
+					Zl[o] = 0u;
+					if ((lane & 3u) == 0) atomicAnd(&Dl[gi >> 5], ~dbit);
+				}
+			} else if (dirty) {
 				Zl[o] = 0u;
+				if ((lane & 3u) == 0) atomicAnd(&Dl[gi >> 5], ~dbit);
 			}
 			o += 4;
 			if (++gq == gpr) { gq = 0; o += WP - gpr * 4; }
@@ -988,10 +1014,14 @@ struct mc33cu_ctx {
 	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
 	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
 	// bitmaps of the single-isovalue path (P.S / P.Z / P.rowZ point here or into a sweep set)
-	uint32_t *S0, *Z0, *rowZ0;
+	uint32_t *S0, *Z0, *rowZ0, *D0;
+	size_t dwords;                         // words of one Z dirty-bit array
+	// who wrote a Z array last: 1 k_classify_sweep (dirty bits valid), 2 a single-isovalue kernel (every word
+	// rewritten each time, dirty bits not kept): switching 2 -> 1 clears the array first
+	uint8_t zmode0, zmode_sw[SWEEP_MAX], *zmode_cur;
 	uint32_t epoch;                        // on-iso hint epoch, bumped by every classify launch
 	// iso sweep: up to SWEEP_MAX pre-classified bitmap sets (allocated by the first sweep)
-	uint32_t *swS, *swZ, *swRowZ, *swAny;
+	uint32_t *swS, *swZ, *swRowZ, *swAny, *swD;
 	double sw_iso[SWEEP_MAX]; int sw_n; uint32_t sw_epoch;
 };
 
@@ -1031,7 +1061,7 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	Params &P = c->P;
 	cudaFree(c->S0); cudaFree(c->Z0); cudaFree(P.A); cudaFree(c->rowZ0); cudaFree(P.wpreV);
-	cudaFree(c->swS); cudaFree(c->swZ); cudaFree(c->swRowZ); cudaFree(c->swAny);
+	cudaFree(c->swS); cudaFree(c->swZ); cudaFree(c->swRowZ); cudaFree(c->swAny); cudaFree(c->swD); cudaFree(c->D0);
 	cudaFree(P.rowBV); cudaFree(P.totals);
 	cudaFree(c->blk_sum);
 	cudaFree(c->vtask);
@@ -1179,6 +1209,12 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 #undef TRYCU
 	c->S0 = P.S; c->Z0 = P.Z; c->rowZ0 = P.rowZ;
 	P.anyZp = &P.totals->anyZ;
+	c->dwords = ((size_t)P.Lrows * (P.W / 4 + 1) + 31) / 32 + 2;
+	if (cudaMalloc((void **)&c->D0, c->dwords * 4) != cudaSuccess || cudaMemset(c->D0, 0, c->dwords * 4) != cudaSuccess) {
+		mc33cu_destroy(c);
+		return fail(MC33CU_ERR_NOMEM, "cudaMalloc (Z dirty bits)");
+	}
+	P.D = c->D0; c->zmode_cur = &c->zmode0;
 	*out = c;
 	return MC33CU_OK;
 }
@@ -1371,6 +1407,7 @@ template <typename Sample> static int launch_classify(mc33cu_ctx *c)
 	if (grid > pl.nchunks) grid = pl.nchunks;
 	// vector path: rows of whole NW-word groups, 16-byte aligned samples
 	const uint32_t nwv = sizeof(Sample) >= 4 ? 4u : 16u / (uint32_t)sizeof(Sample);
+	*c->zmode_cur = 2;                             // both kernels rewrite every Z word and keep no dirty bits
 	if (pl.nwchunk == 1 && P.NX % (32 * nwv) == 0 && ((uintptr_t)P.data & 15) == 0)
 		k_classify_vec<Sample><<<grid, CLS_THREADS, smem, s>>>(P, pl.rows, pl.nchunks, pl.stage_bytes);
 	else k_classify<Sample><<<grid, CLS_THREADS, smem, s>>>(P, pl);
@@ -1400,6 +1437,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 	if (c->timing) CU(cudaEventRecord(c->ev[0], s));
 	if (set < 0) {
 		P.S = c->S0; P.Z = c->Z0; P.rowZ = c->rowZ0; P.anyZp = &P.totals->anyZ;
+		P.D = c->D0; c->zmode_cur = &c->zmode0;
 		int rc = next_epoch(c, &P.zepoch);
 		if (rc) return rc;
 		launch_classify<Sample>(c);
@@ -1407,6 +1445,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 		const size_t bm = (size_t)P.Lrows * P.WP;
 		P.S = c->swS + (size_t)set * bm; P.Z = c->swZ + (size_t)set * bm; P.rowZ = c->swRowZ + (size_t)set * P.Lrows;
 		P.anyZp = c->swAny + set;
+		P.D = c->swD + (size_t)set * c->dwords; c->zmode_cur = &c->zmode_sw[set];
 		P.zepoch = c->sw_epoch;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
@@ -1638,6 +1677,7 @@ template <typename Sample> static int classify_one_into_set(mc33cu_ctx *c, int j
 	const size_t bm = (size_t)P.Lrows * P.WP;
 	P.S = c->swS + (size_t)j * bm; P.Z = c->swZ + (size_t)j * bm; P.rowZ = c->swRowZ + (size_t)j * P.Lrows;
 	P.anyZp = c->swAny + j;
+	P.D = c->swD + (size_t)j * c->dwords; c->zmode_cur = &c->zmode_sw[j];
 	P.zepoch = c->sw_epoch;
 	return launch_classify<Sample>(c);
 }
@@ -1658,6 +1698,8 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 		CU(cudaMalloc((void **)&c->swZ, bm * 4 * SWEEP_MAX));
 		CU(cudaMalloc((void **)&c->swRowZ, (size_t)P.Lrows * 4 * SWEEP_MAX));
 		CU(cudaMalloc((void **)&c->swAny, 4 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swD, c->dwords * 4 * SWEEP_MAX));
+		CU(cudaMemsetAsync(c->swD, 0, c->dwords * 4 * SWEEP_MAX, s));
 		CU(cudaMemsetAsync(c->swS, 0, bm * 4 * SWEEP_MAX, s));
 		CU(cudaMemsetAsync(c->swZ, 0, bm * 4 * SWEEP_MAX, s));
 		CU(cudaMemsetAsync(c->swRowZ, 0, (size_t)P.Lrows * 4 * SWEEP_MAX, s));
@@ -1673,6 +1715,14 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 		SweepSets ss;
 		for (int j = 0; j < SWEEP_MAX; j++) ss.iso[j] = j < n ? (float)isos[j] + 0.0f : __builtin_inff();
 		ss.S = c->swS; ss.Z = c->swZ; ss.rowZ = c->swRowZ; ss.any = c->swAny; ss.set_words = bm;
+		ss.D = c->swD; ss.dwords = c->dwords;
+		for (int j = 0; j < SWEEP_MAX; j++) {
+			if (c->zmode_sw[j] == 2) {
+				CU(cudaMemsetAsync(c->swZ + (size_t)j * bm, 0, bm * 4, s));
+				CU(cudaMemsetAsync(c->swD + (size_t)j * c->dwords, 0, c->dwords * 4, s));
+			}
+			c->zmode_sw[j] = 1;
+		}
 		P.zepoch = c->sw_epoch;
 		const size_t smem = (size_t)pl.stage_bytes * CLS_STAGES;
 		uint32_t per_sm = (uint32_t)((220u << 10) / (smem + 1024));

@@ -186,16 +186,35 @@ def test_zslabs_on_gpu_match_single_extraction(world, variant, iso, scale, shape
     assert np.abs(np.where(fa, m.N[om], 0) - np.where(fb, whole.N[ow], 0)).max() <= 1e-6
 
 
-def test_repeated_extractions_reuse_state():
-    """iso sweep on one context: bitmaps, on-iso hints and prefixes of an earlier isovalue must not leak"""
+@pytest.mark.parametrize("variant,shape", [("u8", (20, 21, 128)),      # general classify kernel (every Z word rewritten)
+                                           ("f32", (12, 13, 256)),     # vector kernel: Z units tracked by dirty bits
+                                           ("u8", (6, 7, 512)), ("u16", (6, 9, 256))])
+def test_repeated_extractions_reuse_state(variant, shape):
+    """iso sweep on one context: bitmaps, on-iso hints, Z dirty bits and prefixes of an earlier isovalue
+    must not leak (integer-valued samples: on-iso samples come and go with the isovalue)"""
     from mc33_c_library_b200.device import Extractor
-    a = noise_grid(0, "u8", scale=5, shape=(20, 21, 128))
-    ex = Extractor(make_desc(a.shape, "u8"))
+    code, sdt, real = DTYPES[variant]
+    a = noise_grid(0, "u8", scale=5, shape=shape).astype(sdt)
+    ex = Extractor(make_desc(a.shape, variant))
     ex.upload(a)
-    for iso in (2.0, 2.5, 1.0, 3.5, 2.0, 0.5):
+    for iso in (2.0, 2.5, 1.0, 3.5, 2.0, 0.5, 3.0, 3.0, 1.5):
         r = ex.extract(iso, keys=True)
         g = Mesh(r["V"], r["N"], r["T"], color=r["color"], vkey=r["vkey"], tcell=r["tcell"])
-        _same(oracle_extract(a, iso, "u8"), g)
+        _same(oracle_extract(a, iso, variant), g)
+    # the same context through the sweep sets and back
+    isos = [3.0, 2.0, 2.5]
+    for _ in range(2):
+        ex.classify_sweep(isos)
+        for j, iso in enumerate(isos):
+            want = oracle_extract(a, iso, variant)
+            b = ex.alloc(want.nV + 8, want.nT + 8, keys=True)
+            ex.extract_set_async(j, b)
+            k = ex.sync()
+            assert (int(k.nV), int(k.nT)) == (want.nV, want.nT)
+            assert np.array_equal(b["T"][:want.nT].cpu().numpy().view(np.uint32), want.T)
+        isos = [1.0, 3.5, 0.5]
+    r = ex.extract(2.0, keys=True)
+    _same(oracle_extract(a, 2.0, variant), Mesh(r["V"], r["N"], r["T"], color=r["color"], vkey=r["vkey"], tcell=r["tcell"]))
     ex.close()
 
 
