@@ -288,96 +288,116 @@ MC_HD int interior_test(int i, int flag13, const Real *v)
 	return 0;
 }
 
-// -> pattern start in MC33_TRI; m = the reference's winding flag
+// -> pattern start in MC33_TRI; m = the reference's winding flag.
+//
+// Same decisions as MC33_findCase (marching_cubes_33.c:693-779), arranged for a warp whose
+// lanes hold cells of DIFFERENT base cases: the six face comparisons are made once,
+// branch free; each case then only names the interior tests it needs (at most two), the
+// tests themselves run at two common call sites where all the lanes that need one meet
+// again, and a last per-case step turns the answers into the table offset.  (With a call
+// inside every case branch the lanes ran the tests one after the other: 2 active threads
+// per instruction on white noise.)  The tests are pure functions of the corner values, so
+// running the second one where the reference short-circuits changes nothing.
 template <typename Real>
 MC_COLD unsigned select_pattern(const Tables &tb, unsigned i, const Real *v, unsigned *mflag)
 {
-	unsigned c = tb.case256[i];
-	int k = (int)(c & 0x7FF);
-	unsigned m = (c >> 11) & 1;
-	unsigned idx = m ? i : (i ^ 0xFF);
-	int f[6];
-	int off;
+	const unsigned c = tb.case256[i];
+	const int k = (int)(c & 0x7FF);
+	const unsigned m = (c >> 11) & 1;
+	const unsigned idx = m ? i : (i ^ 0xFF);
+	const int cs = (int)(c >> 12);
 	*mflag = m;
-	switch (c >> 12) {
-	case 0:
-		off = k;
-		break;
+	if (cs == 0) return (unsigned)(k - 127);
+	// face comparisons and MC33_faceTests results as bit masks (bit j: face j)
+	unsigned lt = 0, fneg = 0, fpos = 0;
+	const unsigned ind = cs == 7 ? 165u : idx;
+	int s = 0;
+#pragma unroll
+	for (int j = 0; j < 6; j++) {
+		const unsigned l = face_lt(v, j) ? 1u : 0u;
+		lt |= l << j;
+		const unsigned mm = ind & face_mask(j);
+		int r = 0;
+		if (ind & face_gate(j)) {
+			if (mm == face_set(j)) r = l ? -1 : 1;
+		} else {
+			if (mm == face_clr(j)) r = l ? 1 : -1;
+		}
+		fneg |= (r < 0 ? 1u : 0u) << j;
+		fpos |= (r > 0 ? 1u : 0u) << j;
+		s += r;
+	}
+#define MC_F(j) ((int)((fpos >> (j)) & 1u) - (int)((fneg >> (j)) & 1u))
+#define MC_FT1(f) (((lt >> (f)) & 1u) ? face_clr(f) : face_set(f))
+	int ia = -1, ib = -1, f13 = 0, off = 0, kk = 0;
+	switch (cs) {
 	case 1:
-		off = (idx & face_test1(k >> 2, v)) ? 183 + 2 * k : 159 + k;
+		off = (idx & MC_FT1(k >> 2)) ? 183 + 2 * k : 159 + k;
 		break;
 	case 2:
-		off = interior_test(k, 0, v) ? 239 + 6 * k : 231 + 2 * k;
+		ia = k;
 		break;
 	case 3:
-		if (idx & face_test1(k % 6, v))
-			off = 575 + 5 * k;
-		else
-			off = interior_test(k / 6, 0, v) ? 407 + 7 * k : 335 + 3 * k;
+		if (idx & MC_FT1(k % 6)) off = 575 + 5 * k; else ia = k / 6;
 		break;
 	case 4:
-		switch (face_tests(f, idx, v)) {
-		case -3: off = 695 + 3 * k; break;
-		case -1: off = (f[4] + f[5] < 0 ? (f[0] + f[2] < 0 ? 759 : 799) : 719) + 5 * k; break;
-		case 1:  off = (f[4] + f[5] < 0 ? 983 : (f[0] + f[2] < 0 ? 839 : 911)) + 9 * k; break;
-		default: off = interior_test(k >> 1, 0, v) ? 1095 + 9 * k : 1055 + 5 * k;
-		}
+		if (s == -3) off = 695 + 3 * k;
+		else if (s == -1) off = (MC_F(4) + MC_F(5) < 0 ? (MC_F(0) + MC_F(2) < 0 ? 759 : 799) : 719) + 5 * k;
+		else if (s == 1) off = (MC_F(4) + MC_F(5) < 0 ? 983 : (MC_F(0) + MC_F(2) < 0 ? 839 : 911)) + 9 * k;
+		else ia = k >> 1;
 		break;
 	case 5:
-		switch (face_tests(f, idx, v)) {
-		case -2:
-			if (k == 2 ? interior_test(0, 0, v) != 0
-			           : (interior_test(0, 0, v) != 0 || interior_test(k ? 1 : 3, 0, v) != 0))
-				off = 1213 + 8 * k;
-			else
-				off = 1189 + 4 * k;
-			break;
-		case 0:
-			off = (f[2 + k] < 0 ? 1261 : 1285) + 8 * k;
-			break;
-		default:
-			if (k == 2 ? interior_test(1, 0, v) != 0
-			           : (interior_test(2, 0, v) != 0 || interior_test(k ? 3 : 1, 0, v) != 0))
-				off = 1237 + 8 * k;
-			else
-				off = 1201 + 4 * k;
-		}
+		if (s == -2) { ia = 0; ib = k == 2 ? -1 : (k ? 1 : 3); }
+		else if (s == 0) off = (MC_F(2 + k) < 0 ? 1261 : 1285) + 8 * k;
+		else if (k == 2) ia = 1;
+		else { ia = 2; ib = k ? 3 : 1; }
 		break;
 	case 6:
-		switch (face_tests(f, idx, v)) {
-		case -2:
-			off = interior_test((int)((0xDA010Cu >> (2 * k)) & 3), 0, v) ? 1453 + 8 * k : 1357 + 4 * k;
-			break;
-		case 0:
-			off = (f[k >> 1] < 0 ? 1645 : 1741) + 8 * k;
-			break;
-		default:
-			off = interior_test((int)((0xA7B7E5u >> (2 * k)) & 3), 0, v) ? 1549 + 8 * k : 1405 + 4 * k;
-		}
+		if (s == -2) ia = (int)((0xDA010Cu >> (2 * k)) & 3);
+		else if (s == 0) off = (MC_F(k >> 1) < 0 ? 1645 : 1741) + 8 * k;
+		else ia = (int)((0xA7B7E5u >> (2 * k)) & 3);
 		break;
 	default: {
-		int s = face_tests(f, 165u, v);
-		if (s < 0) s = -s;
-		if (s == 0) {
-			int kk = ((f[1] < 0) << 1) | (f[5] < 0);
-			if (f[0] * f[1] == f[5])
-				off = 2157 + 12 * kk;
-			else {
-				int cc = interior_test(kk, 1, v);
-				off = 2285 + (cc ? 10 * kk - 40 * cc : 6 * kk);
-			}
-		} else if (s == 2) {
-			off = 1917 + 10 * ((f[0] < 0 ? (int)(f[2] > 0) : 12 + (int)(f[2] < 0)) +
-			                   (f[1] < 0 ? (int)(f[3] < 0) : 6 + (int)(f[3] > 0)));
-			if (f[4] > 0) off += 30;
-		} else if (s == 4) {
-			int kk = 21 + 11 * f[0] + 4 * f[1] + 3 * f[2] + 2 * f[3] + f[4];
-			if (kk >> 4) kk -= (kk & 32 ? 20 : 10);
-			off = 1845 + 3 * kk;
+		const int sa = s < 0 ? -s : s;
+		if (sa == 0) {
+			kk = ((MC_F(1) < 0) << 1) | (MC_F(5) < 0);
+			if (MC_F(0) * MC_F(1) == MC_F(5)) off = 2157 + 12 * kk;
+			else { ia = kk; f13 = 1; }
+		} else if (sa == 2) {
+			off = 1917 + 10 * ((MC_F(0) < 0 ? (int)(MC_F(2) > 0) : 12 + (int)(MC_F(2) < 0)) +
+			                   (MC_F(1) < 0 ? (int)(MC_F(3) < 0) : 6 + (int)(MC_F(3) > 0)));
+			if (MC_F(4) > 0) off += 30;
+		} else if (sa == 4) {
+			int q = 21 + 11 * MC_F(0) + 4 * MC_F(1) + 3 * MC_F(2) + 2 * MC_F(3) + MC_F(4);
+			if (q >> 4) q -= (q & 32 ? 20 : 10);
+			off = 1845 + 3 * q;
 		} else {
-			off = 1839 + 2 * f[0];
+			off = 1839 + 2 * MC_F(0);
 		}
 	}
+	}
+#undef MC_F
+#undef MC_FT1
+	// the interior tests, at common call sites
+	int ra = 0, rb = 0;
+	if (ia >= 0) ra = interior_test(ia, f13, v);
+	if (ib >= 0) rb = interior_test(ib, 0, v);
+	if (ia >= 0) {
+		switch (cs) {
+		case 2: off = ra ? 239 + 6 * k : 231 + 2 * k; break;
+		case 3: off = ra ? 407 + 7 * k : 335 + 3 * k; break;
+		case 4: off = ra ? 1095 + 9 * k : 1055 + 5 * k; break;
+		case 5:
+			if (s == -2) off = (ra || rb) ? 1213 + 8 * k : 1189 + 4 * k;
+			else off = (ra || rb) ? 1237 + 8 * k : 1201 + 4 * k;
+			break;
+		case 6:
+			if (s == -2) off = ra ? 1453 + 8 * k : 1357 + 4 * k;
+			else off = ra ? 1549 + 8 * k : 1405 + 4 * k;
+			break;
+		default:
+			off = 2285 + (ra ? 10 * kk - 40 * ra : 6 * kk);
+		}
 	}
 	return (unsigned)(off - 127);
 }
@@ -1219,6 +1239,31 @@ MC_COLD uint32_t emit_cell_triangles_z(const Params &P, const Tables &tb, unsign
 		if (!(tw >> 12)) break;
 	}
 	return n;
+}
+
+// The complex cells of one quad (words without on-iso samples: not bit k of slow), from
+// scratch: the count kernel defers them to the end of its pass, where almost nothing is
+// live, and only remembers that the quad has some.  -> nT | nC << 32
+template <typename Sample>
+MC_COLD uint64_t count_quad_complex(const Params &P, const Tables &tb, uint32_t lr, uint32_t q, uint32_t slow)
+{
+	const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+	const bool hasY = y < P.ny, hasZ = z < P.nz;
+	const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u;
+	const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
+	const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
+	const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
+	const bool cells = row_cells_owned(P, z, y) && hasZ;
+	uint32_t cx[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		if ((slow >> k) & 1u) continue;
+		WordRec rec;
+		uint32_t c[8];
+		quad_word(P, q00, q10, q01, q11, k, 4 * q + k, cells, rec, c);
+		if (rec.act) count_simple_cells(c, rec.act, cx[k]);
+	}
+	return count_cells_quad<Sample>(P, tb, z, y, q, cx[0], cx[1], cx[2], cx[3], i00, dY, dZ);
 }
 
 // the words of a quad that hold an on-iso sample (bit k of slow), generic rules; one call per

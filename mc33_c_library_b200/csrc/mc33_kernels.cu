@@ -582,13 +582,14 @@ __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32
 #define CNT_WARPS 8
 
 #ifndef CNT_MINB
-#define CNT_MINB 4     // resident CTAs per SM k_count is compiled for
+#define CNT_MINB 3     // resident CTAs per SM k_count is compiled for: 80 registers (A/B on the gyroid: 0.061 ms at 2, 0.064 at 3, 0.073 at 4, where the hot loop spills; white noise wants the warps: 5.5 ms at 2, 3.9 at 4)
 #endif
 template <typename Sample>
 __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t GW, uint32_t *blkSum)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
+	__shared__ uint32_t s_cx[2][CNT_WARPS * 32];     // triangles / centres of the complex cells, per row (added late)
 	__shared__ uint64_t s_w[2][8];
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -600,6 +601,7 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 	// measured better than persistent CTAs pulling blocks by ticket, and than smaller blocks)
 	for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
 		s_row[0][threadIdx.x] = 0; s_row[1][threadIdx.x] = 0; s_row[2][threadIdx.x] = 0;
+		s_cx[0][threadIdx.x] = 0; s_cx[1][threadIdx.x] = 0;
 		__syncthreads();
 	  for (uint32_t sub = 0; sub < GW; sub++) {
 		const uint32_t srow = (wid * GW + sub) * P.G;      // first row of the group within the block
@@ -613,6 +615,8 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 			const uint32_t lr = row0 + r;
 			const bool valid = r < P.G && q < P.Q && lr < P.Lrows;
 			uint64_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, tt = 0;
+			bool has_cx = false;
+			uint32_t slow_q = 0;
 			if (valid) {
 				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
 				const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
@@ -655,7 +659,10 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 					pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
 					*reinterpret_cast<uint4 *>(P.A + i00) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
 					tt += nts;
-					if (act[0] | act[1] | act[2] | act[3]) tt += count_cells_quad<Sample>(P, tb, z, y, q, act[0], act[1], act[2], act[3], i00, dY, dZ);
+					// complex cells: walked at the end of the pass (their triangles only enter the row
+					// totals), so that the call does not sit in the middle of everything that is live here
+					has_cx = (act[0] | act[1] | act[2] | act[3]) != 0;
+					slow_q = slow;
 				}
 			}
 			// lane-local exclusive prefix over the four words, then the warp scan
@@ -691,6 +698,11 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 				}
 			}
 			if (P.Q > 32) { carryV += __shfl_sync(0xFFFFFFFFu, iv, 31); carryT += __shfl_sync(0xFFFFFFFFu, it, 31); }
+			if (has_cx) {
+				const uint64_t cc = count_quad_complex<Sample>(P, tb, lr, q, slow_q);
+				atomicAdd(&s_cx[0][srow + r], (uint32_t)cc);
+				atomicAdd(&s_cx[1][srow + r], (uint32_t)(cc >> 32));
+			}
 		}
 		if (P.Q > 32 && row0 < P.Lrows) {
 			// long rows: the plane totals are only known now; add the offsets in a second sweep
@@ -702,7 +714,7 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 		// CTA-relative row bases
 		{
 			const uint32_t t = threadIdx.x;
-			uint64_t a = (uint64_t)s_row[0][t] | ((uint64_t)s_row[2][t] << 32), b = s_row[1][t], ta, tb2;
+			uint64_t a = (uint64_t)s_row[0][t] | ((uint64_t)(s_row[2][t] + s_cx[1][t]) << 32), b = s_row[1][t] + s_cx[0][t], ta, tb2;
 			block_exscan2(a, b, ta, tb2, s_w);
 			const uint32_t lr = blk * RB + t;
 			if (t < RB && lr < P.Lrows) {
