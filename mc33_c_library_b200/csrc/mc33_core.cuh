@@ -1016,13 +1016,13 @@ MC_HD uint32_t local_to_global(const Params &P, uint32_t z, uint32_t local)
 }
 
 // one vertex: plane a of grid point (x,y,z) -> slab-local vertex index id
-template <typename Sample>
+template <typename Sample, bool KEYS = true>
 MC_HDN void emit_vertex_task(const Params &P, uint32_t x, uint32_t y, uint32_t z, int a, bool is_point, uint32_t id)
 {
 	if (id >= P.capV) { P.totals->overflow = 1; return; }
 	if (is_point) emit_point_vertex<Sample>(P, x, y, z, id);
 	else emit_edge_vertex<Sample>(P, x, y, z, a, id);
-	if (P.vkey) P.vkey[id] = (((uint64_t)z * P.NY + y) * P.NX + x) * 4 + (unsigned)a;
+	if (KEYS && P.vkey) P.vkey[id] = (((uint64_t)z * P.NY + y) * P.NX + x) * 4 + (unsigned)a;
 }
 
 // ---------------------------------------------------------------------------
@@ -1038,13 +1038,13 @@ MC_HD void put_vertex_task(const Params &P, uint32_t id, uint32_t lr, uint32_t x
 	if (id < P.capV) P.vtask[id] = (uint64_t)lr | ((uint64_t)(x | (a << 16) | ((uint32_t)is_point << 18)) << 32);
 }
 
-template <typename Sample>
+template <typename Sample, bool KEYS = true>
 MC_HD void run_vertex_task(const Params &P, uint32_t id)
 {
 	const uint64_t t = P.vtask[id];
 	const uint32_t lr = (uint32_t)t, e = (uint32_t)(t >> 32);
 	const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
-	emit_vertex_task<Sample>(P, e & 0xFFFFu, y, z, (int)((e >> 16) & 3u), ((e >> 18) & 1u) != 0, id);
+	emit_vertex_task<Sample, KEYS>(P, e & 0xFFFFu, y, z, (int)((e >> 16) & 3u), ((e >> 18) & 1u) != 0, id);
 }
 
 // tasks of the vertices owned by grid point (x,y,z) on a grid WITH on-iso samples
@@ -1110,6 +1110,9 @@ MC_COLD void cell_pairs(const Params &P, uint32_t z, uint32_t y, uint32_t w, boo
 	cp.mask[7] = r11.X;   cp.base[7] = local_to_global(P, z + 1, plane_base_local(P, l11, w, 0));
 }
 
+// KEYS: the optional per-triangle / per-vertex canonical keys (tests); the kernels are also
+// built without them so that the hot loops carry no code for them
+template <bool KEYS = true>
 MC_HD void write_triangle(const Params &P, uint32_t tid, const uint32_t *ti, unsigned m, uint64_t cell)
 {
 	if (tid >= P.capT) { P.totals->overflow = 1; return; }
@@ -1118,7 +1121,7 @@ MC_HD void write_triangle(const Params &P, uint32_t tid, const uint32_t *ti, uns
 	if (P.geom.normal_neg) { uint32_t t = a0; a0 = a1; a1 = t; }
 	uint32_t *T = P.T + 3 * (uint64_t)tid;
 	T[0] = a0; T[1] = a1; T[2] = ti[2];
-	if (P.tcell) P.tcell[tid] = cell;
+	if (KEYS && P.tcell) P.tcell[tid] = cell;
 }
 
 // ---------------------------------------------------------------------------
@@ -1173,6 +1176,7 @@ MC_HDN unsigned cell_fast(const Params &P, uint32_t x, uint32_t y, uint32_t z, u
 }
 
 // triangle j of a cell whose 13 vertex ids (12 edges + centre) sit at ids[e * stride]
+template <bool KEYS = true>
 MC_HD void emit_triangle_fast(const Params &P, unsigned tw, unsigned m, const uint32_t *ids, uint32_t stride, uint32_t tid,
                               uint64_t cell)
 {
@@ -1180,7 +1184,7 @@ MC_HD void emit_triangle_fast(const Params &P, unsigned tw, unsigned m, const ui
 	ti[0] = ids[((tw >> 8) & 15u) * stride];
 	ti[1] = ids[((tw >> 4) & 15u) * stride];
 	ti[2] = ids[(tw & 15u) * stride];
-	write_triangle(P, tid, ti, m, cell);
+	write_triangle<KEYS>(P, tid, ti, m, cell);
 }
 
 // global id of the vertex a triangle corner refers to: edge code e (0..11) of the

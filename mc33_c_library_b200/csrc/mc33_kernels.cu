@@ -806,7 +806,7 @@ constexpr int kEmvUnroll = EMV_UNROLL;
 // K3, dense: thread id computes vertex id from the task the cell kernel left in the
 // vertex's own slot of N (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
 // threads write consecutive V / N / color.
-template <typename Sample>
+template <typename Sample, bool KEYS>
 __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_constant__ Params P)
 {
 	const uint32_t nS = P.totals->nShared, n = min(nS, P.capV);
@@ -815,10 +815,10 @@ __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_co
 		P.totals->ticket = 0;                  // re-arm the cell kernel's group counter (it has finished: stream order)
 	}
 #pragma unroll kEmvUnroll
-	for (uint32_t id = blockIdx.x * 256u + threadIdx.x; id < n; id += gridDim.x * 256u) run_vertex_task<Sample>(P, id);
+	for (uint32_t id = blockIdx.x * 256u + threadIdx.x; id < n; id += gridDim.x * 256u) run_vertex_task<Sample, KEYS>(P, id);
 }
 
-template <typename Sample>
+template <typename Sample, bool KEYS>
 __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_constant__ Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups,
                                                                 uint32_t ncoarse, uint32_t gfine)
 {
@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 					if (on && pat.centre) {
 						if (cl < P.capV) {
 							emit_centre_vertex<Sample>(P, x, y, z, cl);
-							if (P.vkey) P.vkey[cl] = cell * 4 + 3;
+							if (KEYS && P.vkey) P.vkey[cl] = cell * 4 + 3;
 						} else {
 							P.totals->overflow = 1;
 						}
@@ -967,9 +967,9 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							const int c = act ? (int)own[t] : 0;
 							const uint32_t csm = __shfl_sync(0xFFFFFFFFu, sm, c), ce0 = __shfl_sync(0xFFFFFFFFu, e0, c);
 							uint64_t ccell = 0;
-							if (P.tcell) ccell = __shfl_sync(0xFFFFFFFFu, cell, c);
+							if (KEYS && P.tcell) ccell = __shfl_sync(0xFFFFFFFFu, cell, c);
 							if (act && !(csm >> 31))
-								emit_triangle_fast(P, tb.tri[(csm & 0xFFFu) + (t - ce0)], (csm >> 12) & 1u, scr + c, 32, tbase + runT + t, ccell);
+								emit_triangle_fast<KEYS>(P, tb.tri[(csm & 0xFFFu) + (t - ce0)], (csm >> 12) & 1u, scr + c, 32, tbase + runT + t, ccell);
 						}
 						__syncwarp();
 						if (zm) cell_slow_triangles<Sample>(P, tb, x, y, z, pat, zm, vb + cl, tid, cell);
@@ -1098,7 +1098,8 @@ template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 	if ((size_t)pl.stage_bytes * CLS_STAGES > CLS_MAX_SMEM) return fail(MC33CU_ERR_ARG, "classify plan exceeds the shared memory ring");
 	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	CU(cudaFuncSetAttribute(k_classify_vec<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
-	CU(cudaFuncSetAttribute(k_emit_cells<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
+	CU(cudaFuncSetAttribute(k_emit_cells<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
+	CU(cudaFuncSetAttribute(k_emit_cells<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
 	CU(cudaFuncSetAttribute(k_classify_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	return MC33CU_OK;
 }
@@ -1496,13 +1497,15 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		const uint32_t ngroups = ncoarse + (nrows - ncoarse * P.G + gfine - 1) / gfine;
 		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		k_emit_cells<Sample><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
+		if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
+		else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[4], s));
 	{
 		// dense over the vertex ids (the count is only known on the device: persistent grid)
-		k_emit_vertices<Sample><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
+		if (P.vkey) k_emit_vertices<Sample, true><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
+		else k_emit_vertices<Sample, false><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
 		c->launches++;
 	}
 	if (c->timing) { CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
