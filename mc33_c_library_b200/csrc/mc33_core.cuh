@@ -1204,20 +1204,6 @@ MC_HD uint32_t corner_vertex(const uint32_t *pmask, const uint32_t *pbase, uint3
 	return pbase[combo * stride] + (uint32_t)popc32(off >= 32 ? mk : (mk & ((1u << off) - 1u)));
 }
 
-// one triangle of a cell WITHOUT on-iso corners: table word tw, cell at bit b
-MC_HD void emit_triangle_task(const Params &P, unsigned tw, unsigned b, unsigned m, uint32_t centre_id,
-                              const uint32_t *pmask, const uint32_t *pbase, uint32_t stride, uint32_t tid, uint64_t cell)
-{
-	uint32_t ti[3];
-#pragma unroll
-	for (int j = 0; j < 3; j++) {
-		const unsigned e = (tw >> (8 - 4 * j)) & 15;
-		unsigned key;
-		ti[j] = e == 12 ? centre_id : corner_vertex(pmask, pbase, stride, e, b, 0u, key);
-	}
-	write_triangle(P, tid, ti, m, cell);
-}
-
 // all triangles of a cell WITH on-iso corners (zero-area triangles are dropped);
 // only ids in [lo, hi) are written.  Returns the number of triangles kept.
 MC_COLD uint32_t emit_cell_triangles_z(const Params &P, const Tables &tb, unsigned b, const CellPattern &cp, unsigned zm,

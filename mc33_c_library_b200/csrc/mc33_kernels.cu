@@ -2,12 +2,13 @@
 // B200 Marching Cubes 33 extractor.  See DESIGN.md for the pipeline:
 //
 //   K1 classify   stream the samples ONCE through a TMA (cp.async.bulk) ring in
-//                 shared memory -> S / Z bitmaps (1 bit per sample)
-//   K2 count      per (row, 32-point word): owned vertices per plane, triangles
-//                 and centre vertices of the 32 cells -> row-local word prefixes;
-//                 fused single-pass decoupled look-back scan over the batches
-//                 -> per-row vertex / triangle / centre bases
-//   K4 emit T     active cells compacted per row group, one lane per cell (vertex
+//                 shared memory -> S / Z bitmaps (1 bit per sample); for an iso
+//                 sweep, once for up to eight isovalues (k_classify_sweep)
+//   K2 count      per (row, 32-point word): owned vertices per plane (popcounts),
+//                 triangles (simple cells 32 at a time, complex ones walked) ->
+//                 row-local word prefixes, visit bitmap, CTA-relative row bases
+//   K2b rowscan   CTA-relative -> absolute row bases (vertices, triangles, centres)
+//   K4 emit T     visited cells compacted per row group, one lane per cell (vertex
 //                 ids, pattern, vertex tasks), then one lane per triangle
 //   K3 emit V     dense: one thread per vertex id runs the task K4 left for it
 //

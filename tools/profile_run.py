@@ -21,11 +21,23 @@ dev = torch.device("cuda", 0)
 if kind == "gyroid":
     grid = bench.gyroid_device(n, 0, n, n, dev)
     isos = [0.0, -0.9, 0.6, -1.2][:n_iso]
+elif kind == "ct":
+    # cfg3-like: u16 blobs + texture + noise 0..15, INTEGER isovalue (on-iso samples everywhere near the surface)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    ax = torch.linspace(-1, 1, n, device=dev)
+    v = torch.full((n, n, n), 1000.0, device=dev)
+    for c0, c1, c2, sg in ((0.1, -0.2, 0.05, 0.3), (-0.4, 0.3, -0.1, 0.25), (0.5, 0.5, 0.1, 0.2), (-0.3, -0.5, 0.6, 0.35)):
+        v += 2500.0 / 3 * torch.exp(-((ax[None, None, :] - c0) ** 2 + (ax[None, :, None] - c1) ** 2 + (ax[:, None, None] - c2) ** 2) / (2 * sg * sg))
+    v += 20.0 * torch.sin(37 * ax[None, None, :]) * torch.sin(29 * ax[None, :, None]) * torch.sin(31 * ax[:, None, None])
+    v += torch.randint(0, 16, v.shape, device=dev, generator=g)
+    grid = v.clamp(0, 65535).to(torch.int32).to(torch.uint16)
+    del v
+    isos = [1500.0, 1500.5][:n_iso]
 else:
     from support import noise_grid
     grid = torch.from_numpy(noise_grid(n, "f32")).to(dev)
     isos = [0.0, 0.1][:n_iso]
-ex = Extractor(cabi.make_desc(cabi.F32, n - 1, n - 1, n - 1), 0)
+ex = Extractor(cabi.make_desc(cabi.U16 if kind == "ct" else cabi.F32, n - 1, n - 1, n - 1), 0)
 ex.bind(grid)
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):
