@@ -365,6 +365,10 @@ def run_ours(args):
     if rank == 0:
         out["e2e"] = e2e_dropin(args)
         out["cpu_baseline"] = cpu_baseline()
+        # full-size parity property: vertex / triangle counts of all 8 isosurfaces against the reference's
+        ref_counts = out["cpu_baseline"].pop("counts", None)
+        if ref_counts is not None and world == 1:
+            out["counts_match_reference"] = ref_counts == [[int(k.nV), int(k.nT)] for k in cnt]
         print(json.dumps(out))
     ex.close()
     if world > 1:
@@ -412,7 +416,7 @@ def cpu_baseline():
     t, res = cpu_sweep(lib, grid, ISOS, 1)
     return {"value": len(ISOS) * N_SIDE ** 3 / t * 1e-9, "unit": "Gvoxels/s", "cores": 1, "kind": "reference",
             "sample": f"the full 8-isovalue sweep once on one core ({t:.1f} s), reference built -Ofast -funroll-loops",
-            "mtriangles_per_s": sum(r[1] for r in res) / t * 1e-6}
+            "mtriangles_per_s": sum(r[1] for r in res) / t * 1e-6, "counts": [list(r) for r in res]}
 
 
 def ncu_traffic(kname):
