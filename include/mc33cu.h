@@ -143,8 +143,9 @@ int  mc33cu_extract_device(mc33cu_ctx *ctx, double iso, const mc33cu_out *out);
  * samples are streamed ONCE for up to 8 isovalues: mc33cu_classify_sweep leaves one set of
  * sign / on-iso bitmaps per isovalue; mc33cu_count_set_async and mc33cu_extract_set_device are
  * mc33cu_count_async / mc33cu_extract_device for pre-classified set `set` (0 .. n-1), in any
- * order, until the next classify call on the context.  Results are identical to n separate
- * extractions. */
+ * order, until the next mc33cu_classify_sweep on the context (single-isovalue calls in between
+ * do not disturb the sets).  The samples must not change between the sweep classify and the
+ * last use of its sets.  Results are identical to n separate extractions. */
 int  mc33cu_classify_sweep(mc33cu_ctx *ctx, const double *isos, int n);
 int  mc33cu_count_set_async(mc33cu_ctx *ctx, int set, uint32_t *dev_counts4);
 int  mc33cu_extract_set_device(mc33cu_ctx *ctx, int set, const mc33cu_out *out);

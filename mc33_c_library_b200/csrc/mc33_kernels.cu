@@ -668,30 +668,47 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 			}
 			// lane-local exclusive prefix over the four words, then the warp scan
 			const uint64_t e1 = pv0, e2 = e1 + pv1, e3 = e2 + pv2, tv = e3 + pv3;
-			uint64_t iv = tv, it = tt;
+			uint64_t lv, it, rst = 0, iv = 0;
+			if (P.Q <= 32) {
+				// whole rows in one pass: a warp's 32 quads hold at most 4096 vertices per plane, 4096
+				// centres and 49152 triangles, so the five counters scan as three 32-bit words
+				// (X | Y << 16, Z | C << 16, T) instead of two 64-bit ones
+				const uint32_t a0 = fldV(tv, 0) | (fldV(tv, 1) << 16), b0 = fldV(tv, 2) | ((uint32_t)(tt >> 32) << 16), c0 = (uint32_t)tt;
+				uint32_t ia = a0, ib = b0, ic = c0;
 #pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint64_t xv = __shfl_up_sync(0xFFFFFFFFu, iv, d), xt = __shfl_up_sync(0xFFFFFFFFu, it, d);
-				if (lane >= (unsigned)d) { iv += xv; it += xt; }
-			}
-			const uint64_t xv = iv - tv, xt = it - tt;
-			uint64_t rsv = 0, rst = 0;
-			if (P.Q <= 32) {
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t xa = __shfl_up_sync(0xFFFFFFFFu, ia, d), xb = __shfl_up_sync(0xFFFFFFFFu, ib, d),
+					               xc = __shfl_up_sync(0xFFFFFFFFu, ic, d);
+					if (lane >= (unsigned)d) { ia += xa; ib += xb; ic += xc; }
+				}
+				// exclusive, relative to the first quad of the lane's row
 				const int srcl = (int)min(r * P.Q, 31u);
-				rsv = __shfl_sync(0xFFFFFFFFu, xv, srcl); rst = __shfl_sync(0xFFFFFFFFu, xt, srcl);
-			}
-			uint64_t lv = carryV + xv - rsv;                 // row-local prefix in front of this quad
-			if (P.Q <= 32) {
+				const uint32_t ea = ia - a0, eb = ib - b0, ec = ic - c0;
+				const uint32_t ra = ea - __shfl_sync(0xFFFFFFFFu, ea, srcl), rb = eb - __shfl_sync(0xFFFFFFFFu, eb, srcl);
+				const uint32_t rc0 = __shfl_sync(0xFFFFFFFFu, ec, srcl);
+				lv = (uint64_t)(ra & 0xFFFFu) | ((uint64_t)(ra >> 16) << 21) | ((uint64_t)(rb & 0xFFFFu) << 42);
 				// fold the plane offsets in: Y ids follow the row's X ids, Z ids follow both
 				const int lastl = (int)min(r * P.Q + P.Q - 1, 31u);
 				lv += plane_offsets(__shfl_sync(0xFFFFFFFFu, lv + tv, lastl));
+				// row totals so far (inclusive of this quad): triangles, centres
+				it = (uint64_t)(ic - rc0) | ((uint64_t)((eb >> 16) + (b0 >> 16) - (__shfl_sync(0xFFFFFFFFu, eb, srcl) >> 16)) << 32);
+			} else {
+				uint64_t jt = tt;
+				iv = tv;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint64_t xv = __shfl_up_sync(0xFFFFFFFFu, iv, d), xt = __shfl_up_sync(0xFFFFFFFFu, jt, d);
+					if (lane >= (unsigned)d) { iv += xv; jt += xt; }
+				}
+				lv = carryV + iv - tv;                           // row-local prefix in front of this quad
+				it = jt;
 			}
 			if (valid) {
 				uint64_t *pw = P.wpreV + (uint64_t)lr * P.WP + 4 * q;
 				*reinterpret_cast<ulonglong2 *>(pw) = make_ulonglong2(lv, lv + e1);
 				*reinterpret_cast<ulonglong2 *>(pw + 2) = make_ulonglong2(lv + e2, lv + e3);
 				if (q == P.Q - 1) {
-					const uint64_t rowT = carryT + it - rst;
+					const uint64_t rowT = P.Q <= 32 ? it : carryT + it - rst;
 					pw[4] = lv + tv;
 					s_row[0][srow + r] = P.Q <= 32 ? fldV(lv + tv, 2) : sumV(lv + tv);
 					s_row[1][srow + r] = (uint32_t)rowT;
@@ -1727,7 +1744,10 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 	for (int j = 0; j < n; j++) c->sw_iso[j] = isos[j];
 	c->ev_valid = false;
 	const ClsPlan &pl = c->cls;
-	if (c->d.dtype == MC33CU_F32 && pl.nwchunk == 1 && P.NX % 128 == 0 && ((uintptr_t)P.data & 15) == 0) {
+	// (one-pass kernel: float rows of whole 128-sample groups; a warp's groups of one chunk must fit the
+	// two dirty words it prefetches: a chunk holds at most 33 groups, far below the 32 per warp allowed)
+	const uint32_t sweep_ipw = (pl.rows * (P.W / 4) + SWEEP_THREADS / 32 - 1) / (SWEEP_THREADS / 32);
+	if (c->d.dtype == MC33CU_F32 && pl.nwchunk == 1 && P.NX % 128 == 0 && ((uintptr_t)P.data & 15) == 0 && sweep_ipw <= 32) {
 		SweepSets ss;
 		for (int j = 0; j < SWEEP_MAX; j++) ss.iso[j] = j < n ? (float)isos[j] + 0.0f : __builtin_inff();
 		ss.S = c->swS; ss.Z = c->swZ; ss.rowZ = c->swRowZ; ss.any = c->swAny; ss.set_words = bm;
