@@ -36,6 +36,17 @@ using namespace mc33;
 // one image: case256 | simple256 | tri | pat, copied to shared memory with 16-byte loads
 __device__ __align__(16) unsigned char d_tables[TBL_BYTES];
 
+// the same tables read in place (kernels that only index them on cold paths)
+__device__ __forceinline__ Tables global_tables()
+{
+	Tables tb;
+	tb.case256 = (const uint16_t *)d_tables;
+	tb.simple256 = tb.case256 + 256;
+	tb.tri = tb.simple256 + 256;
+	tb.pat = (const uint8_t *)tb.tri + TBL_TRI_BYTES;
+	return tb;
+}
+
 __device__ __forceinline__ Tables load_tables(unsigned char *smem)
 {
 	const uint4 *src = reinterpret_cast<const uint4 *>(d_tables);
@@ -588,11 +599,11 @@ __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32
 template <typename Sample>
 __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t GW, uint32_t *blkSum)
 {
-	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
 	__shared__ uint32_t s_cx[2][CNT_WARPS * 32];     // triangles / centres of the complex cells, per row (added late)
 	__shared__ uint64_t s_w[2][8];
-	const Tables tb = load_tables(smem);
+	// (the case tables are only touched by the complex-cell walk: read in place, no copy per CTA)
+	const Tables tb = global_tables();
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const bool anyz = *P.anyZp != 0;
 	const uint32_t RB = CNT_WARPS * GW * P.G;       // rows per block: GW groups of G rows per warp
@@ -1483,7 +1494,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 	{
 		uint32_t grid = (uint32_t)c->n_sm * 8;
 		if (grid > c->nblk) grid = c->nblk;
-		k_count<Sample><<<grid, 256, TBL_BYTES, s>>>(P, c->nblk, c->cnt_gw, c->blk_sum);
+		k_count<Sample><<<grid, 256, 0, s>>>(P, c->nblk, c->cnt_gw, c->blk_sum);
 		c->launches++;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[2], s));
