@@ -760,7 +760,9 @@ __global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__
 // and turns the CTA-relative row bases into slab-local ones: the implicit running
 // M->nV++ / nT++ of the reference (marching_cubes_33.c:487, :1245).
 // ---------------------------------------------------------------------------
+#ifndef RS_BLOCKS
 #define RS_BLOCKS 4      // k_count blocks per k_rowscan CTA
+#endif
 
 __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params P, uint32_t nblk, uint32_t RB, const uint32_t *blkSum, uint32_t owned_end_row)
 {
