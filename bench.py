@@ -237,22 +237,26 @@ def run_ours(args):
     capV = max(int(k.nV) for k in cnt) + 1024
     capT = max(int(k.nT) for k in cnt) + 1024
     buf = ex.alloc(capV, capT)
-    counts_dev = torch.zeros(4, dtype=torch.int32, device=dev)
-    gathered = torch.zeros((world, 4), dtype=torch.int32, device=dev)
-    bases_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+    counts_dev = torch.zeros((len(ISOS), 4), dtype=torch.int32, device=dev)
+    gathered = torch.zeros((world, len(ISOS), 4), dtype=torch.int32, device=dev)
+    bases_dev = torch.zeros((len(ISOS), 2), dtype=torch.int32, device=dev)
 
     def sweep():
         # the sweep's isovalues share one pass over the samples (mc33cu_classify_sweep);
         # count / scan / emit then run per isovalue on its pre-classified bitmap set
         ex.classify_sweep(ISOS)
-        for j in range(len(ISOS)):
-            if world == 1:
+        if world == 1:
+            for j in range(len(ISOS)):
                 ex.extract_set_async(j, buf)
-            else:
-                ex.count_set_async(j, counts_dev)
-                dist.all_gather_into_tensor(gathered, counts_dev)
-                ex.slab_bases(gathered, rank, world, bases_dev)
-                ex.emit(buf, dev_bases=bases_dev)
+        else:
+            # every set keeps its own count state: count them all, ONE all-gather of the sweep's
+            # counts across the slabs, then emit them all
+            for j in range(len(ISOS)):
+                ex.count_set_async(j, counts_dev[j])
+            dist.all_gather_into_tensor(gathered, counts_dev)
+            for j in range(len(ISOS)):
+                ex.slab_bases_strided(gathered[0, j], 4 * len(ISOS), rank, world, bases_dev[j])
+                ex.emit_set(j, buf, dev_bases=bases_dev[j])
 
     def barrier():
         if world > 1:

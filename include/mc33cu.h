@@ -132,6 +132,9 @@ int  mc33cu_count_async(mc33cu_ctx *ctx, double iso, uint32_t *dev_counts4);
  * the global running nV of the reference (marching_cubes_33.c:487) across slabs.  Pass
  * dev_bases2 as mc33cu_out.dev_bases. */
 int  mc33cu_slab_bases(mc33cu_ctx *ctx, const uint32_t *dev_counts_all, int rank, int world, uint32_t *dev_bases2);
+/* the same with slab r's counts at dev_counts_all + r * stride_words (e.g. one all-gather of [sets][4] per slab) */
+int  mc33cu_slab_bases_strided(mc33cu_ctx *ctx, const uint32_t *dev_counts_all, uint32_t stride_words, int rank, int world,
+                               uint32_t *dev_bases2);
 /* emit the mesh of the last mc33cu_count into device buffers (asynchronous on the
  * context's stream; mc33cu_sync reports a capacity overflow). */
 int  mc33cu_emit_device(mc33cu_ctx *ctx, const mc33cu_out *out);
@@ -149,6 +152,9 @@ int  mc33cu_extract_device(mc33cu_ctx *ctx, double iso, const mc33cu_out *out);
 int  mc33cu_classify_sweep(mc33cu_ctx *ctx, const double *isos, int n);
 int  mc33cu_count_set_async(mc33cu_ctx *ctx, int set, uint32_t *dev_counts4);
 int  mc33cu_extract_set_device(mc33cu_ctx *ctx, int set, const mc33cu_out *out);
+/* every set keeps its own count state, so all the sets can be counted first (one all-gather of the
+ * counts per sweep across z-slabs) and emitted afterwards: emit pre-classified, counted set `set` */
+int  mc33cu_emit_set_device(mc33cu_ctx *ctx, int set, const mc33cu_out *out);
 int  mc33cu_sync(mc33cu_ctx *ctx);
 int  mc33cu_get_counts(mc33cu_ctx *ctx, mc33cu_counts *counts);
 /* emit the mesh of the last mc33cu_count into HOST arrays of at least

@@ -37,7 +37,7 @@ class Out(C.Structure):
 
 EXPORTS = ["mc33cu_last_error", "mc33cu_device_count", "mc33cu_create", "mc33cu_destroy", "mc33cu_set_stream", "mc33cu_set_geometry",
            "mc33cu_grid_device", "mc33cu_grid_upload", "mc33cu_grid_upload_rows", "mc33cu_count", "mc33cu_count_async",
-           "mc33cu_slab_bases", "mc33cu_emit_device", "mc33cu_extract_device", "mc33cu_classify_sweep", "mc33cu_count_set_async", "mc33cu_extract_set_device", "mc33cu_sync", "mc33cu_get_counts",
+           "mc33cu_slab_bases", "mc33cu_slab_bases_strided", "mc33cu_emit_set_device", "mc33cu_emit_device", "mc33cu_extract_device", "mc33cu_classify_sweep", "mc33cu_count_set_async", "mc33cu_extract_set_device", "mc33cu_sync", "mc33cu_get_counts",
            "mc33cu_emit_host", "mc33cu_host_alloc", "mc33cu_host_free", "mc33cu_enable_timing", "mc33cu_kernel_times", "mc33cu_launch_count"]
 
 _lib = None
@@ -74,6 +74,8 @@ def load():
     lib.mc33cu_count.argtypes = [vp, C.c_double, C.POINTER(Counts)]
     lib.mc33cu_count_async.argtypes = [vp, C.c_double, vp]
     lib.mc33cu_slab_bases.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    lib.mc33cu_slab_bases_strided.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp]
+    lib.mc33cu_emit_set_device.argtypes = [vp, C.c_int, C.POINTER(Out)]
     lib.mc33cu_emit_device.argtypes = [vp, C.POINTER(Out)]
     lib.mc33cu_extract_device.argtypes = [vp, C.c_double, C.POINTER(Out)]
     lib.mc33cu_classify_sweep.argtypes = [vp, C.POINTER(C.c_double), C.c_int]

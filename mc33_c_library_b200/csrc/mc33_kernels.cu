@@ -1063,8 +1063,14 @@ struct mc33cu_ctx {
 	// rewritten each time, dirty bits not kept): switching 2 -> 1 clears the array first
 	uint8_t zmode0, zmode_sw[SWEEP_MAX], *zmode_cur;
 	uint32_t epoch;                        // on-iso hint epoch, bumped by every classify launch
+	uint32_t epoch0;                       // ... of the last single-isovalue classify
+	int counted_set;                       // what the last count phase ran on: -1 single path, else the sweep set
 	// iso sweep: up to SWEEP_MAX pre-classified bitmap sets (allocated by the first sweep)
 	uint32_t *swS, *swZ, *swRowZ, *swAny, *swD;
+	// ... and per-set count state (visit bitmap, word prefixes, row bases, totals, block sums), so that all
+	// the sets can be counted before any is emitted (one all-gather of the counts per sweep across slabs)
+	uint32_t *A0, *rowBV0, *blk0; uint64_t *wpreV0; Totals *totals0;
+	uint32_t *swA, *swRowB, *swBlk; uint64_t *swWpre; Totals *swTotals;
 	double sw_iso[SWEEP_MAX]; int sw_n; uint32_t sw_epoch;
 };
 
@@ -1103,10 +1109,12 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->own_stream) cudaStreamSynchronize(c->own_stream);
 	Params &P = c->P;
-	cudaFree(c->S0); cudaFree(c->Z0); cudaFree(P.A); cudaFree(c->rowZ0); cudaFree(P.wpreV);
+	if (!c->S0) { c->S0 = P.S; c->Z0 = P.Z; c->rowZ0 = P.rowZ; c->A0 = P.A; c->wpreV0 = P.wpreV; c->rowBV0 = P.rowBV; c->totals0 = P.totals; c->blk0 = c->blk_sum; }
+	cudaFree(c->S0); cudaFree(c->Z0); cudaFree(c->A0); cudaFree(c->rowZ0); cudaFree(c->wpreV0);
+	cudaFree(c->swA); cudaFree(c->swWpre); cudaFree(c->swRowB); cudaFree(c->swTotals); cudaFree(c->swBlk);
 	cudaFree(c->swS); cudaFree(c->swZ); cudaFree(c->swRowZ); cudaFree(c->swAny); cudaFree(c->swD); cudaFree(c->D0);
-	cudaFree(P.rowBV); cudaFree(P.totals);
-	cudaFree(c->blk_sum);
+	cudaFree(c->rowBV0); cudaFree(c->totals0);
+	cudaFree(c->blk0);
 	cudaFree(c->vtask);
 	cudaFree(c->grid_owned);
 	if (c->up_registered) cudaHostUnregister(c->up_registered);
@@ -1251,7 +1259,9 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	TRYCU(cudaStreamSynchronize(c->stream));
 #undef TRY
 #undef TRYCU
+	c->counted_set = -1;
 	c->S0 = P.S; c->Z0 = P.Z; c->rowZ0 = P.rowZ;
+	c->A0 = P.A; c->wpreV0 = P.wpreV; c->rowBV0 = P.rowBV; c->totals0 = P.totals; c->blk0 = c->blk_sum;
 	P.anyZp = &P.totals->anyZ;
 	c->dwords = ((size_t)P.Lrows * (P.W / 4 + 1) + 31) / 32 + 2;
 	if (cudaMalloc((void **)&c->D0, c->dwords * 4) != cudaSuccess || cudaMemset(c->D0, 0, c->dwords * 4) != cudaSuccess) {
@@ -1471,27 +1481,45 @@ static int next_epoch(mc33cu_ctx *c, uint32_t *e)
 	return MC33CU_OK;
 }
 
+// point the kernel parameters at the bitmaps and count state of the single-isovalue path (set < 0) or of
+// pre-classified sweep set `set`
+static void select_state(mc33cu_ctx *c, int set)
+{
+	Params &P = c->P;
+	if (set < 0) {
+		P.S = c->S0; P.Z = c->Z0; P.rowZ = c->rowZ0;
+		P.D = c->D0; c->zmode_cur = &c->zmode0;
+		P.A = c->A0; P.wpreV = c->wpreV0; P.rowBV = c->rowBV0; P.totals = c->totals0; c->blk_sum = c->blk0;
+		P.anyZp = &P.totals->anyZ;
+		P.zepoch = c->epoch0;
+	} else {
+		const size_t bm = (size_t)P.Lrows * P.WP, nr = (size_t)P.Lrows + 1;
+		P.S = c->swS + (size_t)set * bm; P.Z = c->swZ + (size_t)set * bm; P.rowZ = c->swRowZ + (size_t)set * P.Lrows;
+		P.anyZp = c->swAny + set;
+		P.D = c->swD + (size_t)set * c->dwords; c->zmode_cur = &c->zmode_sw[set];
+		P.zepoch = c->sw_epoch;
+		P.A = c->swA + (size_t)set * bm; P.wpreV = c->swWpre + (size_t)set * bm; P.rowBV = c->swRowB + (size_t)set * nr * 3;
+		P.totals = c->swTotals + set; c->blk_sum = c->swBlk + (size_t)set * c->nblk * 3;
+	}
+	P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
+}
+
 // set < 0: classify the single-isovalue bitmaps now; set >= 0: use pre-classified sweep set
 template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 {
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
+	select_state(c, set);
 	// re-arm the totals (overflow / on-iso flags)
 	CU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), s));
 	if (c->timing) CU(cudaEventRecord(c->ev[0], s));
 	if (set < 0) {
-		P.S = c->S0; P.Z = c->Z0; P.rowZ = c->rowZ0; P.anyZp = &P.totals->anyZ;
-		P.D = c->D0; c->zmode_cur = &c->zmode0;
-		int rc = next_epoch(c, &P.zepoch);
+		int rc = next_epoch(c, &c->epoch0);
 		if (rc) return rc;
+		P.zepoch = c->epoch0;
 		launch_classify<Sample>(c);
-	} else {
-		const size_t bm = (size_t)P.Lrows * P.WP;
-		P.S = c->swS + (size_t)set * bm; P.Z = c->swZ + (size_t)set * bm; P.rowZ = c->swRowZ + (size_t)set * P.Lrows;
-		P.anyZp = c->swAny + set;
-		P.D = c->swD + (size_t)set * c->dwords; c->zmode_cur = &c->zmode_sw[set];
-		P.zepoch = c->sw_epoch;
 	}
+	c->counted_set = set;
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
 	{
 		uint32_t grid = (uint32_t)c->n_sm * 8;
@@ -1669,11 +1697,23 @@ extern "C" int mc33cu_count_async(mc33cu_ctx *c, double iso, uint32_t *dev_count
 	return MC33CU_OK;
 }
 
-__global__ void k_slab_bases(const uint32_t *all4, int rank, uint32_t *bases2)
+__global__ void k_slab_bases(const uint32_t *all4, uint32_t stride, int rank, uint32_t *bases2)
 {
 	uint32_t v = 0;
-	for (int r = 0; r < rank; r++) v += all4[4 * r];
-	bases2[0] = v; bases2[1] = v + all4[4 * rank];
+	for (int r = 0; r < rank; r++) v += all4[(size_t)stride * r];
+	bases2[0] = v; bases2[1] = v + all4[(size_t)stride * rank];
+}
+
+extern "C" int mc33cu_slab_bases_strided(mc33cu_ctx *c, const uint32_t *dev_counts_all, uint32_t stride_words, int rank, int world,
+                                         uint32_t *dev_bases2)
+{
+	if (!c || !dev_counts_all || !dev_bases2) return fail(MC33CU_ERR_ARG, "null argument");
+	if (world < 1 || rank < 0 || rank >= world || stride_words < 4) return fail(MC33CU_ERR_ARG, "bad rank / world / stride");
+	CU(cudaSetDevice(c->device));
+	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, stride_words, rank, dev_bases2);
+	c->launches++;
+	CU(cudaGetLastError());
+	return MC33CU_OK;
 }
 
 extern "C" int mc33cu_slab_bases(mc33cu_ctx *c, const uint32_t *dev_counts_all, int rank, int world, uint32_t *dev_bases2)
@@ -1681,7 +1721,7 @@ extern "C" int mc33cu_slab_bases(mc33cu_ctx *c, const uint32_t *dev_counts_all, 
 	if (!c || !dev_counts_all || !dev_bases2) return fail(MC33CU_ERR_ARG, "null argument");
 	if (world < 1 || rank < 0 || rank >= world) return fail(MC33CU_ERR_ARG, "bad rank / world");
 	CU(cudaSetDevice(c->device));
-	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, rank, dev_bases2);
+	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, 4u, rank, dev_bases2);
 	c->launches++;
 	CU(cudaGetLastError());
 	return MC33CU_OK;
@@ -1692,6 +1732,7 @@ extern "C" int mc33cu_emit_device(mc33cu_ctx *c, const mc33cu_out *o)
 	if (!c || !o) return fail(MC33CU_ERR_ARG, "null argument");
 	if (!c->counted) return fail(MC33CU_ERR_STATE, "mc33cu_count has not run");
 	CU(cudaSetDevice(c->device));
+	select_state(c, c->counted_set);               // the mesh of the LAST count, whatever ran in between
 	int rc = set_out(c, o);
 	if (rc) return rc;
 	return dispatch_emit(c);
@@ -1719,12 +1760,7 @@ extern "C" int mc33cu_extract_device(mc33cu_ctx *c, double iso, const mc33cu_out
 template <typename Sample> static int classify_one_into_set(mc33cu_ctx *c, int j)
 {
 	// general shapes / element types: the single-isovalue kernel, once per set
-	Params &P = c->P;
-	const size_t bm = (size_t)P.Lrows * P.WP;
-	P.S = c->swS + (size_t)j * bm; P.Z = c->swZ + (size_t)j * bm; P.rowZ = c->swRowZ + (size_t)j * P.Lrows;
-	P.anyZp = c->swAny + j;
-	P.D = c->swD + (size_t)j * c->dwords; c->zmode_cur = &c->zmode_sw[j];
-	P.zepoch = c->sw_epoch;
+	select_state(c, j);
 	return launch_classify<Sample>(c);
 }
 
@@ -1745,6 +1781,14 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 		CU(cudaMalloc((void **)&c->swRowZ, (size_t)P.Lrows * 4 * SWEEP_MAX));
 		CU(cudaMalloc((void **)&c->swAny, 4 * SWEEP_MAX));
 		CU(cudaMalloc((void **)&c->swD, c->dwords * 4 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swA, bm * 4 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swWpre, bm * 8 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swRowB, ((size_t)P.Lrows + 1) * 3 * 4 * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swTotals, sizeof(Totals) * SWEEP_MAX));
+		CU(cudaMalloc((void **)&c->swBlk, (size_t)c->nblk * 3 * 4 * SWEEP_MAX));
+		CU(cudaMemsetAsync(c->swA, 0, bm * 4 * SWEEP_MAX, s));
+		CU(cudaMemsetAsync(c->swWpre, 0, bm * 8 * SWEEP_MAX, s));
+		CU(cudaMemsetAsync(c->swTotals, 0, sizeof(Totals) * SWEEP_MAX, s));
 		CU(cudaMemsetAsync(c->swD, 0, c->dwords * 4 * SWEEP_MAX, s));
 		CU(cudaMemsetAsync(c->swS, 0, bm * 4 * SWEEP_MAX, s));
 		CU(cudaMemsetAsync(c->swZ, 0, bm * 4 * SWEEP_MAX, s));
@@ -1793,6 +1837,7 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 			}
 		}
 	}
+	select_state(c, -1);
 	CU(cudaGetLastError());
 	return MC33CU_OK;
 }
@@ -1820,6 +1865,20 @@ extern "C" int mc33cu_count_set_async(mc33cu_ctx *c, int set, uint32_t *dev_coun
 	}
 	c->counted = true;
 	return MC33CU_OK;
+}
+
+extern "C" int mc33cu_emit_set_device(mc33cu_ctx *c, int set, const mc33cu_out *o)
+{
+	int rc = check_set(c, set);
+	if (rc) return rc;
+	if (!o) return fail(MC33CU_ERR_ARG, "null argument");
+	if (!c->counted) return fail(MC33CU_ERR_STATE, "the set has not been counted");
+	CU(cudaSetDevice(c->device));
+	set_iso(c, c->sw_iso[set]);
+	select_state(c, set);
+	rc = set_out(c, o);
+	if (rc) return rc;
+	return dispatch_emit(c);
 }
 
 extern "C" int mc33cu_extract_set_device(mc33cu_ctx *c, int set, const mc33cu_out *o)

@@ -107,6 +107,15 @@ class Extractor:
         o = self._out(b, **kw)
         cabi.check(self.lib.mc33cu_extract_set_device(self.h, int(j), C.byref(o)))
 
+    def emit_set(self, j, b, **kw):
+        """emit pre-classified, already counted set j (all sets can be counted before any is emitted)"""
+        o = self._out(b, **kw)
+        cabi.check(self.lib.mc33cu_emit_set_device(self.h, int(j), C.byref(o)))
+
+    def slab_bases_strided(self, counts_all, stride_words, rank, world, bases2):
+        cabi.check(self.lib.mc33cu_slab_bases_strided(self.h, C.c_void_p(counts_all.data_ptr()), int(stride_words), int(rank),
+                                                      int(world), C.c_void_p(bases2.data_ptr())))
+
     def sync(self):
         cabi.check(self.lib.mc33cu_sync(self.h))
         k = cabi.Counts()

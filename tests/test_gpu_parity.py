@@ -455,3 +455,52 @@ def test_classify_sweep_matches_single_extractions(variant, shape, scale, isos):
     assert (int(k.nV), int(k.nT)) == (want.nV, want.nT)
     assert np.array_equal(b["T"][:want.nT].cpu().numpy().view(np.uint32), want.T)
     ex.close()
+
+
+def test_sweep_sets_counted_first_then_emitted_across_slabs():
+    """bench.py's multi-GPU sweep flow on one GPU: every slab classifies the sweep once and counts ALL its
+    sets, the counts are 'all-gathered' as [slab][set][4], mc33cu_slab_bases_strided picks a set's column,
+    and the sets are emitted afterwards from their own count state; merged meshes == oracle"""
+    import torch
+    from mc33_c_library_b200 import slabs
+    from mc33_c_library_b200.device import Extractor
+    from support import merge_slab_meshes
+    variant, isos = "f32", [2.0, 3.0, 2.5, 1.0]
+    a = noise_grid(0, "u8", scale=5, shape=(21, 10, 128)).astype(np.float32)
+    parts = [s for s in slabs.partition(a.shape[0] - 1, 3) if s is not None]
+    dev = torch.device("cuda", 0)
+    exs = []
+    for s in parts:
+        ex = Extractor(make_desc(a.shape, variant, None, s))
+        ex.upload(np.ascontiguousarray(a[s.z_lo:s.z_hi]))
+        exs.append(ex)
+    per = [torch.zeros((len(isos), 4), dtype=torch.int32, device=dev) for _ in exs]
+    for ex, c in zip(exs, per):
+        ex.classify_sweep(isos)
+        for j in range(len(isos)):
+            ex.count_set_async(j, c[j])
+    torch.cuda.synchronize()
+    gathered = torch.stack(per).contiguous()                  # [slab][set][4]
+    for j in (2, 0, 3, 1):
+        whole = oracle_extract(a, isos[j], variant)
+        meshes = []
+        for r, ex in enumerate(exs):
+            nV, nT, nS, nC = (int(v) for v in gathered[r, j].tolist())
+            b = ex.alloc(nV, nT, keys=True)
+            b2 = torch.zeros(2, dtype=torch.int32, device=dev)
+            ex.slab_bases_strided(gathered[0, j], 4 * len(isos), r, len(exs), b2)
+            ex.emit_set(j, b, dev_bases=b2)
+            ex.sync()
+            meshes.append(Mesh(b["V"][:nV].cpu().numpy(), b["N"][:nV].cpu().numpy(), b["T"][:nT].cpu().numpy().view(np.uint32),
+                               vkey=b["vkey"][:nV].cpu().numpy().astype(np.uint64), tcell=b["tcell"][:nT].cpu().numpy().astype(np.uint64),
+                               nShared=nS, nCentre=nC))
+        m = merge_slab_meshes(meshes)
+        assert (m.nV, m.nT) == (whole.nV, whole.nT)
+        assert np.array_equal(m.tcell, whole.tcell)
+        om, ow = np.argsort(m.vkey, kind="stable"), np.argsort(whole.vkey, kind="stable")
+        assert np.array_equal(m.vkey[om], whole.vkey[ow])
+        inv = np.empty(m.nV, np.int64); inv[om] = ow
+        assert np.array_equal(inv[m.T.astype(np.int64)], whole.T.astype(np.int64))
+        assert np.array_equal(m.V[om], whole.V[ow])
+    for ex in exs:
+        ex.close()
