@@ -415,7 +415,7 @@ __device__ __forceinline__ uint32_t feq_mask(float a, float b)
 }
 
 #ifndef SWEEP_THREADS
-#define SWEEP_THREADS 128    // (A/B: 128 x unroll 2 measured best; 256 / 512 threads and unroll 1 / 4 are within 5 %)
+#define SWEEP_THREADS 256    // (A/B: 256 x unroll 2 measured best, 128 threads within 3 %; 512 threads spill)
 #endif
 #ifndef SWEEP_UNROLL
 #define SWEEP_UNROLL 2
