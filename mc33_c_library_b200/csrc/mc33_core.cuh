@@ -1048,12 +1048,10 @@ MC_HD void run_vertex_task(const Params &P, uint32_t id)
 }
 
 // tasks of the vertices owned by grid point (x,y,z) on a grid WITH on-iso samples
-// (generic path): plane masks of the point's own row, POINT vertices flagged
-MC_COLD void put_vertex_tasks_generic(const Params &P, uint32_t x, uint32_t y, uint32_t z)
+// (generic path): rec = plane masks of the point's own row and word, POINT vertices flagged
+MC_HDN void put_vertex_tasks_rec(const Params &P, uint32_t x, uint32_t y, uint32_t z, const WordRec &rec)
 {
 	const uint32_t lr = (z - P.zlo) * P.NY + y, w = x >> 5, b = x & 31u;
-	WordRec rec; CellWords cw;
-	word_masks_generic(P, z, y, w, rec, cw);
 	const uint32_t zw = P.rowZ[lr] == P.zepoch ? P.Z[(uint64_t)lr * P.WP + w] : 0u;
 	const uint32_t lo = (1u << b) - 1u;
 #pragma unroll
@@ -1292,11 +1290,11 @@ MC_COLD CellPattern cell_slow(const Params &P, const Tables &tb, uint32_t x, uin
 	CellPattern pat;
 	pat.start = 0; pat.m = 0; pat.ntri = 0; pat.centre = 0;
 	zm = 0;
-	if (ownp) put_vertex_tasks_generic(P, x, y, z);
-	if (!cellok) return pat;
 	const uint32_t w = x >> 5, b = x & 31u;
 	WordRec rec; CellWords cw;
-	word_masks_generic(P, z, y, w, rec, cw);
+	word_masks_generic(P, z, y, w, rec, cw);         // once: the point's tasks and the cell share it
+	if (ownp) put_vertex_tasks_rec(P, x, y, z, rec);
+	if (!cellok) return pat;
 	// (with on-iso samples a point can own a vertex while its cell is inactive)
 	if (!((rec.act >> b) & 1u)) return pat;
 	const unsigned idx = cell_index(cw.c, 1, (int)b);
