@@ -1921,6 +1921,7 @@ extern "C" int mc33cu_emit_host(mc33cu_ctx *c, void *V, float *N, int32_t *color
 	if (!c) return fail(MC33CU_ERR_ARG, "null context");
 	if (!c->counted) return fail(MC33CU_ERR_STATE, "mc33cu_count has not run");
 	CU(cudaSetDevice(c->device));
+	select_state(c, c->counted_set);               // the mesh of the LAST count
 	mc33cu_counts k;
 	fill_counts(c, &k);
 	if (k.nV == 0 && k.nT == 0) return MC33CU_OK;
