@@ -596,8 +596,15 @@ __device__ __forceinline__ void lane_item(const Params &P, unsigned lane, uint32
 #ifndef CNT_MINB
 #define CNT_MINB 3     // resident CTAs per SM k_count is compiled for: 80 registers (A/B on the gyroid: 0.061 ms at 2, 0.064 at 3, 0.073 at 4, where the hot loop spills; white noise wants the warps: 5.5 ms at 2, 3.9 at 4)
 #endif
+// (integer grids are CT-like in practice: many complex / on-iso cells to walk, which wants resident warps more
+// than registers -- 1024^3 u16: 1.31 ms at 4 CTAs per SM against 1.37 at 3)
+template <typename Sample> struct CountMinBlocks { enum { value = CNT_MINB }; };
+template <> struct CountMinBlocks<uint8_t> { enum { value = 4 }; };
+template <> struct CountMinBlocks<uint16_t> { enum { value = 4 }; };
+template <> struct CountMinBlocks<uint32_t> { enum { value = 4 }; };
+
 template <typename Sample>
-__global__ void __launch_bounds__(256, CNT_MINB) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t GW, uint32_t *blkSum)
+__global__ void __launch_bounds__(256, CountMinBlocks<Sample>::value) k_count(const __grid_constant__ Params P, uint32_t nblk, uint32_t GW, uint32_t *blkSum)
 {
 	__shared__ uint32_t s_row[3][CNT_WARPS * 32];
 	__shared__ uint32_t s_cx[2][CNT_WARPS * 32];     // triangles / centres of the complex cells, per row (added late)
