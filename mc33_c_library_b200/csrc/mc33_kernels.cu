@@ -1072,6 +1072,8 @@ struct mc33cu_ctx {
 	uint32_t epoch;                        // on-iso hint epoch, bumped by every classify launch
 	uint32_t epoch0;                       // ... of the last single-isovalue classify
 	int counted_set;                       // what the last count phase ran on: -1 single path, else the sweep set
+	int cur_state;                         // ... and what the kernel parameters point at right now
+	uint32_t emits_since_count[SWEEP_MAX + 1];   // emit launches since the count phase of each state (index set + 1)
 	// iso sweep: up to SWEEP_MAX pre-classified bitmap sets (allocated by the first sweep)
 	uint32_t *swS, *swZ, *swRowZ, *swAny, *swD;
 	// ... and per-set count state (visit bitmap, word prefixes, row bases, totals, block sums), so that all
@@ -1266,7 +1268,7 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	TRYCU(cudaStreamSynchronize(c->stream));
 #undef TRY
 #undef TRYCU
-	c->counted_set = -1;
+	c->counted_set = -1; c->cur_state = -1;
 	c->S0 = P.S; c->Z0 = P.Z; c->rowZ0 = P.rowZ;
 	c->A0 = P.A; c->wpreV0 = P.wpreV; c->rowBV0 = P.rowBV; c->totals0 = P.totals; c->blk0 = c->blk_sum;
 	P.anyZp = &P.totals->anyZ;
@@ -1493,6 +1495,7 @@ static int next_epoch(mc33cu_ctx *c, uint32_t *e)
 static void select_state(mc33cu_ctx *c, int set)
 {
 	Params &P = c->P;
+	c->cur_state = set;
 	if (set < 0) {
 		P.S = c->S0; P.Z = c->Z0; P.rowZ = c->rowZ0;
 		P.D = c->D0; c->zmode_cur = &c->zmode0;
@@ -1526,7 +1529,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 		P.zepoch = c->epoch0;
 		launch_classify<Sample>(c);
 	}
-	c->counted_set = set;
+	c->counted_set = set; c->emits_since_count[set + 1] = 0;
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
 	{
 		uint32_t grid = (uint32_t)c->n_sm * 8;
@@ -1549,6 +1552,8 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 {
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
+	// (the count phase re-arms the totals; a second emit of the same count must not see the first one's overflow flag)
+	if (c->emits_since_count[c->cur_state + 1]++) CU(cudaMemsetAsync(&P.totals->overflow, 0, sizeof(uint32_t), s));
 	{
 		// cell rows of the slab, plus the point rows above them whose vertices it owns
 		// (the grid's last slice on the last slab)

@@ -504,3 +504,33 @@ def test_sweep_sets_counted_first_then_emitted_across_slabs():
         assert np.array_equal(m.V[om], whole.V[ow])
     for ex in exs:
         ex.close()
+
+
+def test_output_capacity_is_respected():
+    """too small output buffers: mc33cu_sync reports MC33CU_ERR_CAPACITY and nothing is written past
+    the stated capacities (vertices, vertex tasks, triangles, centre vertices)"""
+    import torch
+    from mc33_c_library_b200 import _cabi as cabi
+    from mc33_c_library_b200.device import Extractor
+    a = noise_grid(0, "f32", shape=(24, 25, 128))
+    ex = Extractor(make_desc(a.shape, "f32"))
+    ex.upload(a)
+    k = ex.count(0.0)
+    nV, nT = int(k.nV), int(k.nT)
+    assert nV > 100 and nT > 100
+    for capV, capT in ((nV // 2, nT), (nV, nT // 2), (nV // 3, nT // 3), (int(k.nShared) + 1, nT)):
+        b = ex.alloc(nV, nT)
+        for t in (b["V"], b["N"]):
+            t.fill_(-77.0)
+        b["color"].fill_(-77); b["T"].fill_(-77)
+        b["capV"], b["capT"] = capV, capT
+        ex.emit(b)
+        with pytest.raises(cabi.Mc33CudaError) as e:
+            ex.sync()
+        assert e.value.code == cabi.ERR_CAPACITY
+        assert bool((b["V"][capV:] == -77.0).all()) and bool((b["N"][capV:] == -77.0).all())
+        assert bool((b["color"][capV:] == -77).all()) and bool((b["T"][capT:] == -77).all())
+    b = ex.alloc(nV, nT)                       # exact capacities still work afterwards
+    ex.emit(b)
+    ex.sync()
+    ex.close()
