@@ -42,6 +42,14 @@ def test_cabi_argument_errors_without_gpu():
     assert lib.mc33cu_create(C.byref(d), 0, C.byref(h)) == _cabi.ERR_ARG       # halo too small
     assert lib.mc33cu_count(None, 0.0, None) == _cabi.ERR_ARG
     assert b"null" in lib.mc33cu_last_error()
+    # the sweep / slab entry points reject null contexts and arguments the same way
+    isos = (C.c_double * 2)(0.0, 1.0)
+    assert lib.mc33cu_classify_sweep(None, isos, 2) == _cabi.ERR_ARG
+    assert lib.mc33cu_count_set_async(None, 0, None) == _cabi.ERR_ARG
+    assert lib.mc33cu_extract_set_device(None, 0, None) == _cabi.ERR_ARG
+    assert lib.mc33cu_emit_set_device(None, 0, None) == _cabi.ERR_ARG
+    assert lib.mc33cu_slab_bases(None, None, 0, 1, None) == _cabi.ERR_ARG
+    assert lib.mc33cu_slab_bases_strided(None, None, 4, 0, 1, None) == _cabi.ERR_ARG
     lib.mc33cu_destroy(None)
 
 

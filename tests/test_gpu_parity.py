@@ -534,3 +534,33 @@ def test_output_capacity_is_respected():
     ex.emit(b)
     ex.sync()
     ex.close()
+
+
+def test_sweep_api_state_errors():
+    import ctypes as C
+    import torch
+    from mc33_c_library_b200 import _cabi as cabi
+    from mc33_c_library_b200.device import Extractor
+    a = noise_grid(0, "f32", shape=(6, 7, 128))
+    ex = Extractor(make_desc(a.shape, "f32"))
+    b = ex.alloc(16, 16)
+    with pytest.raises(cabi.Mc33CudaError) as e:            # no grid bound yet
+        ex.classify_sweep([0.0])
+    assert e.value.code == cabi.ERR_STATE
+    ex.upload(a)
+    with pytest.raises(cabi.Mc33CudaError) as e:            # no pre-classified set yet
+        ex.extract_set_async(0, b)
+    assert e.value.code == cabi.ERR_STATE
+    with pytest.raises(cabi.Mc33CudaError) as e:            # more than 8 isovalues
+        ex.classify_sweep([0.1 * i for i in range(9)])
+    assert e.value.code == cabi.ERR_ARG
+    ex.classify_sweep([0.0, 0.2])
+    with pytest.raises(cabi.Mc33CudaError) as e:            # set index beyond the sweep
+        ex.extract_set_async(2, b)
+    assert e.value.code == cabi.ERR_STATE
+    c4 = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ex.count_set_async(1, c4)
+    torch.cuda.synchronize()
+    want = oracle_extract(a, 0.2, "f32")
+    assert (int(c4[0]), int(c4[1])) == (want.nV, want.nT)
+    ex.close()
