@@ -62,7 +62,8 @@ def build_cuda(force=False, extra=()):
 
 def build_dropin(force=False):
     outs = []
-    srcs = [CSRC / "mc33_api.c", CSRC / "mc33_io.c", ROOT / "include" / "marching_cubes_33.h", ROOT / "include" / "mc33cu.h"]
+    srcs = [CSRC / "mc33_api.c", CSRC / "mc33_io.c", CSRC / "mc33_internal.h", ROOT / "include" / "marching_cubes_33.h",
+            ROOT / "include" / "mc33cu.h"]
     srcs = [s for s in srcs if s.exists()]
     csrcs = [s for s in srcs if s.suffix == ".c"]
     for name, defs in VARIANTS.items():

@@ -19,7 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../../include/marching_cubes_33.h"
+#include "mc33_internal.h"
 #include "../../include/mc33cu.h"
 
 #ifndef DEFAULT_SURFACE_COLOR
@@ -57,16 +57,21 @@ typedef struct {
 /* 3x3 helpers: reference MC33_util_grd.c:86-121                              */
 /* ------------------------------------------------------------------------- */
 #ifndef GRD_ORTHOGONAL
+/* upper-triangular A: c = A b (t == 0) keeps the terms j >= i, c = A^T b (t != 0) the
+ * terms j <= i; c may alias b only in the order the reference evaluates them
+ * (row 2 first for the transpose, row 0 first otherwise: MC33_util_grd.c:87-98) */
 void _multTSA_bf(const double (*A)[3], MC33_real *b, MC33_real *c, int t)
 {
-	if (t) {
-		c[2] = (MC33_real)(A[0][2] * b[0] + A[1][2] * b[1] + A[2][2] * b[2]);
-		c[1] = (MC33_real)(A[0][1] * b[0] + A[1][1] * b[1]);
-		c[0] = (MC33_real)(A[0][0] * b[0]);
-	} else {
-		c[0] = (MC33_real)(A[0][0] * b[0] + A[0][1] * b[1] + A[0][2] * b[2]);
-		c[1] = (MC33_real)(A[1][1] * b[1] + A[1][2] * b[2]);
-		c[2] = (MC33_real)(A[2][2] * b[2]);
+	for (int n = 0; n < 3; n++) {
+		const int i = t ? 2 - n : n;
+		double acc = 0.0;
+		int first = 1;
+		for (int j = t ? 0 : i; j <= (t ? i : 2); j++) {
+			const double term = (t ? A[j][i] : A[i][j]) * b[j];
+			acc = first ? term : acc + term;
+			first = 0;
+		}
+		c[i] = (MC33_real)acc;
 	}
 }
 
@@ -88,14 +93,24 @@ void setIdentMat3x3d(double (*A)[3])
 }
 #endif
 
-/* Markers for MC33.store.  In the reference these are the four vertex store
- * routines (marching_cubes_33.c:485-621); here the store runs on the GPU and the
- * pointer only records which variant create_MC33 selected. */
-unsigned int MC33_spn0(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
-unsigned int MC33_spnA(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
-unsigned int MC33_spnB(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
+/* Markers for MC33.store.  In the reference these are the four vertex store routines
+ * (marching_cubes_33.c:485-621), called by MC33_findCase for every new vertex; here the
+ * store runs inside the CUDA kernels (mc33_core.cuh store_vertex) and the pointer only
+ * records which variant create_MC33 selected.  There is no host-side vertex stream to
+ * append to, so a direct call cannot do what the caller expects: it stops the program
+ * with a message instead of returning a made-up index. */
+static unsigned int store_marker_called(const char *name)
+{
+	fprintf(stderr, "libMC33_b200: %s() is a marker for MC33.store; vertices are stored on the GPU by "
+	                "calculate_isosurface and the routine cannot be called directly\n", name);
+	abort();
+	return 0;
+}
+unsigned int MC33_spn0(void *m, MC33_real *r) { (void)m; (void)r; return store_marker_called("MC33_spn0"); }
+unsigned int MC33_spnA(void *m, MC33_real *r) { (void)m; (void)r; return store_marker_called("MC33_spnA"); }
+unsigned int MC33_spnB(void *m, MC33_real *r) { (void)m; (void)r; return store_marker_called("MC33_spnB"); }
 #ifndef GRD_ORTHOGONAL
-unsigned int MC33_spnC(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
+unsigned int MC33_spnC(void *m, MC33_real *r) { (void)m; (void)r; return store_marker_called("MC33_spnC"); }
 #endif
 
 /* ------------------------------------------------------------------------- */
@@ -104,40 +119,68 @@ unsigned int MC33_spnC(void *m, MC33_real *r) { (void)m; (void)r; return 0; }
 void free_memory_grd(_GRD *Z)
 {
 	if (!Z) return;
-	if (Z->F) {
-		for (unsigned int k = 0; k <= Z->N[2]; k++) {
-			if (Z->internal_data) {
-				if (!Z->F[k]) break;
-				for (unsigned int j = 0; j <= Z->N[1]; j++) free(Z->F[k][j]);
+	GRD_data_type ***F = Z->F;
+	if (F) {
+		const unsigned int nzp = Z->N[2] + 1, nyp = Z->N[1] + 1;
+		if (Z->internal_data == MC33_GRD_BLOCK && F[0]) mc33_result_free(F[0][0]);
+		for (unsigned int k = 0; k < nzp; k++) {
+			GRD_data_type **rows = F[k];
+			if (Z->internal_data == MC33_GRD_ROWS) {
+				if (!rows) break;           /* alloc_F stopped here */
+				for (unsigned int j = 0; j < nyp; j++) free(rows[j]);
 			}
-			free(Z->F[k]);
+			free(rows);
 		}
-		free(Z->F);
+		free(F);
 	}
 	free(Z);
 }
 
-/* one malloc per x-row, like the reference: callers may free rows themselves */
+/* Row tables of Z->N[2]+1 slices x Z->N[1]+1 rows; rows == NULL: every x-row gets its
+ * own malloc (the reference's layout, MC33_util_grd.c:147-169: callers may replace or
+ * free single rows), else row (k,j) points at rows + (k*ny+j)*nx samples.
+ * On failure the slice that could not be completed is left NULL (free_memory_grd stops there). */
+static int build_F(_GRD *Z, GRD_data_type *rows)
+{
+	const size_t nx = (size_t)Z->N[0] + 1, ny = (size_t)Z->N[1] + 1, nz = (size_t)Z->N[2] + 1;
+	Z->F = (GRD_data_type ***)calloc(nz, sizeof(GRD_data_type **));
+	if (!Z->F) return -1;
+	for (size_t k = 0; k < nz; k++) {
+		GRD_data_type **tab = (GRD_data_type **)calloc(ny, sizeof(GRD_data_type *));
+		if (!tab) return -1;
+		size_t j = 0;
+		for (; j < ny; j++) {
+			tab[j] = rows ? rows + (k * ny + j) * nx : (GRD_data_type *)malloc(nx * sizeof(GRD_data_type));
+			if (!tab[j]) break;
+		}
+		if (j < ny) {
+			while (j) free(tab[--j]);
+			free(tab);
+			return -1;
+		}
+		Z->F[k] = tab;
+	}
+	return 0;
+}
+
 int alloc_F(_GRD *Z)
 {
-	const unsigned int ny1 = Z->N[1] + 1, nz1 = Z->N[2] + 1;
-	const size_t rowb = ((size_t)Z->N[0] + 1) * sizeof(GRD_data_type);
-	Z->F = (GRD_data_type ***)malloc(nz1 * sizeof(void *));
-	if (!Z->F) return -1;
-	for (unsigned int k = 0; k < nz1; k++) {
-		Z->F[k] = (GRD_data_type **)malloc(ny1 * sizeof(void *));
-		if (!Z->F[k]) return -1;
-		for (unsigned int j = 0; j < ny1; j++) {
-			Z->F[k][j] = (GRD_data_type *)malloc(rowb);
-			if (!Z->F[k][j]) {
-				while (j) free(Z->F[k][--j]);
-				free(Z->F[k]);
-				Z->F[k] = 0;
-				return -1;
-			}
-		}
+	Z->internal_data = MC33_GRD_ROWS;
+	return build_F(Z, 0);
+}
+
+int mc33_alloc_F_block(_GRD *Z)
+{
+	const size_t n = ((size_t)Z->N[0] + 1) * ((size_t)Z->N[1] + 1) * ((size_t)Z->N[2] + 1);
+	GRD_data_type *blk = (GRD_data_type *)mc33_result_alloc(n * sizeof(GRD_data_type));
+	Z->F = 0;
+	if (!blk) return -1;
+	Z->internal_data = MC33_GRD_BLOCK;
+	if (build_F(Z, blk)) {
+		/* free_memory_grd releases the block through F[0][0]: make sure it can, or do it here */
+		if (!Z->F || !Z->F[0]) { mc33_result_free(blk); Z->internal_data = 0; }
+		return -1;
 	}
-	Z->internal_data = 1;
 	return 0;
 }
 
@@ -221,14 +264,14 @@ _GRD *generate_grid_from_fn(double xi, double yi, double zi, double xf, double y
  * either kind is released here.  The reference's contract is kept: the arrays are
  * ordinary writable host memory owned by the library and released through
  * free_surface_memory. */
-static void *result_alloc(size_t bytes)
+void *mc33_result_alloc(size_t bytes)
 {
 	void *p = 0;
 	if (!getenv("MC33_B200_NO_PIN") && mc33cu_host_alloc(bytes, &p) == MC33CU_OK && p) return p;
 	return malloc(bytes ? bytes : 1);
 }
 
-static void result_free(void *p)
+void mc33_result_free(void *p)
 {
 	if (p && mc33cu_host_free(p) != MC33CU_OK) free(p);
 }
@@ -236,7 +279,7 @@ static void result_free(void *p)
 void free_surface_memory(surface *S)
 {
 	if (!S) return;
-	result_free(S->T); result_free(S->V); result_free(S->N); result_free(S->color);
+	mc33_result_free(S->T); mc33_result_free(S->V); mc33_result_free(S->N); mc33_result_free(S->color);
 	free(S);
 }
 
@@ -245,7 +288,7 @@ static int shrink(void **p, size_t bytes)
 	void *q = malloc(bytes ? bytes : 1);
 	if (!q) return -1;
 	memcpy(q, *p, bytes);
-	result_free(*p);
+	mc33_result_free(*p);
 	*p = q;
 	return 0;
 }
@@ -402,10 +445,10 @@ surface *calculate_isosurface(MC33 *M, MC33_real iso)
 	S->nV = (unsigned int)k.nV; S->nT = (unsigned int)k.nT;
 	S->capv = S->nV; S->capt = S->nT ? S->nT : 1;
 	S->iso = iso;
-	S->T = (unsigned int (*)[3])result_alloc((size_t)S->capt * 3 * sizeof(int));
-	S->V = (MC33_real (*)[3])result_alloc((size_t)S->capv * 3 * sizeof(MC33_real));
-	S->N = (float (*)[3])result_alloc((size_t)S->capv * 3 * sizeof(float));
-	S->color = (int *)result_alloc((size_t)S->capv * sizeof(int));
+	S->T = (unsigned int (*)[3])mc33_result_alloc((size_t)S->capt * 3 * sizeof(int));
+	S->V = (MC33_real (*)[3])mc33_result_alloc((size_t)S->capv * 3 * sizeof(MC33_real));
+	S->N = (float (*)[3])mc33_result_alloc((size_t)S->capv * 3 * sizeof(float));
+	S->color = (int *)mc33_result_alloc((size_t)S->capv * sizeof(int));
 	if (!S->T || !S->V || !S->N || !S->color) goto fail;
 	rc = mc33cu_emit_host(p->ctx, S->V, (float *)S->N, S->color, (unsigned int *)S->T, DefaultColorMC);
 	if (rc != MC33CU_OK) goto fail;

@@ -1052,8 +1052,12 @@ struct mc33cu_ctx {
 	// k_count blocks (CNT_WARPS * G rows each) and their (V, T, C) sums
 	uint32_t *blk_sum; uint32_t nblk, cnt_gw, cnt_rb;
 	// host mirror of totals
-	Totals *h_totals;
+	Totals *h_all;           // pinned: [0] single-isovalue state, [1 + j] sweep set j
+	Totals *h_totals;        // = &h_all[counted_set + 1]
 	bool counted;
+	uint32_t counted_mask;   // bit (state + 1): the state has a valid count (cleared for the sets by a new sweep classify)
+	uint32_t pending_mask;   // ... has count / emit launches whose flags mc33cu_sync has not looked at yet
+	uint32_t hvalid_mask;    // ... its totals are in the host mirror
 	// staging outputs for the host path
 	void *oV; float *oN; int32_t *oC; uint32_t *oT; uint64_t ocapV, ocapT;
 	// timing
@@ -1081,6 +1085,7 @@ struct mc33cu_ctx {
 	uint32_t *A0, *rowBV0, *blk0; uint64_t *wpreV0; Totals *totals0;
 	uint32_t *swA, *swRowB, *swBlk; uint64_t *swWpre; Totals *swTotals;
 	double sw_iso[SWEEP_MAX]; int sw_n; uint32_t sw_epoch;
+	bool sweep_ready;                      // all the sweep-set arrays are allocated
 };
 
 extern "C" const char *mc33cu_last_error(void) { return g_err; }
@@ -1129,7 +1134,7 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	if (c->up_registered) cudaHostUnregister(c->up_registered);
 	cudaFree(c->oV); cudaFree(c->oN); cudaFree(c->oC); cudaFree(c->oT);
 	if (c->pinned) cudaFreeHost(c->pinned);
-	if (c->h_totals) cudaFreeHost(c->h_totals);
+	if (c->h_all) cudaFreeHost(c->h_all);
 	for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	free(c);
@@ -1263,7 +1268,9 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	TRY(dalloc(&P.totals, 1));
 	TRYCU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), c->stream));
 	TRY(dalloc(&c->blk_sum, (size_t)c->nblk * 3));
-	TRYCU(cudaMallocHost((void **)&c->h_totals, sizeof(Totals)));
+	TRYCU(cudaMallocHost((void **)&c->h_all, sizeof(Totals) * (SWEEP_MAX + 1)));
+	memset(c->h_all, 0, sizeof(Totals) * (SWEEP_MAX + 1));
+	c->h_totals = c->h_all;
 	for (int i = 0; i < 6; i++) TRYCU(cudaEventCreate(&c->ev[i]));
 	TRYCU(cudaStreamSynchronize(c->stream));
 #undef TRY
@@ -1530,6 +1537,8 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 		launch_classify<Sample>(c);
 	}
 	c->counted_set = set; c->emits_since_count[set + 1] = 0;
+	c->h_totals = c->h_all + (set + 1);
+	c->counted_mask |= 1u << (set + 1); c->pending_mask |= 1u << (set + 1); c->hvalid_mask &= ~(1u << (set + 1));
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
 	{
 		uint32_t grid = (uint32_t)c->n_sm * 8;
@@ -1554,6 +1563,7 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 	cudaStream_t s = c->stream;
 	// (the count phase re-arms the totals; a second emit of the same count must not see the first one's overflow flag)
 	if (c->emits_since_count[c->cur_state + 1]++) CU(cudaMemsetAsync(&P.totals->overflow, 0, sizeof(uint32_t), s));
+	c->pending_mask |= 1u << (c->cur_state + 1); c->hvalid_mask &= ~(1u << (c->cur_state + 1));
 	{
 		// cell rows of the slab, plus the point rows above them whose vertices it owns
 		// (the grid's last slice on the last slab)
@@ -1654,10 +1664,32 @@ static int set_out(mc33cu_ctx *c, const mc33cu_out *o)
 	return MC33CU_OK;
 }
 
-static int fetch_totals(mc33cu_ctx *c)
+static Totals *state_totals(mc33cu_ctx *c, int state) { return state < 0 ? c->totals0 : c->swTotals + state; }
+
+// Bring the totals (counts, overflow / range flags) of every state with launches since the last
+// fetch to the host, plus those of the last counted state; one synchronisation.  *flags = OR of
+// {1: range, 2: overflow} over the fetched states.
+static int fetch_totals(mc33cu_ctx *c, uint32_t *flags = nullptr)
 {
-	CU(cudaMemcpyAsync(c->h_totals, c->P.totals, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+	uint32_t want = c->pending_mask | (c->counted ? 1u << (c->counted_set + 1) : 0u);
+	if (!c->counted && !want) want = 1u;
+	want &= ~c->hvalid_mask | c->pending_mask;
+	for (int st = -1; st < SWEEP_MAX; st++)
+		if ((want >> (st + 1)) & 1u) {
+			if (st >= 0 && !c->swTotals) continue;
+			CU(cudaMemcpyAsync(c->h_all + (st + 1), state_totals(c, st), sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+		}
 	CU(cudaStreamSynchronize(c->stream));
+	uint32_t f = 0;
+	for (int st = -1; st < SWEEP_MAX; st++)
+		if ((want >> (st + 1)) & 1u) {
+			const Totals &t = c->h_all[st + 1];
+			if (t.range) f |= 1u;
+			if (t.overflow) f |= 2u;
+		}
+	c->hvalid_mask |= want;
+	c->pending_mask = 0;
+	if (flags) *flags = f;
 	return MC33CU_OK;
 }
 
@@ -1709,11 +1741,16 @@ extern "C" int mc33cu_count_async(mc33cu_ctx *c, double iso, uint32_t *dev_count
 	return MC33CU_OK;
 }
 
-__global__ void k_slab_bases(const uint32_t *all4, uint32_t stride, int rank, uint32_t *bases2)
+// (64-bit sums: the per-slab range check of the scan does not see an overflow of the GLOBAL vertex count)
+__global__ void k_slab_bases(const uint32_t *all4, uint32_t stride, int rank, int world, uint32_t *bases2, Totals *tot)
 {
-	uint32_t v = 0;
-	for (int r = 0; r < rank; r++) v += all4[(size_t)stride * r];
-	bases2[0] = v; bases2[1] = v + all4[(size_t)stride * rank];
+	uint64_t v = 0, all = 0;
+	for (int r = 0; r < world; r++) {
+		if (r == rank) { bases2[0] = (uint32_t)v; bases2[1] = (uint32_t)(v + all4[(size_t)stride * r]); }
+		if (r <= rank) v += all4[(size_t)stride * r];
+		all += all4[(size_t)stride * r];
+	}
+	if (all >= 0xFFFFFFFFull) tot->range = 1u;
 }
 
 extern "C" int mc33cu_slab_bases_strided(mc33cu_ctx *c, const uint32_t *dev_counts_all, uint32_t stride_words, int rank, int world,
@@ -1722,7 +1759,8 @@ extern "C" int mc33cu_slab_bases_strided(mc33cu_ctx *c, const uint32_t *dev_coun
 	if (!c || !dev_counts_all || !dev_bases2) return fail(MC33CU_ERR_ARG, "null argument");
 	if (world < 1 || rank < 0 || rank >= world || stride_words < 4) return fail(MC33CU_ERR_ARG, "bad rank / world / stride");
 	CU(cudaSetDevice(c->device));
-	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, stride_words, rank, dev_bases2);
+	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, stride_words, rank, world, dev_bases2, c->P.totals);
+	c->pending_mask |= 1u << (c->cur_state + 1);
 	c->launches++;
 	CU(cudaGetLastError());
 	return MC33CU_OK;
@@ -1733,7 +1771,8 @@ extern "C" int mc33cu_slab_bases(mc33cu_ctx *c, const uint32_t *dev_counts_all, 
 	if (!c || !dev_counts_all || !dev_bases2) return fail(MC33CU_ERR_ARG, "null argument");
 	if (world < 1 || rank < 0 || rank >= world) return fail(MC33CU_ERR_ARG, "bad rank / world");
 	CU(cudaSetDevice(c->device));
-	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, 4u, rank, dev_bases2);
+	k_slab_bases<<<1, 1, 0, c->stream>>>(dev_counts_all, 4u, rank, world, dev_bases2, c->P.totals);
+	c->pending_mask |= 1u << (c->cur_state + 1);
 	c->launches++;
 	CU(cudaGetLastError());
 	return MC33CU_OK;
@@ -1742,7 +1781,8 @@ extern "C" int mc33cu_slab_bases(mc33cu_ctx *c, const uint32_t *dev_counts_all, 
 extern "C" int mc33cu_emit_device(mc33cu_ctx *c, const mc33cu_out *o)
 {
 	if (!c || !o) return fail(MC33CU_ERR_ARG, "null argument");
-	if (!c->counted) return fail(MC33CU_ERR_STATE, "mc33cu_count has not run");
+	if (!c->counted || !((c->counted_mask >> (c->counted_set + 1)) & 1u))
+		return fail(MC33CU_ERR_STATE, "mc33cu_count has not run (or its sweep set was re-classified since)");
 	CU(cudaSetDevice(c->device));
 	select_state(c, c->counted_set);               // the mesh of the LAST count, whatever ran in between
 	int rc = set_out(c, o);
@@ -1785,31 +1825,36 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
 	const size_t bm = (size_t)P.Lrows * P.WP;
-	if (!c->swS) {
-		// (first sweep on this context: not on the steady-state path)
+	if (!c->sweep_ready) {
+		// (first sweep on this context: not on the steady-state path).  All or nothing: a failed
+		// allocation releases what the earlier ones got, so that a later call starts over.
 		CU(cudaStreamSynchronize(s));
-		CU(cudaMalloc((void **)&c->swS, bm * 4 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swZ, bm * 4 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swRowZ, (size_t)P.Lrows * 4 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swAny, 4 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swD, c->dwords * 4 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swA, bm * 4 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swWpre, bm * 8 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swRowB, ((size_t)P.Lrows + 1) * 3 * 4 * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swTotals, sizeof(Totals) * SWEEP_MAX));
-		CU(cudaMalloc((void **)&c->swBlk, (size_t)c->nblk * 3 * 4 * SWEEP_MAX));
-		CU(cudaMemsetAsync(c->swA, 0, bm * 4 * SWEEP_MAX, s));
-		CU(cudaMemsetAsync(c->swWpre, 0, bm * 8 * SWEEP_MAX, s));
-		CU(cudaMemsetAsync(c->swTotals, 0, sizeof(Totals) * SWEEP_MAX, s));
-		CU(cudaMemsetAsync(c->swD, 0, c->dwords * 4 * SWEEP_MAX, s));
-		CU(cudaMemsetAsync(c->swS, 0, bm * 4 * SWEEP_MAX, s));
-		CU(cudaMemsetAsync(c->swZ, 0, bm * 4 * SWEEP_MAX, s));
-		CU(cudaMemsetAsync(c->swRowZ, 0, (size_t)P.Lrows * 4 * SWEEP_MAX, s));
+		struct { void **p; size_t bytes; bool zero; } al[] = {
+			{(void **)&c->swS, bm * 4 * SWEEP_MAX, true}, {(void **)&c->swZ, bm * 4 * SWEEP_MAX, true},
+			{(void **)&c->swRowZ, (size_t)P.Lrows * 4 * SWEEP_MAX, true}, {(void **)&c->swAny, 4 * SWEEP_MAX, true},
+			{(void **)&c->swD, c->dwords * 4 * SWEEP_MAX, true}, {(void **)&c->swA, bm * 4 * SWEEP_MAX, true},
+			{(void **)&c->swWpre, bm * 8 * SWEEP_MAX, true}, {(void **)&c->swRowB, ((size_t)P.Lrows + 1) * 3 * 4 * SWEEP_MAX, false},
+			{(void **)&c->swTotals, sizeof(Totals) * SWEEP_MAX, true}, {(void **)&c->swBlk, (size_t)c->nblk * 3 * 4 * SWEEP_MAX, false}};
+		cudaError_t e = cudaSuccess;
+		for (auto &a : al) {
+			*a.p = nullptr;
+			e = cudaMalloc(a.p, a.bytes);
+			if (e == cudaSuccess && a.zero) e = cudaMemsetAsync(*a.p, 0, a.bytes, s);
+			if (e != cudaSuccess) break;
+		}
+		if (e != cudaSuccess) {
+			for (auto &a : al) { cudaFree(*a.p); *a.p = nullptr; }
+			cudaGetLastError();
+			return fail(e == cudaErrorMemoryAllocation ? MC33CU_ERR_NOMEM : MC33CU_ERR_CUDA, "sweep sets: %s", cudaGetErrorString(e));
+		}
+		c->sweep_ready = true;
 	}
 	CU(cudaMemsetAsync(c->swAny, 0, 4 * SWEEP_MAX, s));
 	int rc = next_epoch(c, &c->sw_epoch);
 	if (rc) return rc;
 	c->sw_n = n;
+	c->counted_mask &= 1u;            // the sets' earlier counts belong to the previous sweep's bitmaps
+	c->hvalid_mask &= 1u;
 	for (int j = 0; j < n; j++) c->sw_iso[j] = isos[j];
 	c->ev_valid = false;
 	const ClsPlan &pl = c->cls;
@@ -1884,7 +1929,7 @@ extern "C" int mc33cu_emit_set_device(mc33cu_ctx *c, int set, const mc33cu_out *
 	int rc = check_set(c, set);
 	if (rc) return rc;
 	if (!o) return fail(MC33CU_ERR_ARG, "null argument");
-	if (!c->counted) return fail(MC33CU_ERR_STATE, "the set has not been counted");
+	if (!((c->counted_mask >> (set + 1)) & 1u)) return fail(MC33CU_ERR_STATE, "the set has not been counted since the last mc33cu_classify_sweep");
 	CU(cudaSetDevice(c->device));
 	set_iso(c, c->sw_iso[set]);
 	select_state(c, set);
@@ -1913,10 +1958,14 @@ extern "C" int mc33cu_extract_set_device(mc33cu_ctx *c, int set, const mc33cu_ou
 extern "C" int mc33cu_sync(mc33cu_ctx *c)
 {
 	if (!c) return fail(MC33CU_ERR_ARG, "null context");
-	int rc = fetch_totals(c);
+	CU(cudaSetDevice(c->device));
+	// every state (single-isovalue path, sweep sets) counted or emitted since the last sync is looked at:
+	// an overflow of set 0 is not hidden by a later emit of set 1
+	uint32_t flags = 0;
+	int rc = fetch_totals(c, &flags);
 	if (rc) return rc;
-	if (c->h_totals->range) return fail(MC33CU_ERR_RANGE, "more than 2^32-1 vertices or triangles");
-	if (c->h_totals->overflow) return fail(MC33CU_ERR_CAPACITY, "output capacity exceeded");
+	if (flags & 1u) return fail(MC33CU_ERR_RANGE, "more than 2^32-1 vertices or triangles");
+	if (flags & 2u) return fail(MC33CU_ERR_CAPACITY, "output capacity exceeded");
 	return MC33CU_OK;
 }
 
@@ -1924,6 +1973,10 @@ extern "C" int mc33cu_get_counts(mc33cu_ctx *c, mc33cu_counts *k)
 {
 	if (!c || !k) return fail(MC33CU_ERR_ARG, "null argument");
 	if (!c->counted) return fail(MC33CU_ERR_STATE, "nothing counted yet");
+	if (!((c->hvalid_mask >> (c->counted_set + 1)) & 1u)) {   // counted without a host fetch (*_async): fetch now
+		int rc = fetch_totals(c);
+		if (rc) return rc;
+	}
 	fill_counts(c, k);
 	return MC33CU_OK;
 }
@@ -1931,9 +1984,14 @@ extern "C" int mc33cu_get_counts(mc33cu_ctx *c, mc33cu_counts *k)
 extern "C" int mc33cu_emit_host(mc33cu_ctx *c, void *V, float *N, int32_t *color, uint32_t *T, int32_t color_value)
 {
 	if (!c) return fail(MC33CU_ERR_ARG, "null context");
-	if (!c->counted) return fail(MC33CU_ERR_STATE, "mc33cu_count has not run");
+	if (!c->counted || !((c->counted_mask >> (c->counted_set + 1)) & 1u))
+		return fail(MC33CU_ERR_STATE, "mc33cu_count has not run (or its sweep set was re-classified since)");
 	CU(cudaSetDevice(c->device));
 	select_state(c, c->counted_set);               // the mesh of the LAST count
+	if (!((c->hvalid_mask >> (c->counted_set + 1)) & 1u)) {
+		int rc0 = fetch_totals(c);
+		if (rc0) return rc0;
+	}
 	mc33cu_counts k;
 	fill_counts(c, &k);
 	if (k.nV == 0 && k.nT == 0) return MC33CU_OK;
