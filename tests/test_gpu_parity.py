@@ -564,3 +564,47 @@ def test_sweep_api_state_errors():
     want = oracle_extract(a, 0.2, "f32")
     assert (int(c4[0]), int(c4[1])) == (want.nV, want.nT)
     ex.close()
+
+
+def test_sync_reports_overflow_of_any_set_emitted_since_the_last_sync():
+    """count every set, emit set 0 into too small buffers and set 1 into large enough ones, sync ONCE:
+    the overflow of set 0 must not be hidden by the later emit (round-1 advisor finding)"""
+    import torch
+    from mc33_c_library_b200 import _cabi as cabi
+    from mc33_c_library_b200.device import Extractor
+    a = noise_grid(0, "f32", shape=(12, 13, 128))
+    ex = Extractor(make_desc(a.shape, "f32"))
+    ex.upload(a)
+    isos = [0.0, 0.3]
+    ex.classify_sweep(isos)
+    c4 = torch.zeros((2, 4), dtype=torch.int32, device="cuda")
+    for j in range(2):
+        ex.count_set_async(j, c4[j])
+    torch.cuda.synchronize()
+    nV, nT = int(c4[:, 0].max()), int(c4[:, 1].max())
+    small, big = ex.alloc(nV, nT), ex.alloc(nV, nT)
+    small["capV"], small["capT"] = nV // 4, nT // 4
+    ex.emit_set(0, small)
+    ex.emit_set(1, big)
+    with pytest.raises(cabi.Mc33CudaError) as e:
+        ex.sync()
+    assert e.value.code == cabi.ERR_CAPACITY
+    # the same two emits with room for both: clean
+    ex.emit_set(0, big); ex.sync()
+    want = oracle_extract(a, isos[0], "f32")
+    assert np.array_equal(big["T"][:want.nT].cpu().numpy().view(np.uint32), want.T)
+    ex.emit_set(1, big); ex.sync()
+    # a new sweep classify invalidates the sets' counts: emit without a new count is a state error, not a wrong mesh
+    ex.classify_sweep([0.1, 0.2])
+    with pytest.raises(cabi.Mc33CudaError) as e:
+        ex.emit_set(0, big)
+    assert e.value.code == cabi.ERR_STATE
+    ex.count_set_async(0, c4[0])
+    ex.emit_set(0, big)
+    ex.sync()
+    want = oracle_extract(a, 0.1, "f32")
+    assert np.array_equal(big["T"][:want.nT].cpu().numpy().view(np.uint32), want.T)
+    # counts fetched lazily after an *_async count (the host mirror is not stale)
+    k = ex.sync()
+    assert (int(k.nV), int(k.nT)) == (want.nV, want.nT)
+    ex.close()
