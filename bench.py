@@ -127,12 +127,14 @@ def sample_range(W):
 
 def cpu_run(lib, W, host, isos, threads, count_only=False):
     """reference calculate_isosurface (or size_of_isosurface) for every isovalue on `host` (z,y,x samples).
-    threads > 1: the volume is cut into z-chunks that overlap by one slice, one independent MC33 per task
-    (the reference itself is single threaded; distinct MC33 objects are independent)."""
+    The reference is single threaded; the one parallel use of it that still returns the SAME meshes is one
+    independent MC33 object per isovalue (distinct MC33 on one grid are independent), so
+    `threads` is capped at the number of isovalues.  (Cutting the grid into z-chunks would return pieces with
+    duplicated seam vertices and separate index spaces: not the reference's output.)"""
     import ctypes as C
     geom = W.geometry()
     NZ = host.shape[0]
-    nchunk = 1 if threads <= 1 else max(1, min((threads + len(isos) - 1) // len(isos), (NZ - 1) // 8 or 1))
+    nchunk = 1
     bounds = [round(i * (NZ - 1) / nchunk) for i in range(nchunk + 1)]
     tasks = [(i, bounds[c], bounds[c + 1] + 1) for i in range(len(isos)) for c in range(nchunk) if bounds[c + 1] > bounds[c]]
     res = [[0, 0] for _ in isos]
@@ -191,8 +193,8 @@ def run_reference(args):
     import torch
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     (z0, z1), host = host_sample(W, dev)
-    cores = max(1, os.cpu_count() or 1)
     isos = list(W.isos)
+    cores = max(1, min(len(isos), os.cpu_count() or 1))
     for _ in range(min(args.warmup, 1)):
         cpu_run(lib, W, host, isos, cores)
     ts, ntri, ntask = [], 0, 0
@@ -205,7 +207,8 @@ def run_reference(args):
     val = vox / t * 1e-9
     used = min(cores, ntask)
     sample = (f"z slices [{z0},{z1}) of the grid ({host.shape[0]}x{host.shape[1]}x{host.shape[2]} samples), {len(isos)} isovalue(s), "
-              f"{ntask} independent MC33 tasks ({nchunk} z-chunk(s) per isovalue) on {used} host threads")
+              f"one independent MC33 per isovalue on {used} host thread(s) (the reference is single threaded: this is all the "
+              "parallelism that returns the same meshes)")
     print(json.dumps({"impl": "reference", "metric": "Gvoxels/s per isosurface", "value": val, "unit": "Gvoxels/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
                       "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,

@@ -118,6 +118,21 @@ int  mc33cu_set_stream(mc33cu_ctx *ctx, void *cuda_stream);
 int  mc33cu_grid_device(mc33cu_ctx *ctx, const void *dev_samples);
 int  mc33cu_grid_upload(mc33cu_ctx *ctx, const void *host_samples);
 int  mc33cu_grid_upload_rows(mc33cu_ctx *ctx, const void *const *const *F);
+/* the same without waiting for the copy (it is ordered on the context's stream in front of whatever is
+ * launched next): several contexts on several devices upload their slabs side by side, each over its own
+ * link.  Only page-locked host memory is copied asynchronously by the driver; mc33cu_grid_upload_rows_async
+ * falls back to the staged, synchronous row copy when the rows are separate allocations. */
+int  mc33cu_grid_upload_async(mc33cu_ctx *ctx, const void *host_samples);
+int  mc33cu_grid_upload_rows_async(mc33cu_ctx *ctx, const void *const *const *F);
+/* *block = the contiguous host block the slab's rows form (grid_from_data_pointer layout,
+ * MC33_util_grd.c:600-612) and its size, or NULL / 0 when the rows are separate allocations */
+int  mc33cu_grid_rows_block(mc33cu_ctx *ctx, const void *const *const *F, const void **block, size_t *bytes);
+/* Explicit page-locking of caller-owned memory (cudaHostRegisterPortable, reference counted per
+ * block, process wide).  The upload calls never register memory on their own; the drop-in
+ * registers the grid's sample block at its first upload and releases it in free_MC33.  The
+ * block must stay mapped until it is unregistered. */
+int  mc33cu_host_register(const void *p, size_t bytes);
+int  mc33cu_host_unregister(const void *p);
 
 /* classify + count + scan for isovalue iso; synchronises and returns the counts
  * (the GPU form of size_of_isosurface).  iso is converted to MC33_real. */
@@ -161,6 +176,12 @@ int  mc33cu_get_counts(mc33cu_ctx *ctx, mc33cu_counts *counts);
  * counts.nV / counts.nT entries (device staging is owned by the context). */
 int  mc33cu_emit_host(mc33cu_ctx *ctx, void *V, float *N, int32_t *color, uint32_t *T,
                       int32_t color_value);
+/* the same for one z-slab of several, without waiting: the slab's vertices / triangles go to the given host
+ * positions (the caller offsets the arrays by the slab's vertex / triangle base), triangles carry global ids
+ * (vbase, vbase_next as in mc33cu_out); the triangle download overlaps the vertex kernel on a second stream.
+ * mc33cu_sync waits for everything and reports overflow. */
+int  mc33cu_emit_host_async(mc33cu_ctx *ctx, void *V, float *N, int32_t *color, uint32_t *T, uint32_t vbase,
+                            uint32_t vbase_next, int32_t color_value);
 
 /* Page-locked host memory for result arrays, pooled across calls (device-to-host
  * copies into it run at PCIe speed).  mc33cu_host_free returns MC33CU_ERR_ARG for a

@@ -46,12 +46,25 @@
 /* reference marching_cubes_33.c:76-80 */
 int DefaultColorMC = (int)DEFAULT_SURFACE_COLOR;
 
-/* The MC33 handed to the caller is the head of this private record. */
+/* The MC33 handed to the caller is the head of this private record.  The grid is cut into
+ * nslab contiguous z-slabs of cell layers, one CUDA context (= one GPU) each: the same
+ * decomposition bench.py drives over NCCL ranks, here inside one process, with
+ * the per-slab counts exchanged through the host -- they are needed there anyway to size the
+ * surface.  Every GPU pulls its slab over its own PCIe link and pushes its part of the mesh
+ * straight into the final host arrays. */
+#define MC33_MAX_SLABS 16
 typedef struct {
 	MC33 pub;
-	mc33cu_ctx *ctx;
+	int nslab;
+	mc33cu_ctx *ctx[MC33_MAX_SLABS];
 	int grid_uploaded;
+	const void *registered;      /* the grid's sample block, page-locked by us at the first upload */
+	int reg_tried;
 } mc33_private;
+
+static int g_last_nslab = 0;
+/* how many GPUs the most recently created MC33 uses (reporting hook of bench.py) */
+int mc33_dropin_gpus_last(void) { return g_last_nslab; }
 
 /* ------------------------------------------------------------------------- */
 /* 3x3 helpers: reference MC33_util_grd.c:86-121                              */
@@ -315,18 +328,30 @@ void free_MC33(MC33 *M)
 {
 	if (!M) return;
 	mc33_private *p = (mc33_private *)M;
-	mc33cu_destroy(p->ctx);
+	for (int i = 0; i < p->nslab; i++) mc33cu_destroy(p->ctx[i]);
+	if (p->registered) mc33cu_host_unregister(p->registered);
 	free(p);
 }
 
-static void describe(const MC33 *M, mc33cu_desc *d)
+/* cell layers [*z0, *z1) of slab i of n (the first slabs take the remainder), and the sample slices
+ * it needs: one below (normals / on-iso neighbours of its first slice), two above (the seam slice is
+ * numbered by the next slab, whose on-iso points look one slice further) */
+static void slab_range(unsigned int nz, int i, int n, unsigned int *z0, unsigned int *z1, unsigned int *lo, unsigned int *hi)
+{
+	const unsigned int base = nz / (unsigned int)n, rem = nz % (unsigned int)n, ui = (unsigned int)i;
+	*z0 = ui * base + (ui < rem ? ui : rem);
+	*z1 = *z0 + base + (ui < rem ? 1u : 0u);
+	*lo = (*z0 > 0 ? *z0 : 1u) - 1u;
+	*hi = *z1 + 2 < nz + 1 ? *z1 + 2 : nz + 1;
+}
+
+static void describe(const MC33 *M, mc33cu_desc *d, int slab, int nslab)
 {
 	memset(d, 0, sizeof *d);
 	d->dtype = MC33_DTYPE;
 	d->nx = M->nx; d->ny = M->ny; d->nz = M->nz;
-	d->z_lo = 0; d->z_hi = M->nz + 1;
-	d->cell_z0 = 0; d->cell_z1 = M->nz;
-	d->is_last = 1;
+	slab_range(M->nz, slab, nslab, &d->cell_z0, &d->cell_z1, &d->z_lo, &d->z_hi);
+	d->is_last = slab == nslab - 1;
 	d->normal_neg = MC33_NORMAL_NEG;
 	d->store = M->store == MC33_spn0 ? MC33CU_SPN0 : M->store == MC33_spnA ? MC33CU_SPNA
 	         : M->store == MC33_spnB ? MC33CU_SPNB : -1;
@@ -378,44 +403,118 @@ MC33 *create_MC33(_GRD *G)
 	}
 	M->F = (const GRD_data_type ***)G->F;
 	if (!M->nx || !M->ny || !M->nz) { free(p); return 0; }
-	mc33cu_desc d;
-	describe(M, &d);
-	if (d.tsa < 0) d.tsa = 0;
-	if (mc33cu_create(&d, 0, &p->ctx) != MC33CU_OK) {
-		if (getenv("MC33_B200_VERBOSE")) fprintf(stderr, "create_MC33: %s\n", mc33cu_last_error());
-		free(p);
-		return 0;
+	/* how many GPUs: MC33_B200_GPUS (default: all visible), never more than cell layers; without an
+	 * explicit request a slab is not made smaller than 64 MB of samples (below that the per-call
+	 * overheads of one more device outweigh its share of the copy) */
+	int ndev = mc33cu_device_count(), want = ndev;
+	const char *e = getenv("MC33_B200_GPUS");
+	if (e && atoi(e) > 0) want = atoi(e);
+	else {
+		const double bytes = ((double)M->nx + 1) * ((double)M->ny + 1) * ((double)M->nz + 1) * sizeof(GRD_data_type);
+		const int by_size = (int)(bytes / (64.0 * 1024 * 1024));
+		if (want > by_size) want = by_size;
 	}
+	if (want > ndev) want = ndev;
+	/* MC33_B200_DEVICES="2,3" names the device of every slab explicitly (a device may appear more than
+	 * once: slabs are independent contexts) and overrides the count above */
+	int devs[MC33_MAX_SLABS];
+	for (int i = 0; i < MC33_MAX_SLABS; i++) devs[i] = i;
+	const char *dl = getenv("MC33_B200_DEVICES");
+	if (dl && *dl) {
+		int n = 0;
+		for (const char *q = dl; *q && n < MC33_MAX_SLABS;) {
+			char *end = 0;
+			const long v = strtol(q, &end, 10);
+			if (end == q) break;
+			devs[n++] = (int)v;
+			q = *end == ',' ? end + 1 : end;
+		}
+		if (n > 0) want = n;
+	}
+	if (want > MC33_MAX_SLABS) want = MC33_MAX_SLABS;
+	if ((unsigned int)want > M->nz) want = (int)M->nz;
+	if (want < 1) want = 1;
+	for (int i = 0; i < want; i++) {
+		mc33cu_desc d;
+		describe(M, &d, i, want);
+		if (d.tsa < 0) d.tsa = 0;
+		if (mc33cu_create(&d, devs[i], &p->ctx[i]) != MC33CU_OK) {
+			if (getenv("MC33_B200_VERBOSE")) fprintf(stderr, "create_MC33: %s\n", mc33cu_last_error());
+			for (int j = 0; j < i; j++) mc33cu_destroy(p->ctx[j]);
+			free(p);
+			return 0;
+		}
+		p->nslab = i + 1;
+	}
+	g_last_nslab = p->nslab;
 	return M;
 }
 
-/* shared front half of calculate_isosurface / size_of_isosurface: bring the
- * samples to the device and count */
-static int count_on_device(MC33 *M, MC33_real iso, mc33cu_counts *k)
+/* is the whole grid one x-fastest block (grid_from_data_pointer, the block readers)? */
+static const void *whole_block(const MC33 *M, size_t *bytes)
+{
+	const size_t rowb = ((size_t)M->nx + 1) * sizeof(GRD_data_type), NY = (size_t)M->ny + 1, NZ = (size_t)M->nz + 1;
+	const char *first = (const char *)M->F[0][0];
+	for (size_t z = 0; z < NZ; z++)
+		for (size_t y = 0; y < NY; y++)
+			if ((const char *)M->F[z][y] != first + (z * NY + y) * rowb) return 0;
+	*bytes = NZ * NY * rowb;
+	return first;
+}
+
+/* shared front half of calculate_isosurface / size_of_isosurface: bring the samples to the
+ * devices and count; k[i] = counts of slab i, *tot = their sums */
+static int count_on_devices(MC33 *M, MC33_real iso, mc33cu_counts *k, mc33cu_counts *tot)
 {
 	mc33_private *p = (mc33_private *)M;
-	mc33cu_desc d;
-	describe(M, &d);
-	if (d.store < 0 || d.tsa < 0) return MC33CU_ERR_ARG;
-	int rc = mc33cu_set_geometry(p->ctx, &d);
-	if (rc) return rc;
-	/* The reference reads the samples at calculate time (c:1792, c:1820), so they
-	 * are uploaded on every call; MC33_B200_CACHE_GRID=1 promises they do not
-	 * change between calls on the same MC33 and uploads them once. */
+	int rc;
+	for (int i = 0; i < p->nslab; i++) {
+		mc33cu_desc d;
+		describe(M, &d, i, p->nslab);
+		if (d.store < 0 || d.tsa < 0) return MC33CU_ERR_ARG;
+		rc = mc33cu_set_geometry(p->ctx[i], &d);
+		if (rc) return rc;
+	}
+	/* The reference reads the samples at calculate time (c:1792, c:1820), so they are uploaded on
+	 * every call; MC33_B200_CACHE_GRID=1 promises they do not change between calls on the same MC33
+	 * and uploads them once.  A grid that is one block is page-locked at its first upload (DMA at
+	 * link speed, all slabs in flight together) and released in free_MC33: G and its samples must
+	 * outlive M, as for the reference (M borrows G->F, c:1792).  MC33_B200_NO_PIN=1 turns that off. */
 	const char *cache = getenv("MC33_B200_CACHE_GRID");
 	if (!(p->grid_uploaded && cache && cache[0] == '1')) {
-		rc = mc33cu_grid_upload_rows(p->ctx, (const void *const *const *)M->F);
-		if (rc) return rc;
+		if (!p->reg_tried) {
+			p->reg_tried = 1;
+			size_t bytes = 0;
+			const void *blk = getenv("MC33_B200_NO_PIN") ? 0 : whole_block(M, &bytes);
+			if (blk && mc33cu_host_register(blk, bytes) == MC33CU_OK) p->registered = blk;
+		}
+		for (int i = 0; i < p->nslab; i++) {
+			rc = mc33cu_grid_upload_rows_async(p->ctx[i], (const void *const *const *)M->F);
+			if (rc) return rc;
+		}
 		p->grid_uploaded = 1;
 	}
 	M->iso = iso;
-	return mc33cu_count(p->ctx, (double)iso, k);
+	for (int i = 0; i < p->nslab; i++) {
+		rc = mc33cu_count_async(p->ctx[i], (double)iso, 0);
+		if (rc) return rc;
+	}
+	memset(tot, 0, sizeof *tot);
+	for (int i = 0; i < p->nslab; i++) {
+		rc = mc33cu_sync(p->ctx[i]);
+		if (rc) return rc;
+		rc = mc33cu_get_counts(p->ctx[i], &k[i]);
+		if (rc) return rc;
+		tot->nV += k[i].nV; tot->nT += k[i].nT; tot->nShared += k[i].nShared; tot->nCentre += k[i].nCentre;
+	}
+	if (tot->nV >= 0xFFFFFFFFull || tot->nT >= 0xFFFFFFFFull) return MC33CU_ERR_RANGE;   /* unsigned int indices, h:140 */
+	return MC33CU_OK;
 }
 
 unsigned long long size_of_isosurface(MC33 *M, MC33_real iso, unsigned int *nV, unsigned int *nT)
 {
-	mc33cu_counts k;
-	if (!M || count_on_device(M, iso, &k) != MC33CU_OK) {
+	mc33cu_counts ks[MC33_MAX_SLABS], k;
+	if (!M || count_on_devices(M, iso, ks, &k) != MC33CU_OK) {
 		if (nV) *nV = 0;
 		if (nT) *nT = 0;
 		return 0;
@@ -433,9 +532,9 @@ surface *calculate_isosurface(MC33 *M, MC33_real iso)
 	mc33_private *p = (mc33_private *)M;
 	surface *S = (surface *)calloc(1, sizeof(surface));
 	if (!S) return 0;
-	mc33cu_counts k;
+	mc33cu_counts ks[MC33_MAX_SLABS], k;
 	M->memoryfault = 0;
-	int rc = count_on_device(M, iso, &k);
+	int rc = count_on_devices(M, iso, ks, &k);
 	if (rc != MC33CU_OK) goto fail;
 	if (k.nV == 0) {
 		/* empty isosurface: zero-filled struct, iso included (reference c:1880-1883) */
@@ -450,8 +549,22 @@ surface *calculate_isosurface(MC33 *M, MC33_real iso)
 	S->N = (float (*)[3])mc33_result_alloc((size_t)S->capv * 3 * sizeof(float));
 	S->color = (int *)mc33_result_alloc((size_t)S->capv * sizeof(int));
 	if (!S->T || !S->V || !S->N || !S->color) goto fail;
-	rc = mc33cu_emit_host(p->ctx, S->V, (float *)S->N, S->color, (unsigned int *)S->T, DefaultColorMC);
-	if (rc != MC33CU_OK) goto fail;
+	{
+		/* slab i's vertices are [vb, vb + nV_i) and its triangles [tb, tb + nT_i) of the result (the running nV / nT
+		 * of the reference's sweep, c:487, c:1245, across slabs); every device writes its range in place */
+		size_t vb = 0, tb = 0;
+		for (int i = 0; i < p->nslab; i++) {
+			rc = mc33cu_emit_host_async(p->ctx[i], &S->V[vb], (float *)&S->N[vb], S->color + vb, (unsigned int *)&S->T[tb],
+			                            (uint32_t)vb, (uint32_t)(vb + ks[i].nV), DefaultColorMC);
+			if (rc != MC33CU_OK) goto fail;
+			vb += ks[i].nV; tb += ks[i].nT;
+		}
+		for (int i = 0; i < p->nslab; i++) {
+			const int r2 = mc33cu_sync(p->ctx[i]);
+			if (r2 != MC33CU_OK) rc = r2;
+		}
+		if (rc != MC33CU_OK) goto fail;
+	}
 	/* the MC33 mirrors the surface head, as in the reference (c:1873) */
 	memcpy(M, S, offsetof(MC33, memoryfault));
 	return S;

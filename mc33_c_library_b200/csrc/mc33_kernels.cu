@@ -1046,8 +1046,9 @@ struct mc33cu_ctx {
 	size_t sample_size, real_size;
 	uint64_t n_samples;
 	void *grid_owned;        // device copy made by the upload calls
-	const void *up_host;     // host block of the previous contiguous upload
-	void *up_registered;     // ... page-locked by us (cudaHostRegister) from its second upload on
+	// second stream: the triangle download of mc33cu_emit_host_async runs on it next to the vertex kernel
+	cudaStream_t copy_stream; cudaEvent_t ev_cells, ev_copy; bool copy_pending;
+	uint32_t *dlT; uint64_t dlT_words;     // where the triangles go on the host (set by mc33cu_emit_host_async for one emit)
 	void *pinned; size_t pinned_bytes;   // staging for row-wise uploads
 	// k_count blocks (CNT_WARPS * G rows each) and their (V, T, C) sums
 	uint32_t *blk_sum; uint32_t nblk, cnt_gw, cnt_rb;
@@ -1131,7 +1132,9 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaFree(c->blk0);
 	cudaFree(c->vtask);
 	cudaFree(c->grid_owned);
-	if (c->up_registered) cudaHostUnregister(c->up_registered);
+	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+	if (c->ev_cells) cudaEventDestroy(c->ev_cells);
+	if (c->ev_copy) cudaEventDestroy(c->ev_copy);
 	cudaFree(c->oV); cudaFree(c->oN); cudaFree(c->oC); cudaFree(c->oT);
 	if (c->pinned) cudaFreeHost(c->pinned);
 	if (c->h_all) cudaFreeHost(c->h_all);
@@ -1333,31 +1336,23 @@ static int ensure_grid(mc33cu_ctx *c)
 	return MC33CU_OK;
 }
 
-extern "C" int mc33cu_grid_upload(mc33cu_ctx *c, const void *host)
+// Page-locking of CALLER memory is explicit (mc33cu_host_register): the upload calls never
+// register anything behind the caller's back.  A registered block is copied by DMA at link
+// speed and asynchronously; pageable memory goes through the driver's staging buffers.
+static int upload_block(mc33cu_ctx *c, const void *host, bool wait)
 {
 	if (!c || !host) return fail(MC33CU_ERR_ARG, "null argument");
 	int rc = ensure_grid(c);
 	if (rc) return rc;
+	CU(cudaSetDevice(c->device));
 	const size_t bytes = c->n_samples * c->sample_size;
-	// An iso sweep uploads the same host block again and again (the reference reads the
-	// samples at calculate time, so the drop-in may not keep them): from the second
-	// upload on, the block is page-locked so that the copy runs at PCIe speed instead of
-	// through the driver's staging buffers.  MC33_B200_NO_PIN=1 turns this off.
-	if (host == c->up_host) {
-		if (!c->up_registered && !getenv("MC33_B200_NO_PIN")) {
-			if (cudaHostRegister(const_cast<void *>(host), bytes, cudaHostRegisterDefault) == cudaSuccess)
-				c->up_registered = const_cast<void *>(host);
-			else
-				cudaGetLastError();
-		}
-	} else {
-		if (c->up_registered) { cudaHostUnregister(c->up_registered); c->up_registered = nullptr; }
-		c->up_host = host;
-	}
 	CU(cudaMemcpyAsync(c->grid_owned, host, bytes, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	if (wait) CU(cudaStreamSynchronize(c->stream));
 	return MC33CU_OK;
 }
+
+extern "C" int mc33cu_grid_upload(mc33cu_ctx *c, const void *host) { return upload_block(c, host, true); }
+extern "C" int mc33cu_grid_upload_async(mc33cu_ctx *c, const void *host) { return upload_block(c, host, false); }
 
 // ---------------------------------------------------------------------------
 // pooled page-locked host memory for result arrays (the drop-in hands them to the
@@ -1414,6 +1409,75 @@ extern "C" int mc33cu_host_free(void *p)
 	return MC33CU_OK;
 }
 
+// process-wide registry of caller blocks page-locked through mc33cu_host_register (reference counted: several
+// extractors may share one grid); cudaHostRegisterPortable makes the block DMA-able from every device
+namespace {
+struct RegBlock { const void *p; size_t bytes; int refs; };
+std::vector<RegBlock> g_reg;
+}
+
+extern "C" int mc33cu_host_register(const void *p, size_t bytes)
+{
+	if (!p || !bytes) return fail(MC33CU_ERR_ARG, "null argument");
+	std::lock_guard<std::mutex> lk(g_pool_mx);
+	for (auto &r : g_reg)
+		if (r.p == p && r.bytes == bytes) { r.refs++; return MC33CU_OK; }
+	for (auto &b : g_pool)                               // pool memory is page-locked already
+		if ((const char *)p >= (const char *)b.p && (const char *)p + bytes <= (const char *)b.p + b.cap) return MC33CU_OK;
+	cudaError_t e = cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(MC33CU_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+	}
+	g_reg.push_back({p, bytes, 1});
+	return MC33CU_OK;
+}
+
+extern "C" int mc33cu_host_unregister(const void *p)
+{
+	if (!p) return MC33CU_OK;
+	std::lock_guard<std::mutex> lk(g_pool_mx);
+	for (size_t i = 0; i < g_reg.size(); i++)
+		if (g_reg[i].p == p) {
+			if (--g_reg[i].refs == 0) {
+				if (cudaHostUnregister(const_cast<void *>(p)) != cudaSuccess) cudaGetLastError();
+				g_reg.erase(g_reg.begin() + (long)i);
+			}
+			return MC33CU_OK;
+		}
+	return MC33CU_OK;                                    // pool memory or never registered: nothing to do
+}
+
+// is the slab's part of F one contiguous block (grid_from_data_pointer layout, MC33_util_grd.c:600-612)?
+static const char *rows_contiguous(const mc33cu_ctx *c, const void *const *const *F)
+{
+	const Params &P = c->P;
+	const size_t rowb = (size_t)P.NX * c->sample_size;
+	const char *first = (const char *)F[P.zlo][0];
+	for (uint32_t z = P.zlo; z < P.zhi; z++)
+		for (uint32_t y = 0; y < P.NY; y++)
+			if ((const char *)F[z][y] != first + ((size_t)(z - P.zlo) * P.NY + y) * rowb) return nullptr;
+	return first;
+}
+
+extern "C" int mc33cu_grid_rows_block(mc33cu_ctx *c, const void *const *const *F, const void **block, size_t *bytes)
+{
+	if (!c || !F || !block || !bytes) return fail(MC33CU_ERR_ARG, "null argument");
+	*block = rows_contiguous(c, F);
+	*bytes = *block ? c->n_samples * c->sample_size : 0;
+	return MC33CU_OK;
+}
+
+// the same as mc33cu_grid_upload_rows without the final synchronisation when the rows form one block (the copy
+// is then one asynchronous DMA on the context's stream: several contexts / devices upload side by side);
+// separately allocated rows are staged and copied synchronously as in mc33cu_grid_upload_rows
+extern "C" int mc33cu_grid_upload_rows_async(mc33cu_ctx *c, const void *const *const *F)
+{
+	if (!c || !F) return fail(MC33CU_ERR_ARG, "null argument");
+	if (const char *first = rows_contiguous(c, F)) return upload_block(c, first, false);
+	return mc33cu_grid_upload_rows(c, F);
+}
+
 extern "C" int mc33cu_grid_upload_rows(mc33cu_ctx *c, const void *const *const *F)
 {
 	if (!c || !F) return fail(MC33CU_ERR_ARG, "null argument");
@@ -1422,12 +1486,7 @@ extern "C" int mc33cu_grid_upload_rows(mc33cu_ctx *c, const void *const *const *
 	const Params &P = c->P;
 	const size_t rowb = (size_t)P.NX * c->sample_size;
 	// fast path: grid_from_data_pointer layout (MC33_util_grd.c:600-612), one block
-	const char *first = (const char *)F[P.zlo][0];
-	bool contiguous = true;
-	for (uint32_t z = P.zlo; z < P.zhi && contiguous; z++)
-		for (uint32_t y = 0; y < P.NY; y++)
-			if ((const char *)F[z][y] != first + ((size_t)(z - P.zlo) * P.NY + y) * rowb) { contiguous = false; break; }
-	if (contiguous) return mc33cu_grid_upload(c, first);
+	if (const char *first = rows_contiguous(c, F)) return mc33cu_grid_upload(c, first);
 	// general path: alloc_F layout, one malloc per row (MC33_util_grd.c:147-169):
 	// gather rows into pinned chunks, copy chunk by chunk (double buffered)
 	const size_t chunk_rows = (32u << 20) / rowb ? (32u << 20) / rowb : 1;
@@ -1581,6 +1640,15 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
 		else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
 		c->launches++;
+	}
+	if (c->dlT) {
+		// mc33cu_emit_host_async: the triangles are complete; their download runs on the second stream
+		// while the vertex kernel runs on this one
+		CU(cudaEventRecord(c->ev_cells, s));
+		CU(cudaStreamWaitEvent(c->copy_stream, c->ev_cells, 0));
+		CU(cudaMemcpyAsync(c->dlT, P.T, c->dlT_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+		c->copy_pending = true;
+		c->dlT = nullptr;
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[4], s));
 	{
@@ -1964,6 +2032,7 @@ extern "C" int mc33cu_sync(mc33cu_ctx *c)
 	uint32_t flags = 0;
 	int rc = fetch_totals(c, &flags);
 	if (rc) return rc;
+	if (c->copy_pending) { CU(cudaStreamSynchronize(c->copy_stream)); c->copy_pending = false; }
 	if (flags & 1u) return fail(MC33CU_ERR_RANGE, "more than 2^32-1 vertices or triangles");
 	if (flags & 2u) return fail(MC33CU_ERR_CAPACITY, "output capacity exceeded");
 	return MC33CU_OK;
@@ -1981,7 +2050,8 @@ extern "C" int mc33cu_get_counts(mc33cu_ctx *c, mc33cu_counts *k)
 	return MC33CU_OK;
 }
 
-extern "C" int mc33cu_emit_host(mc33cu_ctx *c, void *V, float *N, int32_t *color, uint32_t *T, int32_t color_value)
+static int emit_host_impl(mc33cu_ctx *c, void *V, float *N, int32_t *color, uint32_t *T, uint32_t vbase, uint32_t vbase_next,
+                          int32_t color_value, bool wait)
 {
 	if (!c) return fail(MC33CU_ERR_ARG, "null context");
 	if (!c->counted || !((c->counted_mask >> (c->counted_set + 1)) & 1u))
@@ -1997,35 +2067,60 @@ extern "C" int mc33cu_emit_host(mc33cu_ctx *c, void *V, float *N, int32_t *color
 	if (k.nV == 0 && k.nT == 0) return MC33CU_OK;
 	if (!V || !N || !color || !T) return fail(MC33CU_ERR_ARG, "null output array");
 	if (c->ocapV < k.nV) {
+		CU(cudaStreamSynchronize(c->stream));
 		cudaFree(c->oV); cudaFree(c->oN); cudaFree(c->oC);
 		c->oV = nullptr; c->oN = nullptr; c->oC = nullptr; c->ocapV = 0;
-		CU(cudaMalloc(&c->oV, k.nV * 3 * c->real_size));
-		CU(cudaMalloc((void **)&c->oN, k.nV * 3 * sizeof(float)));
-		CU(cudaMalloc((void **)&c->oC, k.nV * sizeof(int32_t)));
-		c->ocapV = k.nV;
+		const uint64_t cap = k.nV + k.nV / 4 + 1024;      // head room: an iso sweep does not re-allocate at every step
+		CU(cudaMalloc(&c->oV, cap * 3 * c->real_size));
+		CU(cudaMalloc((void **)&c->oN, cap * 3 * sizeof(float)));
+		CU(cudaMalloc((void **)&c->oC, cap * sizeof(int32_t)));
+		c->ocapV = cap;
 	}
 	if (c->ocapT < k.nT) {
+		CU(cudaStreamSynchronize(c->stream));
 		cudaFree(c->oT);
 		c->oT = nullptr; c->ocapT = 0;
-		CU(cudaMalloc((void **)&c->oT, (k.nT ? k.nT : 1) * 3 * sizeof(uint32_t)));
-		c->ocapT = k.nT;
+		const uint64_t cap = k.nT + k.nT / 4 + 1024;
+		CU(cudaMalloc((void **)&c->oT, cap * 3 * sizeof(uint32_t)));
+		c->ocapT = cap;
+	}
+	if (!c->copy_stream) {
+		CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&c->ev_cells, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
 	}
 	mc33cu_out o;
 	memset(&o, 0, sizeof o);
 	o.V = c->oV; o.N = c->oN; o.color = c->oC; o.T = c->oT;
 	o.capV = (uint32_t)k.nV; o.capT = (uint32_t)k.nT;
+	o.vbase = vbase; o.vbase_next = vbase_next;
 	o.color_value = color_value;
 	int rc = set_out(c, &o);
 	if (rc) return rc;
+	c->dlT = T; c->dlT_words = k.nT * 3;
 	rc = dispatch_emit(c);
+	c->dlT = nullptr;
 	if (rc) return rc;
 	cudaStream_t s = c->stream;
-	CU(cudaMemcpyAsync(T, c->oT, k.nT * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	CU(cudaMemcpyAsync(V, c->oV, k.nV * 3 * c->real_size, cudaMemcpyDeviceToHost, s));
 	CU(cudaMemcpyAsync(N, c->oN, k.nV * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
 	CU(cudaMemcpyAsync(color, c->oC, k.nV * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-	CU(cudaStreamSynchronize(s));
+	if (wait) {
+		CU(cudaStreamSynchronize(s));
+		if (c->copy_pending) { CU(cudaStreamSynchronize(c->copy_stream)); c->copy_pending = false; }
+	}
 	return MC33CU_OK;
+}
+
+extern "C" int mc33cu_emit_host(mc33cu_ctx *c, void *V, float *N, int32_t *color, uint32_t *T, int32_t color_value)
+{
+	return emit_host_impl(c, V, N, color, T, 0u, 0u, color_value, true);
+}
+
+extern "C" int mc33cu_emit_host_async(mc33cu_ctx *c, void *V, float *N, int32_t *color, uint32_t *T, uint32_t vbase,
+                                      uint32_t vbase_next, int32_t color_value)
+{
+	return emit_host_impl(c, V, N, color, T, vbase, vbase_next, color_value, false);
 }
 
 extern "C" int mc33cu_enable_timing(mc33cu_ctx *c, int on)

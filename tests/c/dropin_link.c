@@ -69,7 +69,8 @@ int main(int argc, char **argv)
 		for (unsigned int j = 0; j < n; j++)
 			for (unsigned int i = 0; i < n; i++) {
 				const double dx = i - 11.5, dy = j - 11.5, dz = k - 11.5;
-				data[((size_t)k * n + j) * n + i] = (GRD_data_type)(100.0 - 8.0 * sqrt(dx * dx + dy * dy + dz * dz) + 0.5);
+				const double v = 100.0 - 8.0 * sqrt(dx * dx + dy * dy + dz * dz) + 0.5;
+				data[((size_t)k * n + j) * n + i] = (GRD_data_type)(v < 0 ? 0 : v);
 			}
 	_GRD *G = grid_from_data_pointer(n, n, n, data);
 	const MC33_real iso = 40.0f;

@@ -49,7 +49,7 @@ def test_c_program_links_and_runs_host_side(variant, tmp_path):
 def _int_sphere(n, dtype):
     k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
     r = np.sqrt((i - 11.5) ** 2 + (j - 11.5) ** 2 + (k - 11.5) ** 2)
-    return (100.0 - 8.0 * r + 0.5).astype(dtype)     # same expression as the C program (C casts truncate, as astype does)
+    return np.clip(100.0 - 8.0 * r + 0.5, 0, None).astype(dtype)     # same expression as the C program (C casts truncate, as astype does)
 
 
 @pytest.mark.gpu

@@ -608,3 +608,38 @@ def test_sync_reports_overflow_of_any_set_emitted_since_the_last_sync():
     k = ex.sync()
     assert (int(k.nV), int(k.nT)) == (want.nV, want.nT)
     ex.close()
+
+
+@pytest.mark.parametrize("variant,iso,scale,shape,nslab", [("f32", 0.0, 0, (41, 20, 128), 3), ("u8", 2.0, 4, (23, 9, 40), 2),
+                                                           ("f32", 0.05, 0, (70, 33, 65), 8), ("u16", 500.0, 1000, (19, 17, 96), 4)])
+def test_dropin_multi_slab_matches_single_slab_and_the_oracle(variant, iso, scale, shape, nslab, monkeypatch):
+    """calculate_isosurface with the grid cut into z-slabs, one context each (MC33_B200_DEVICES names a device per
+    slab; on a one-GPU box they all sit on device 0, on a multi-GPU box the same code runs one slab per GPU):
+    the mesh equals the one-slab drop-in mesh and the oracle's after canonical ordering by key-free comparison:
+    triangles in the same (sweep) order, vertex numbering by slab"""
+    a = noise_grid(0, variant, scale=scale, shape=shape)
+    want = oracle_extract(a, iso, variant)
+    monkeypatch.setenv("MC33_B200_DEVICES", "0")
+    one = dropin(variant).extract(a, iso)
+    compare_exact(want, one, nrm_atol=1e-6)
+    monkeypatch.setenv("MC33_B200_DEVICES", ",".join(["0"] * nslab))
+    lib = dropin(variant)
+    many = lib.extract(a, iso)
+    assert lib.lib.mc33_dropin_gpus_last() == nslab
+    assert (many.nV, many.nT) == (one.nV, one.nT)
+    # same triangles in the same order; the vertex numbering differs (per slab: shared vertices, then centres), so
+    # corner k of triangle j induces the id map, which must be a bijection carrying positions / normals / colours over
+    fwd = np.full(one.nV, -1, np.int64)
+    fwd[one.T.reshape(-1).astype(np.int64)] = many.T.reshape(-1).astype(np.int64)
+    used = fwd >= 0
+    assert np.array_equal(fwd[one.T.reshape(-1).astype(np.int64)], many.T.reshape(-1).astype(np.int64))
+    assert len(np.unique(fwd[used])) == used.sum()
+    assert np.array_equal(one.V[used], many.V[fwd[used]])
+    fa = np.isfinite(one.N[used])
+    assert np.array_equal(np.where(fa, one.N[used], 0), np.where(fa, many.N[fwd[used]], 0))
+    assert (many.color == -10724260).all()
+    # vertices no triangle refers to (on-iso points whose triangles were all dropped) still exist on both sides
+    assert sorted(map(tuple, np.round(one.V[~used].astype(np.float64), 5))) == \
+        sorted(map(tuple, np.round(np.delete(many.V, fwd[used], axis=0).astype(np.float64), 5)))
+    sz, nV, nT = lib.size(a, iso)
+    assert (nV, nT) == (one.nV, one.nT)
