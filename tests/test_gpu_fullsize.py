@@ -30,7 +30,7 @@ def _extractor(shape, variant, geom=None, slab=None):
     return Extractor(make_desc(shape, variant, geom, slab))
 
 
-def _device_invariants(b, k, NX, NY, check_used):
+def _device_invariants(b, k, NX, NY, check_used, max_unused=0):
     """size-independent properties of a mesh left on the device (buffers with keys)"""
     import torch
     nV, nT, nS = int(k.nV), int(k.nT), int(k.nShared)
@@ -44,7 +44,9 @@ def _device_invariants(b, k, NX, NY, check_used):
         if check_used:
             used[t.reshape(-1)] = True
     if check_used:
-        assert bool(used.all())                                       # every vertex is referenced
+        # every vertex is referenced -- except on-iso grid points whose triangles were all dropped as zero-area
+        # (marching_cubes_33.c:1235 keeps the vertex): at most one per on-iso sample
+        assert int((~used).sum()) <= max_unused
     tc = b["tcell"][:nT]
     assert bool((tc[1:] >= tc[:-1]).all())                            # sweep (cell-major) order
     vk = b["vkey"][:nV]
@@ -115,7 +117,8 @@ def test_cfg5_full_size_inclined_noise():
     b = ex.alloc(nV, nT, keys=True)
     ex.emit(b)
     ex.sync()
-    _device_invariants(b, k, 768, 768, check_used=True)
+    n_oniso = int((vol == 0.0).sum())          # a 24-bit uniform generator hits 0.0 exactly a few dozen times in 453 M samples
+    _device_invariants(b, k, 768, 768, check_used=True, max_unused=n_oniso)
     del b
     ex.close()
     torch.cuda.empty_cache()
