@@ -143,6 +143,7 @@ struct Totals {                   // written by the scan kernel
 struct Tables {
 	const uint16_t *case256, *simple256, *tri;
 	const uint8_t *pat;           // ntri | centre << 7, at pattern starts
+	const uint32_t *cinfo;        // per case index: simple256 entry (start | ntri << 12, or 0xFFFF) | winding flag m << 16
 };
 
 struct Params {
@@ -180,6 +181,8 @@ struct Params {
 	void *V; float *N; int32_t *color; uint32_t *T;
 	uint64_t *vkey, *tcell;       // optional canonical keys (tests)
 	uint64_t *vtask;              // [capV] vertex tasks left by the cell kernel for the vertex kernel
+	uint16_t *pcache;             // [Lrows][32 WP] pattern start of every COMPLEX cell (face / interior tests decided it),
+	                              // left by the count kernel so that the cell kernel does not run the tests again
 	uint32_t capV, capT;
 	uint32_t vbase, vbase_next;   // global vertex id of this / the next slab's first vertex (0 on one GPU)
 	const uint32_t *dbases;       // optional device copy {vbase, vbase_next}: overrides the two above

@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include "mc33_core.cuh"
+#include "mc33_pipeline.cuh"
 #include "../../include/mc33cu.h"
 
 using namespace mc33;
@@ -31,9 +32,11 @@ using namespace mc33;
 // ---------------------------------------------------------------------------
 #define TBL_TRI_BYTES ((MC33_NTRI_WORDS * 2 + 15) / 16 * 16)
 #define TBL_PAT_BYTES ((MC33_NTRI_WORDS + 15) / 16 * 16)
-#define TBL_BYTES (512 + 512 + TBL_TRI_BYTES + TBL_PAT_BYTES)
+#define TBL_CINFO_BYTES 1024
+#define TBL_BYTES (512 + 512 + TBL_TRI_BYTES + TBL_PAT_BYTES + TBL_CINFO_BYTES)
+#define TBL2_BYTES (TBL_TRI_BYTES + TBL_PAT_BYTES + TBL_CINFO_BYTES)     // what the round-2 cell kernel keeps in shared memory
 
-// one image: case256 | simple256 | tri | pat, copied to shared memory with 16-byte loads
+// one image: case256 | simple256 | tri | pat | cinfo, copied to shared memory with 16-byte loads
 __device__ __align__(16) unsigned char d_tables[TBL_BYTES];
 
 // the same tables read in place (kernels that only index them on cold paths)
@@ -44,6 +47,23 @@ __device__ __forceinline__ Tables global_tables()
 	tb.simple256 = tb.case256 + 256;
 	tb.tri = tb.simple256 + 256;
 	tb.pat = (const uint8_t *)tb.tri + TBL_TRI_BYTES;
+	tb.cinfo = (const uint32_t *)(tb.pat + TBL_PAT_BYTES);
+	return tb;
+}
+
+// tri | pat | cinfo in shared memory (the cell kernel of round 2 never runs the MC33 tests: no case256 / simple256)
+__device__ __forceinline__ Tables load_tables2(unsigned char *smem)
+{
+	const uint4 *src = reinterpret_cast<const uint4 *>(d_tables + 1024);
+	uint4 *dst = reinterpret_cast<uint4 *>(smem);
+	for (int i = threadIdx.x; i < TBL2_BYTES / 16; i += blockDim.x) dst[i] = src[i];
+	__syncthreads();
+	Tables tb;
+	tb.case256 = (const uint16_t *)d_tables;
+	tb.simple256 = tb.case256 + 256;
+	tb.tri = (const uint16_t *)smem;
+	tb.pat = (const uint8_t *)smem + TBL_TRI_BYTES;
+	tb.cinfo = (const uint32_t *)(smem + TBL_TRI_BYTES + TBL_PAT_BYTES);
 	return tb;
 }
 
@@ -58,6 +78,7 @@ __device__ __forceinline__ Tables load_tables(unsigned char *smem)
 	tb.simple256 = tb.case256 + 256;
 	tb.tri = tb.simple256 + 256;
 	tb.pat = (const uint8_t *)tb.tri + TBL_TRI_BYTES;
+	tb.cinfo = (const uint32_t *)(tb.pat + TBL_PAT_BYTES);
 	return tb;
 }
 
@@ -256,7 +277,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
 					zacc |= e;
 					if (lane == 0) { Sr[g] = b; Zr[g] = e; }
 				}
-				if (lane == 0 && zacc) { P.rowZ[lr] = P.zepoch; *P.anyZp = 1u; }
+				if (lane == 0 && zacc) { P.rowZ[lr] = P.zepoch; *P.anyZp = P.zepoch; }
 			}
 		}
 		__syncthreads();                                     // every warp is done with stage s
@@ -350,7 +371,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify_vec(const __grid_const
 					for (int d = LW / 2; d; d >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, d);
 					if (lane % LW == 0) Zb[o + j * NS + lane / LW] = v;
 				}
-				if (lane == 0) { P.rowZ[o / WP] = P.zepoch; *P.anyZp = 1u; }
+				if (lane == 0) { P.rowZ[o / WP] = P.zepoch; *P.anyZp = P.zepoch; }
 			} else if (lane < NW) {
 				// (every Z word is rewritten on every launch; tracking dirty units as k_classify_sweep
 				// does measured slower here: one isovalue leaves this kernel enough slack for the zeros)
@@ -512,7 +533,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) k_classify_sweep(const __gri
 				const bool hit = ((__ballot_sync(0xFFFFFFFFu, e != 0u) >> (lane & ~3u)) & 0xFu) != 0u;
 				if (hit) {
 					Zl[o] = e;
-					if (e) { ss.rowZ[(uint64_t)(lane >> 2) * Lrows + o / WP] = P.zepoch; ss.any[lane >> 2] = 1u; }
+					if (e) { ss.rowZ[(uint64_t)(lane >> 2) * Lrows + o / WP] = P.zepoch; ss.any[lane >> 2] = P.zepoch; }
 					if (!dirty && (lane & 3u) == 0) atomicOr(&Dl[gi >> 5], dbit);
 				} else if (dirty) {
 					Zl[o] = 0u;
@@ -612,7 +633,7 @@ __global__ void __launch_bounds__(256, CountMinBlocks<Sample>::value) k_count(co
 	// (the case tables are only touched by the complex-cell walk: read in place, no copy per CTA)
 	const Tables tb = global_tables();
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const bool anyz = *P.anyZp != 0;
+	const bool anyz = *P.anyZp == P.zepoch;     // (tagged with the classify epoch: never has to be cleared)
 	const uint32_t RB = CNT_WARPS * GW * P.G;       // rows per block: GW groups of G rows per warp
 	const uint32_t npass = (P.Q + 31) / 32;
 
@@ -866,7 +887,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + wid * CQ;
 	uint32_t *scr = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * CQ + wid * EM_SCR;
 	uint2 *rowt = reinterpret_cast<uint2 *>((uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (CQ + EM_SCR) + wid * EM_ROWT);
-	const bool anyz = *P.anyZp != 0;
+	const bool anyz = *P.anyZp == P.zepoch;     // (tagged with the classify epoch: never has to be cleared)
 	const uint32_t nShared = P.totals->nShared;
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
 	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
@@ -1020,6 +1041,30 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 	}
 }
 
+// ---------------------------------------------------------------------------
+// round-2 kernels: the bodies live in mc33_pipeline.cuh (shared with the CPU test harness)
+// ---------------------------------------------------------------------------
+#ifndef CNT2_MINB
+#define CNT2_MINB 3
+#endif
+template <typename Sample>
+__global__ void __launch_bounds__(256, CNT2_MINB) k_count2(const __grid_constant__ Params P, const __grid_constant__ CountArgs A)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	const DevCtx cx(smem);
+	count_body<Sample>(cx, P, global_tables(), A);
+}
+
+#define EMC2_SMEM (TBL2_BYTES + P2_EM_WARPS * P2_EM_WARP_BYTES)
+template <typename Sample, bool KEYS>
+__global__ void __launch_bounds__(256, 3) k_emit_cells2(const __grid_constant__ Params P, const __grid_constant__ EmitArgs A)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	const Tables tb = load_tables2(smem);
+	const DevCtx cx(smem);
+	emit_cells_body<Sample, KEYS>(cx, P, tb, A, smem + TBL2_BYTES + (threadIdx.x >> 5) * P2_EM_WARP_BYTES);
+}
+
 // ===========================================================================
 // host side
 // ===========================================================================
@@ -1065,7 +1110,7 @@ struct mc33cu_ctx {
 	bool timing; cudaEvent_t ev[6]; bool ev_valid;
 	uint64_t launches;
 	// resident CTAs per SM of the two emit kernels (persistent grids)
-	uint32_t emc_per_sm, emv_per_sm;
+	uint32_t emc_per_sm, emv_per_sm, emc2_per_sm;
 	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
 	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
 	// bitmaps of the single-isovalue path (P.S / P.Z / P.rowZ point here or into a sweep set)
@@ -1087,6 +1132,14 @@ struct mc33cu_ctx {
 	uint32_t *swA, *swRowB, *swBlk; uint64_t *swWpre; Totals *swTotals;
 	double sw_iso[SWEEP_MAX]; int sw_n; uint32_t sw_epoch;
 	bool sweep_ready;                      // all the sweep-set arrays are allocated
+	// round-2 pipeline (count with look-back, record-based cell kernel); MC33_B200_PIPE=1 selects the round-1 kernels
+	int pipe;
+	unsigned long long *lb0, *swLb, *lb_cur;   // look-back words [nblk][6] per state
+	uint32_t *lbt0, *swLbt, *lbt_cur;          // {ticket, finished} per state
+	uint16_t *pcache0, *swPcache;              // pattern of every complex cell, per state
+	uint32_t lb_tag;                           // 16-bit launch tag of the look-back words
+	uint32_t *export4;                         // where the next count leaves {nV, nT, nShared, nCentre} on the device (or null)
+	EmitArgs emit_shape;
 };
 
 extern "C" const char *mc33cu_last_error(void) { return g_err; }
@@ -1100,13 +1153,15 @@ extern "C" int mc33cu_device_count(void)
 
 static int upload_tables()
 {
-	static unsigned char img[TBL_BYTES];
+	alignas(16) static unsigned char img[TBL_BYTES];
 	memset(img, 0, sizeof img);
 	memcpy(img, MC33_CASE256, 512);
 	memcpy(img + 512, MC33_SIMPLE256, 512);
 	memcpy(img + 1024, MC33_TRI, sizeof(MC33_TRI));
 	unsigned char *pat = img + 1024 + TBL_TRI_BYTES;
 	for (int i = 0; i < MC33_NTRI_WORDS; i++) pat[i] = (uint8_t)(MC33_PAT_NTRI[i] | (MC33_PAT_CENTRE[i] << 7));
+	uint32_t *cinfo = (uint32_t *)(pat + TBL_PAT_BYTES);
+	for (int i = 0; i < 256; i++) cinfo[i] = (uint32_t)MC33_SIMPLE256[i] | ((uint32_t)((MC33_CASE256[i] >> 11) & 1u) << 16);
 	CU(cudaMemcpyToSymbol(d_tables, img, sizeof img));
 	return MC33CU_OK;
 }
@@ -1131,6 +1186,7 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaFree(c->rowBV0); cudaFree(c->totals0);
 	cudaFree(c->blk0);
 	cudaFree(c->vtask);
+	cudaFree(c->lb0); cudaFree(c->lbt0); cudaFree(c->pcache0); cudaFree(c->swLb); cudaFree(c->swLbt); cudaFree(c->swPcache);
 	cudaFree(c->grid_owned);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
 	if (c->ev_cells) cudaEventDestroy(c->ev_cells);
@@ -1156,6 +1212,8 @@ template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 	CU(cudaFuncSetAttribute(k_classify_vec<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	CU(cudaFuncSetAttribute(k_emit_cells<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
 	CU(cudaFuncSetAttribute(k_emit_cells<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
+	CU(cudaFuncSetAttribute(k_emit_cells2<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC2_SMEM));
+	CU(cudaFuncSetAttribute(k_emit_cells2<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC2_SMEM));
 	CU(cudaFuncSetAttribute(k_classify_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	return MC33CU_OK;
 }
@@ -1185,7 +1243,8 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	if (!c) return fail(MC33CU_ERR_NOMEM, "calloc");
 	c->d = *d;
 	c->device = device;
-	c->emc_per_sm = EMC_MINB; c->emv_per_sm = EMV_MINB;
+	c->emc_per_sm = EMC_MINB; c->emv_per_sm = EMV_MINB; c->emc2_per_sm = 3;
+	if (const char *e = getenv("MC33_B200_EMC2_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emc2_per_sm = (uint32_t)v; }
 	c->P.dbg_noz = getenv("MC33_B200_DEBUG_NOZ") ? 1u : 0u;
 	c->fine_pct = 8; c->fine_rows = 4;
 	if (const char *e = getenv("MC33_B200_FINE_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) c->fine_pct = (uint32_t)v; }
@@ -1288,6 +1347,20 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 		return fail(MC33CU_ERR_NOMEM, "cudaMalloc (Z dirty bits)");
 	}
 	P.D = c->D0; c->zmode_cur = &c->zmode0;
+	c->pipe = 2;
+	if (const char *e = getenv("MC33_B200_PIPE")) { if (atoi(e) == 1) c->pipe = 1; }
+	{
+		const size_t bmw = (size_t)P.Lrows * P.WP;
+		if (cudaMalloc((void **)&c->lb0, (size_t)c->nblk * P2_LB_WORDS * 8) != cudaSuccess ||
+		    cudaMemset(c->lb0, 0, (size_t)c->nblk * P2_LB_WORDS * 8) != cudaSuccess ||
+		    cudaMalloc((void **)&c->lbt0, 8) != cudaSuccess || cudaMemset(c->lbt0, 0, 8) != cudaSuccess ||
+		    cudaMalloc((void **)&c->pcache0, bmw * 32 * sizeof(uint16_t)) != cudaSuccess) {
+			mc33cu_destroy(c);
+			return fail(MC33CU_ERR_NOMEM, "cudaMalloc (look-back words / pattern cache)");
+		}
+		P.pcache = c->pcache0; c->lb_cur = c->lb0; c->lbt_cur = c->lbt0;
+		emit_geometry(P.Q, c->emit_shape);
+	}
 	*out = c;
 	return MC33CU_OK;
 }
@@ -1568,6 +1641,7 @@ static void select_state(mc33cu_ctx *c, int set)
 		P.A = c->A0; P.wpreV = c->wpreV0; P.rowBV = c->rowBV0; P.totals = c->totals0; c->blk_sum = c->blk0;
 		P.anyZp = &P.totals->anyZ;
 		P.zepoch = c->epoch0;
+		P.pcache = c->pcache0; c->lb_cur = c->lb0; c->lbt_cur = c->lbt0;
 	} else {
 		const size_t bm = (size_t)P.Lrows * P.WP, nr = (size_t)P.Lrows + 1;
 		P.S = c->swS + (size_t)set * bm; P.Z = c->swZ + (size_t)set * bm; P.rowZ = c->swRowZ + (size_t)set * P.Lrows;
@@ -1576,9 +1650,12 @@ static void select_state(mc33cu_ctx *c, int set)
 		P.zepoch = c->sw_epoch;
 		P.A = c->swA + (size_t)set * bm; P.wpreV = c->swWpre + (size_t)set * bm; P.rowBV = c->swRowB + (size_t)set * nr * 3;
 		P.totals = c->swTotals + set; c->blk_sum = c->swBlk + (size_t)set * c->nblk * 3;
+		P.pcache = c->swPcache + (size_t)set * bm * 32; c->lb_cur = c->swLb + (size_t)set * c->nblk * P2_LB_WORDS; c->lbt_cur = c->swLbt + 2 * set;
 	}
 	P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
 }
+
+__global__ void k_export_counts(const Totals *t, uint32_t *out4);
 
 // set < 0: classify the single-isovalue bitmaps now; set >= 0: use pre-classified sweep set
 template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
@@ -1586,8 +1663,8 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 	Params &P = c->P;
 	cudaStream_t s = c->stream;
 	select_state(c, set);
-	// re-arm the totals (overflow / on-iso flags)
-	CU(cudaMemsetAsync(P.totals, 0, sizeof(Totals), s));
+	// round-1 kernels: re-arm the totals (overflow flag) with a memset; the round-2 count kernel does it itself
+	if (c->pipe == 1) CU(cudaMemsetAsync(P.totals, 0, offsetof(Totals, anyZ), s));
 	if (c->timing) CU(cudaEventRecord(c->ev[0], s));
 	if (set < 0) {
 		int rc = next_epoch(c, &c->epoch0);
@@ -1599,18 +1676,32 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 	c->h_totals = c->h_all + (set + 1);
 	c->counted_mask |= 1u << (set + 1); c->pending_mask |= 1u << (set + 1); c->hvalid_mask &= ~(1u << (set + 1));
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
-	{
+	const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
+	if (c->pipe == 1) {
 		uint32_t grid = (uint32_t)c->n_sm * 8;
 		if (grid > c->nblk) grid = c->nblk;
 		k_count<Sample><<<grid, 256, 0, s>>>(P, c->nblk, c->cnt_gw, c->blk_sum);
 		c->launches++;
-	}
-	if (c->timing) CU(cudaEventRecord(c->ev[2], s));
-	{
-		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
+		if (c->timing) CU(cudaEventRecord(c->ev[2], s));
 		k_rowscan<<<(c->nblk + RS_BLOCKS - 1) / RS_BLOCKS, 256, 0, s>>>(P, c->nblk, c->cnt_rb, c->blk_sum, owned_end);
 		c->launches++;
+		if (c->export4) { k_export_counts<<<1, 1, 0, s>>>(P.totals, c->export4); c->launches++; }
+	} else {
+		// one kernel: counts, row bases by decoupled look-back, totals, optional export of the counts
+		if (++c->lb_tag > 0xFFFFu) {
+			// the 16-bit tag wraps: words of 65535 launches ago must not match
+			CU(cudaMemsetAsync(c->lb0, 0, (size_t)c->nblk * P2_LB_WORDS * 8, s));
+			if (c->swLb) CU(cudaMemsetAsync(c->swLb, 0, (size_t)c->nblk * P2_LB_WORDS * 8 * SWEEP_MAX, s));
+			c->lb_tag = 1;
+		}
+		CountArgs A;
+		A.nblk = c->nblk; A.GW = c->cnt_gw; A.lb = c->lb_cur; A.lb_ticket = c->lbt_cur; A.tag = c->lb_tag;
+		A.owned_end_row = owned_end; A.export4 = c->export4;
+		k_count2<Sample><<<c->nblk, 256, P2_CNT_SMEM, s>>>(P, A);
+		c->launches++;
+		if (c->timing) CU(cudaEventRecord(c->ev[2], s));
 	}
+	c->export4 = nullptr;
 	if (c->timing) CU(cudaEventRecord(c->ev[3], s));
 	CU(cudaGetLastError());
 	return MC33CU_OK;
@@ -1637,8 +1728,20 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		const uint32_t ngroups = ncoarse + (nrows - ncoarse * P.G + gfine - 1) / gfine;
 		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
-		else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
+		if (c->pipe == 1) {
+			if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
+			else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
+		} else {
+			EmitArgs A = c->emit_shape;
+			A.row_begin = rb; A.row_end = re;
+			A.ngroups = (nrows + A.Ge - 1) / A.Ge;
+			A.nunits = (A.ngroups + P2_EM_UNIT - 1) / P2_EM_UNIT;
+			uint32_t g2 = (uint32_t)c->n_sm * c->emc2_per_sm;
+			if (g2 > (A.nunits + P2_EM_WARPS - 1) / P2_EM_WARPS) g2 = (A.nunits + P2_EM_WARPS - 1) / P2_EM_WARPS;
+			if (g2 < 1) g2 = 1;
+			if (P.vkey || P.tcell) k_emit_cells2<Sample, true><<<g2, 256, EMC2_SMEM, s>>>(P, A);
+			else k_emit_cells2<Sample, false><<<g2, 256, EMC2_SMEM, s>>>(P, A);
+		}
 		c->launches++;
 	}
 	if (c->dlT) {
@@ -1798,13 +1901,9 @@ extern "C" int mc33cu_count_async(mc33cu_ctx *c, double iso, uint32_t *dev_count
 	CU(cudaSetDevice(c->device));
 	set_iso(c, iso);
 	c->ev_valid = false;
+	c->export4 = dev_counts4;
 	int rc = dispatch_count(c);
 	if (rc) return rc;
-	if (dev_counts4) {
-		k_export_counts<<<1, 1, 0, c->stream>>>(c->P.totals, dev_counts4);
-		c->launches++;
-		CU(cudaGetLastError());
-	}
 	c->counted = true;
 	return MC33CU_OK;
 }
@@ -1902,7 +2001,9 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 			{(void **)&c->swRowZ, (size_t)P.Lrows * 4 * SWEEP_MAX, true}, {(void **)&c->swAny, 4 * SWEEP_MAX, true},
 			{(void **)&c->swD, c->dwords * 4 * SWEEP_MAX, true}, {(void **)&c->swA, bm * 4 * SWEEP_MAX, true},
 			{(void **)&c->swWpre, bm * 8 * SWEEP_MAX, true}, {(void **)&c->swRowB, ((size_t)P.Lrows + 1) * 3 * 4 * SWEEP_MAX, false},
-			{(void **)&c->swTotals, sizeof(Totals) * SWEEP_MAX, true}, {(void **)&c->swBlk, (size_t)c->nblk * 3 * 4 * SWEEP_MAX, false}};
+			{(void **)&c->swTotals, sizeof(Totals) * SWEEP_MAX, true}, {(void **)&c->swBlk, (size_t)c->nblk * 3 * 4 * SWEEP_MAX, false},
+			{(void **)&c->swLb, (size_t)c->nblk * P2_LB_WORDS * 8 * SWEEP_MAX, true}, {(void **)&c->swLbt, 8 * SWEEP_MAX, true},
+			{(void **)&c->swPcache, bm * 32 * sizeof(uint16_t) * SWEEP_MAX, false}};
 		cudaError_t e = cudaSuccess;
 		for (auto &a : al) {
 			*a.p = nullptr;
@@ -1917,7 +2018,6 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 		}
 		c->sweep_ready = true;
 	}
-	CU(cudaMemsetAsync(c->swAny, 0, 4 * SWEEP_MAX, s));
 	int rc = next_epoch(c, &c->sw_epoch);
 	if (rc) return rc;
 	c->sw_n = n;
@@ -1981,13 +2081,9 @@ extern "C" int mc33cu_count_set_async(mc33cu_ctx *c, int set, uint32_t *dev_coun
 	CU(cudaSetDevice(c->device));
 	set_iso(c, c->sw_iso[set]);
 	c->ev_valid = false;
+	c->export4 = dev_counts4;
 	rc = dispatch_count(c, set);
 	if (rc) return rc;
-	if (dev_counts4) {
-		k_export_counts<<<1, 1, 0, c->stream>>>(c->P.totals, dev_counts4);
-		c->launches++;
-		CU(cudaGetLastError());
-	}
 	c->counted = true;
 	return MC33CU_OK;
 }

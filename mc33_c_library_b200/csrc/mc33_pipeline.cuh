@@ -1,0 +1,797 @@
+// mc33_pipeline.cuh -- bodies of the round-2 count and cell kernels, written against the small
+// SIMT context of mc33_simt.h so that the very same code runs as sm_100a kernels
+// (mc33_kernels.cu) and, lane by lane as fibers, in the CPU test harness (tests/hostemu).
+//
+//   count_body       K2: per (row, 32-point word) owned vertices per plane and triangles.  New in
+//                    round 2: (1) the on-iso rules are applied per WORD with masks (one cold call
+//                    per quad that has an on-iso sample in reach), never per cell; (2) the cells
+//                    that must be looked at one by one -- complex (face / interior tests) or with
+//                    an on-iso corner -- are compacted across the warp into a shared-memory queue
+//                    and drained 32 at a time, neighbouring lanes holding neighbouring cells
+//                    (coalesced corner loads, full lanes in select_pattern); the pattern each
+//                    complex cell selects is kept in P.pcache for the cell kernel; (3) the row
+//                    bases come out of a single-pass decoupled look-back over the per-CTA
+//                    aggregates (status word + inclusive prefix per block, Merrill & Garland),
+//                    which replaces the second kernel (k_rowscan) and the one-thread count
+//                    export kernels of round 1.
+//                    Replaces reference marching_cubes_33.c:1892-1940 / :1258-1724.
+//   emit_cells_body  K4: a warp stages, per point row and word of its row group, one record
+//                    {sign word, on-iso word, (plane mask, id of the plane's first vertex) x 3} in
+//                    shared memory -- computed once per word, on-iso rules included -- and every
+//                    visited cell then takes its 12 edge vertex ids from four records with 8
+//                    popcounts.  Triangles are written one lane per triangle; the owner cell of a
+//                    triangle is found by a 5-step search over the shuffled scan (no byte scatter
+//                    in shared memory).  Cells with an on-iso corner redirect edge ids to the
+//                    corner's POINT vertex and drop zero-area triangles with a keep mask, in the
+//                    same dense loops.  Replaces reference marching_cubes_33.c:780-1253.
+#pragma once
+#include "mc33_core.cuh"
+#include "mc33_simt.h"
+
+namespace mc33 {
+
+// ---------------------------------------------------------------------------
+// shared pieces
+// ---------------------------------------------------------------------------
+// any row among (y .. y+n+1) x (slices z .. z+2) of the group starting at local row lr0 with an on-iso sample?
+template <typename CX>
+SIMT_FN bool group_oniso(const CX &cx, const Params &P, bool any, uint32_t lr0, uint32_t nrows)
+{
+	if (!any) return false;
+	bool f = false;
+	const uint32_t n = nrows + 2;
+	for (uint32_t i = cx.lane(); i < 3 * n; i += 32) {
+		const uint32_t dz = i / n, dy = i - dz * n;
+		const uint64_t row = (uint64_t)lr0 + dy + (uint64_t)dz * P.NY;
+		if (row < P.Lrows) f = f || P.rowZ[row] == P.zepoch;
+	}
+	return cx.any(f);
+}
+
+// exclusive scan of a 32-bit value across the warp; *total = sum
+template <typename CX>
+SIMT_FN uint32_t warp_exscan(const CX &cx, uint32_t v, uint32_t *total)
+{
+	uint32_t iv = v;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (unsigned d = 1; d < 32; d <<= 1) {
+		const uint32_t x = cx.shfl_up(iv, d);
+		if (cx.lane() >= d) iv += x;
+	}
+	*total = cx.shfl(iv, 31);
+	return iv - v;
+}
+
+// case index and on-iso corner mask of the cell at bit b, from the sign / on-iso words of its four point rows
+// (rows 00, 10, 11, 01 = corners 0..3 at x, 4..7 at x+1; n* = the next word of the same row)
+SIMT_HD unsigned corner_bits(uint32_t s00, uint32_t n00, uint32_t s10, uint32_t n10, uint32_t s11, uint32_t n11,
+                             uint32_t s01, uint32_t n01, uint32_t b)
+{
+	const uint32_t p00 = funnel_r_clamp(s00, n00, b) & 3u, p10 = funnel_r_clamp(s10, n10, b) & 3u;
+	const uint32_t p11 = funnel_r_clamp(s11, n11, b) & 3u, p01 = funnel_r_clamp(s01, n01, b) & 3u;
+	// corner k -> bit 7-k
+	return ((p00 & 1u) << 7) | ((p10 & 1u) << 6) | ((p11 & 1u) << 5) | ((p01 & 1u) << 4) |
+	       ((p00 >> 1) << 3) | ((p10 >> 1) << 2) | ((p11 >> 1) << 1) | (p01 >> 1);
+}
+// index bits (corner k -> bit 7-k) to the zmask convention (corner k -> bit k)
+SIMT_HD unsigned index_to_zmask(unsigned i)
+{
+	unsigned z = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int k = 0; k < 8; k++) z |= ((i >> (7 - k)) & 1u) << k;
+	return z;
+}
+
+// which triangles of the pattern survive the zero-area drop (marching_cubes_33.c:1235) for on-iso corner mask zm:
+// bit j = triangle j is kept
+MC_COLD uint32_t keep_mask(const Tables &tb, unsigned start, unsigned zm)
+{
+	uint32_t keep = 0;
+	for (unsigned j = 0;; j++) {
+		const unsigned tw = tb.tri[start + j];
+		const unsigned k0 = vertex_key((tw >> 8) & 15, zm), k1 = vertex_key((tw >> 4) & 15, zm), k2 = vertex_key(tw & 15, zm);
+		if (k0 != k1 && k0 != k2 && k1 != k2) keep |= 1u << j;
+		if (!(tw >> 12)) break;
+	}
+	return keep;
+}
+
+// ---------------------------------------------------------------------------
+// K2: count
+// ---------------------------------------------------------------------------
+#define P2_CNT_WARPS 8
+#define P2_CNT_CQ 256                          // queue entries per warp
+#define P2_CNT_SMEM (3 * 1024 + 2 * 1024 + 128 + 64 + P2_CNT_WARPS * P2_CNT_CQ * 4)
+#define P2_LB_WORDS 6                          // look-back words per block
+
+struct CountArgs {
+	uint32_t nblk, GW;
+	unsigned long long *lb;       // [nblk][6]: aggregate {tag<<48 | V, T, C}, inclusive prefix {tag<<48 | V, T, C}
+	uint32_t *lb_ticket;          // [0] hands out block ids in launch order, [1] counts finished blocks; re-armed by the last to finish
+	uint32_t tag;                 // 16-bit tag of this launch (1..65535): stale words of earlier launches do not match
+	uint32_t owned_end_row;       // first row after the point rows this slab owns
+	uint32_t *export4;            // optional DEVICE {nV, nT, nShared, nCentre} for the all-gather across slabs
+};
+
+struct QuadZ { uint64_t pv[4]; uint32_t vis[4], walk[4]; uint32_t nts; };
+
+// the words of quad q of row (z,y) with an on-iso sample in reach (bit k of slow): generic rules per WORD
+template <typename Sample>
+MC_COLD QuadZ count_quad_z(const Params &P, uint32_t z, uint32_t y, uint32_t q, uint32_t slow, bool own_p, bool own_c)
+{
+	QuadZ r;
+	r.nts = 0;
+	const uint32_t pm = row_points_owned(P, z) ? 0xFFFFFFFFu : 0u;
+	for (int k = 0; k < 4; k++) {
+		r.pv[k] = 0; r.vis[k] = 0; r.walk[k] = 0;
+		const uint32_t w = 4 * q + (uint32_t)k;
+		if (!((slow >> k) & 1u) || w >= P.W) continue;
+		WordRec rec;
+		CellWords cw;
+		word_masks_generic(P, z, y, w, rec, cw);
+		if (!own_c) rec.act = 0;
+		r.vis[k] = rec.act | ((rec.X | rec.Y | rec.Z) & pm);
+		if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
+		r.pv[k] = pack_planes(rec);
+		uint32_t zcells = 0;
+		if (cw.zany) zcells = (cw.zc[0] | cw.zc[1] | cw.zc[2] | cw.zc[3] | cw.zc[4] | cw.zc[5] | cw.zc[6] | cw.zc[7]) & rec.act;
+		uint32_t cxm = 0;
+		if (rec.act & ~zcells) r.nts += count_simple_cells(cw.c, rec.act & ~zcells, cxm);
+		r.walk[k] = cxm | zcells;
+	}
+	return r;
+}
+
+// one queued cell: complex (pattern by the MC33 tests, remembered in pcache) and / or with an on-iso corner
+// (triangle count after the zero-area drop) -> ntri | centre << 16
+template <typename Sample>
+SIMT_HD uint32_t count_walk_cell(const Params &P, const Tables &tb, uint32_t lr, uint32_t x, uint32_t y, uint32_t z, bool gz)
+{
+	typedef typename Traits<Sample>::Real Real;
+	const uint32_t w = x >> 5, b = x & 31u;
+	const uint32_t i00 = lr * P.WP + w, i10 = i00 + P.WP, i01 = i00 + P.NY * P.WP, i11 = i01 + P.WP;
+	const unsigned idx = corner_bits(P.S[i00], P.S[i00 + 1], P.S[i10], P.S[i10 + 1], P.S[i11], P.S[i11 + 1], P.S[i01], P.S[i01 + 1], b);
+	unsigned zm = 0;
+	if (gz) zm = index_to_zmask(corner_bits(P.Z[i00], P.Z[i00 + 1], P.Z[i10], P.Z[i10 + 1], P.Z[i11], P.Z[i11 + 1], P.Z[i01], P.Z[i01 + 1], b));
+	const uint32_t es = tb.cinfo[idx] & 0xFFFFu;
+	unsigned start, ntri, centre = 0;
+	if (es != 0xFFFFu) {
+		start = es & 0xFFFu; ntri = es >> 12;
+	} else {
+		Real v[8];
+		unsigned m;
+		cell_values<Sample>(P, (Real)P.iso, x, y, z, v);
+		start = select_pattern<Real>(tb, idx, v, &m);
+		const unsigned pi = tb.pat[start];
+		ntri = pi & 0x7Fu; centre = pi >> 7;
+		P.pcache[(uint64_t)lr * (P.WP * 32u) + x] = (uint16_t)start;
+	}
+	if (zm) ntri = (unsigned)popc32(keep_mask(tb, start, zm));
+	return ntri | (centre << 16);
+}
+
+template <typename CX>
+SIMT_FN void block_exscan2(const CX &cx, uint64_t &a, uint64_t &b, uint64_t &ta, uint64_t &tb, uint64_t (*sw)[8])
+{
+	const unsigned lane = cx.lane(), wid = cx.warp();
+	uint64_t ia = a, ib = b;
+	for (unsigned d = 1; d < 32; d <<= 1) {
+		const uint64_t xa = cx.shfl_up(ia, d), xb = cx.shfl_up(ib, d);
+		if (lane >= d) { ia += xa; ib += xb; }
+	}
+	if (lane == 31) { sw[0][wid] = ia; sw[1][wid] = ib; }
+	cx.syncthreads();
+	uint64_t oa = 0, ob = 0, sa = 0, sb = 0;
+	for (unsigned k = 0; k < P2_CNT_WARPS; k++) {
+		const uint64_t va = sw[0][k], vb = sw[1][k];
+		if (k < wid) { oa += va; ob += vb; }
+		sa += va; sb += vb;
+	}
+	cx.syncthreads();
+	a = oa + ia - a; b = ob + ib - b;   // exclusive
+	ta = sa; tb = sb;
+}
+
+template <typename Sample, typename CX>
+SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const CountArgs &A)
+{
+	unsigned char *sm = cx.smem();
+	uint32_t (*s_row)[256] = reinterpret_cast<uint32_t (*)[256]>(sm);             // [3][256] row totals: V, T of the simple cells ([2] spare)
+	uint32_t (*s_cx)[256] = reinterpret_cast<uint32_t (*)[256]>(sm + 3072);       // [2][256] T, C of the queued cells
+	uint64_t (*s_w)[8] = reinterpret_cast<uint64_t (*)[8]>(sm + 5120);            // [2][8]
+	uint64_t *s_base = reinterpret_cast<uint64_t *>(sm + 5248);                   // [3] exclusive prefix of this block
+	uint32_t *s_blk = reinterpret_cast<uint32_t *>(sm + 5280);
+	uint32_t *queue = reinterpret_cast<uint32_t *>(sm + 5312) + cx.warp() * P2_CNT_CQ;
+	const unsigned lane = cx.lane(), wid = cx.warp(), tid = cx.tid();
+	const bool anyz = *P.anyZp != 0;
+	const uint32_t RB = P2_CNT_WARPS * A.GW * P.G;       // rows per block (<= 256)
+	const uint32_t npass = (P.Q + 31) / 32;
+
+	// block ids in launch order: a block only ever waits for blocks that already run (or ran)
+	if (tid == 0) *s_blk = cx.atomic_add(A.lb_ticket, 1u);
+	s_row[0][tid] = 0; s_row[1][tid] = 0; s_row[2][tid] = 0;
+	s_cx[0][tid] = 0; s_cx[1][tid] = 0;
+	cx.syncthreads();
+	const uint32_t blk = *s_blk;
+
+	for (uint32_t sub = 0; sub < A.GW; sub++) {
+		const uint32_t srow = (wid * A.GW + sub) * P.G;      // first row of the group within the block
+		const uint32_t row0 = blk * RB + srow;
+		if (row0 >= P.Lrows) break;                          // (warp uniform)
+		const bool gz = group_oniso(cx, P, anyz, row0, P.G);
+		uint64_t carryV = 0, carryT = 0;
+		for (uint32_t pass = 0; pass < npass; pass++) {
+			uint32_t r, q;
+			if (P.Q <= 32) { r = fastdiv(lane, P.Q, P.mQ); q = lane - r * P.Q; }
+			else { r = 0; q = pass * 32 + lane; }
+			const uint32_t lr = row0 + r;
+			const bool valid = r < P.G && q < P.Q && lr < P.Lrows;
+			uint64_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, tt = 0;
+			uint32_t wk0 = 0, wk1 = 0, wk2 = 0, wk3 = 0;
+			if (valid) {
+				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+				const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
+				const bool own_c = row_cells_owned(P, z, y);
+				if (own_p || own_c) {
+					const bool hasY = y < P.ny, hasZ = z < P.nz;
+					const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u;
+					const uint64_t i00 = (uint64_t)lr * P.WP + 4 * q;
+					const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY);
+					const Quad q01 = load_quad(P.S, i00 + dZ), q11 = load_quad(P.S, i00 + dY + dZ);
+					// words with an on-iso sample in reach take the generic rules (one cold call for the quad)
+					const uint32_t slow = gz ? quad_oniso_mask(P.Z, i00, dY, dZ) : 0u;
+					uint64_t pv[4];
+					uint32_t walk[4], vis[4];
+					uint32_t nts = 0;
+					const uint32_t pm = row_points_owned(P, z) ? 0xFFFFFFFFu : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+					for (int k = 0; k < 4; k++) {
+						walk[k] = 0; pv[k] = 0; vis[k] = 0;
+						if (!((slow >> k) & 1u)) {
+							WordRec rec;
+							uint32_t c[8];
+							quad_word(P, q00, q10, q01, q11, k, 4 * q + k, own_c && hasZ, rec, c);
+							vis[k] = rec.act | ((rec.X | rec.Y | rec.Z) & pm);
+							if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
+							pv[k] = pack_planes(rec);
+							// simple cells are counted 32 at a time; the complex ones go to the warp's queue
+							if (rec.act) nts += count_simple_cells(c, rec.act, walk[k]);
+						}
+					}
+					if (slow) {
+						const QuadZ rz = count_quad_z<Sample>(P, z, y, q, slow, own_p, own_c);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+						for (int k = 0; k < 4; k++)
+							if ((slow >> k) & 1u) { pv[k] = rz.pv[k]; vis[k] = rz.vis[k]; walk[k] = rz.walk[k]; }
+						nts += rz.nts;
+					}
+					pv0 = pv[0]; pv1 = pv[1]; pv2 = pv[2]; pv3 = pv[3];
+#if defined(__CUDA_ARCH__)
+					*reinterpret_cast<uint4 *>(P.A + i00) = make_uint4(vis[0], vis[1], vis[2], vis[3]);
+#else
+					P.A[i00] = vis[0]; P.A[i00 + 1] = vis[1]; P.A[i00 + 2] = vis[2]; P.A[i00 + 3] = vis[3];
+#endif
+					tt = nts;
+					wk0 = walk[0]; wk1 = walk[1]; wk2 = walk[2]; wk3 = walk[3];
+				}
+			}
+			// lane-local exclusive prefix over the four words, then the warp scan
+			const uint64_t e1 = pv0, e2 = e1 + pv1, e3 = e2 + pv2, tv = e3 + pv3;
+			uint64_t lv, it, iv = 0;
+			if (P.Q <= 32) {
+				// whole rows in one pass: a warp's 32 quads hold at most 4096 vertices per plane and 49152 triangles,
+				// so the four counters scan as three 32-bit words (X | Y << 16, Z, T)
+				const uint32_t a0 = fldV(tv, 0) | (fldV(tv, 1) << 16), b0 = fldV(tv, 2), c0 = (uint32_t)tt;
+				uint32_t ia = a0, ib = b0, ic = c0;
+				for (unsigned d = 1; d < 32; d <<= 1) {
+					const uint32_t xa = cx.shfl_up(ia, d), xb = cx.shfl_up(ib, d), xc = cx.shfl_up(ic, d);
+					if (lane >= d) { ia += xa; ib += xb; ic += xc; }
+				}
+				// exclusive, relative to the first quad of the lane's row
+				const int srcl = (int)(r * P.Q < 31u ? r * P.Q : 31u);
+				const uint32_t ea = ia - a0, eb = ib - b0, ec = ic - c0;
+				const uint32_t ra = ea - cx.shfl(ea, srcl), rb = eb - cx.shfl(eb, srcl);
+				const uint32_t rc0 = cx.shfl(ec, srcl);
+				lv = (uint64_t)(ra & 0xFFFFu) | ((uint64_t)(ra >> 16) << 21) | ((uint64_t)(rb & 0xFFFFu) << 42);
+				// fold the plane offsets in: Y ids follow the row's X ids, Z ids follow both
+				const int lastl = (int)(r * P.Q + P.Q - 1 < 31u ? r * P.Q + P.Q - 1 : 31u);
+				lv += plane_offsets(cx.shfl(lv + tv, lastl));
+				it = (uint64_t)(ic - rc0);                       // triangles of the row up to and including this quad
+			} else {
+				uint64_t jt = tt;
+				iv = tv;
+				for (unsigned d = 1; d < 32; d <<= 1) {
+					const uint64_t xv = cx.shfl_up(iv, d), xt = cx.shfl_up(jt, d);
+					if (lane >= d) { iv += xv; jt += xt; }
+				}
+				lv = carryV + iv - tv;                           // row-local prefix in front of this quad
+				it = jt;
+			}
+			if (valid) {
+				uint64_t *pw = P.wpreV + (uint64_t)lr * P.WP + 4 * q;
+				pw[0] = lv; pw[1] = lv + e1; pw[2] = lv + e2; pw[3] = lv + e3;
+				if (q == P.Q - 1) {
+					const uint64_t rowT = P.Q <= 32 ? it : carryT + it;
+					pw[4] = lv + tv;
+					s_row[0][srow + r] = P.Q <= 32 ? fldV(lv + tv, 2) : fldV(lv + tv, 0) + fldV(lv + tv, 1) + fldV(lv + tv, 2);
+					s_row[1][srow + r] = (uint32_t)rowT;
+				}
+			}
+			if (P.Q > 32) { carryV += cx.shfl(iv, 31); carryT += cx.shfl(it, 31); }
+
+			// ---- the cells that have to be looked at: compacted across the warp, 32 at a time ----
+			const uint32_t nw = (uint32_t)(popc32(wk0) + popc32(wk1) + popc32(wk2) + popc32(wk3));
+			uint32_t nwt;
+			const uint32_t wpos = warp_exscan(cx, nw, &nwt);
+			for (uint32_t w0 = 0; w0 < nwt; w0 += P2_CNT_CQ) {
+				if (nw && wpos < w0 + P2_CNT_CQ && wpos + nw > w0) {
+					uint32_t slot = wpos - w0;                   // (may start "negative": wraps, compared unsigned below)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+					for (int k = 0; k < 4; k++) {
+						uint32_t m = k == 0 ? wk0 : (k == 1 ? wk1 : (k == 2 ? wk2 : wk3));
+						while (m) {
+							const int b = ffs32(m);
+							m &= m - 1;
+							if (slot < P2_CNT_CQ) queue[slot] = (((4 * q + (uint32_t)k) << 5) + (uint32_t)b) | (r << 16);
+							slot++;
+						}
+					}
+				}
+				cx.syncwarp();
+				const uint32_t ncw = nwt - w0 < P2_CNT_CQ ? nwt - w0 : P2_CNT_CQ;
+				for (uint32_t j0 = 0; j0 < ncw; j0 += 32) {
+					const bool on = j0 + lane < ncw;
+					uint32_t res = 0, rr = 0;
+					if (on) {
+						const uint32_t e = queue[j0 + lane];
+						rr = e >> 16;
+						const uint32_t clr = row0 + rr, zl = fastdiv(clr, P.NY, P.mNY);
+						res = count_walk_cell<Sample>(P, tb, clr, e & 0xFFFFu, clr - zl * P.NY, zl + P.zlo, gz);
+					}
+					// per-row sums: the queue is in row order, so a round holds one or two runs of equal rows
+					uint32_t pending = cx.ballot(on);
+					while (pending) {
+						const int l0 = ffs32(pending);
+						const uint32_t r0 = cx.shfl(rr, l0);
+						const bool mine = on && rr == r0;
+						const uint32_t st = cx.reduce_add(mine ? (res & 0xFFFFu) : 0u), sc = cx.reduce_add(mine ? (res >> 16) : 0u);
+						if ((int)lane == l0) { s_cx[0][srow + r0] += st; s_cx[1][srow + r0] += sc; }
+						pending &= ~cx.ballot(mine);
+					}
+				}
+				cx.syncwarp();
+			}
+		}
+		if (P.Q > 32) {
+			// long rows: the plane totals are only known now; add the offsets in a second sweep
+			const uint64_t add = plane_offsets(carryV);
+			for (uint32_t i = lane; i <= 4 * P.Q; i += 32) P.wpreV[(uint64_t)row0 * P.WP + i] += add;
+		}
+	}
+	cx.syncthreads();
+
+	// ---- block-relative row bases, then the block's own prefix by decoupled look-back ----
+	const uint32_t t = tid;
+	uint64_t a = (uint64_t)s_row[0][t] | ((uint64_t)s_cx[1][t] << 32), b = (uint64_t)s_row[1][t] + s_cx[0][t], ta, tb2;
+	block_exscan2(cx, a, b, ta, tb2, s_w);
+	const uint64_t aggV = ta & 0xFFFFFFFFull, aggC = ta >> 32, aggT = tb2;
+	const uint64_t FIELD = 0xFFFFFFFFFFFFull;                  // 48 value bits under the 16-bit tag
+	if (wid == 0) {
+		unsigned long long *me = A.lb + (uint64_t)blk * P2_LB_WORDS;
+		const unsigned long long tagw = (unsigned long long)A.tag << 48;
+		if (lane == 0 && blk > 0) {
+			// aggregate first: successors can walk over this block while it is still looking back itself
+			me[1] = aggT; me[2] = aggC;
+			cx.st_release(&me[0], tagw | aggV);
+		}
+		uint64_t exV = 0, exT = 0, exC = 0;
+		for (int64_t base = (int64_t)blk - 1; base >= 0; base -= 32) {      // (warp uniform)
+			const int64_t j = base - (int64_t)lane;             // lane 0 looks at the nearest predecessor of the window
+			unsigned long long v0 = 0, t1 = 0, c2 = 0;
+			bool isP = false;
+			if (j >= 0) {
+				const unsigned long long *o = A.lb + (uint64_t)j * P2_LB_WORDS;
+				for (;;) {
+					const unsigned long long p0 = cx.ld_acquire(&o[3]);
+					if ((p0 >> 48) == A.tag) { v0 = p0; t1 = o[4]; c2 = o[5]; isP = true; break; }
+					const unsigned long long a0 = cx.ld_acquire(&o[0]);
+					if ((a0 >> 48) == A.tag) { v0 = a0; t1 = o[1]; c2 = o[2]; break; }
+					cx.backoff();                                // neither published yet: that block is still counting
+				}
+			}
+			// the nearest predecessor that already has an inclusive prefix ends the walk; the ones nearer than it
+			// contribute their aggregates
+			const uint32_t pmask = cx.ballot(j >= 0 && isP);
+			const int first = pmask ? ffs32(pmask) : 32;
+			const bool use = j >= 0 && (int)lane <= first;
+			uint64_t sV = use ? (v0 & FIELD) : 0, sT = use ? t1 : 0, sC = use ? c2 : 0;
+			for (unsigned d = 16; d; d >>= 1) {
+				sV += cx.shfl(sV, (int)(lane ^ d));
+				sT += cx.shfl(sT, (int)(lane ^ d));
+				sC += cx.shfl(sC, (int)(lane ^ d));
+			}
+			exV += sV; exT += sT; exC += sC;
+			if (pmask) break;
+		}
+		if (lane == 0) {
+			me[4] = exT + aggT; me[5] = exC + aggC;
+			cx.st_release(&me[3], tagw | ((exV + aggV) & FIELD));
+			s_base[0] = exV; s_base[1] = exT; s_base[2] = exC;
+		}
+	}
+	cx.syncthreads();
+	{
+		const uint64_t bV = s_base[0], bT = s_base[1], bC = s_base[2];
+		const uint32_t lr = blk * RB + t;
+		if (t < RB && lr < P.Lrows) {
+			const uint32_t v = (uint32_t)(bV + (a & 0xFFFFFFFFull));
+			P.rowBV[lr] = v; P.rowBC[lr] = (uint32_t)(bC + (a >> 32)); P.rowBT[lr] = (uint32_t)(bT + b);
+			if (lr == A.owned_end_row) P.totals->nShared = v;
+		}
+		if (blk == A.nblk - 1 && t == 0) {
+			const uint64_t tv = bV + aggV, tt = bT + aggT, tc = bC + aggC;
+			P.rowBV[P.Lrows] = (uint32_t)tv; P.rowBT[P.Lrows] = (uint32_t)tt; P.rowBC[P.Lrows] = (uint32_t)tc;
+			if (A.owned_end_row >= P.Lrows) P.totals->nShared = (uint32_t)tv;
+			P.totals->nCentre = (uint32_t)tc;
+			P.totals->nT = (uint32_t)tt;
+			P.totals->nSharedAll = (uint32_t)tv;
+			// 32-bit index range check (include/marching_cubes_33.h:140 uses unsigned int)
+			P.totals->range = (tv + tc >= 0xFFFFFFFFull || tt >= 0xFFFFFFFFull) ? 1u : 0u;
+		}
+	}
+	// the block that FINISHES last (whatever its id) re-arms the counters and exports the counts: every other
+	// block's totals are visible to it (fence + atomic on the way out)
+	cx.threadfence();
+	cx.syncthreads();
+	if (t == 0) {
+		const uint32_t done = cx.atomic_add(A.lb_ticket + 1, 1u);
+		if (done == A.nblk - 1) {
+			cx.threadfence();
+			A.lb_ticket[0] = 0; A.lb_ticket[1] = 0;
+			P.totals->overflow = 0;
+			P.totals->ticket = 0;
+			if (A.export4) {
+				const volatile Totals *tz = P.totals;
+				const uint32_t nS = tz->nShared, nC = tz->nCentre, nT = tz->nT;
+				A.export4[0] = nS + nC; A.export4[1] = nT; A.export4[2] = nS; A.export4[3] = nC;
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K4: cells -> triangles, centre vertices, vertex tasks
+// ---------------------------------------------------------------------------
+#define P2_EM_WARPS 8
+#define P2_RCAP 144                            // records per warp
+#define P2_EM_CQ 128                           // visited cells per queue window
+#define P2_GEMAX 16                            // cell rows per group
+#define P2_EM_WARP_BYTES (P2_RCAP * 32 + P2_GEMAX * 32 + P2_EM_CQ * 4 + 32 * 16 * 4)      // 7680
+#define P2_EM_UNIT 4                           // groups per ticket
+
+struct EmitArgs {
+	uint32_t row_begin, row_end;  // local rows [row_begin, row_end): cell rows + owned point rows of the slab
+	uint32_t Ge;                  // cell rows per group
+	uint32_t Ws, nseg;            // words per x-segment (multiple of 4), segments per row
+	uint32_t ngroups, nunits;
+};
+
+struct RowInfo { uint32_t o00, o10, o01, o11, y, z, flags, g0; };
+
+// group shape for rows of Q quads: as many cell rows as the record budget allows in one x-segment, or
+// one cell row in several segments when a row does not fit
+SIMT_HD void emit_geometry(uint32_t Q, EmitArgs &A)
+{
+	const uint32_t W4 = 4 * Q;
+	const uint32_t rows = P2_RCAP / (2 * (W4 + 1));              // point rows per slice that fit
+	if (rows >= 2) {
+		A.Ge = rows - 1 < P2_GEMAX ? rows - 1 : P2_GEMAX; A.Ws = W4; A.nseg = 1;
+	} else {
+		A.Ge = 1; A.Ws = ((P2_RCAP / 4 - 1) / 4) * 4; A.nseg = (W4 + A.Ws - 1) / A.Ws;
+	}
+}
+
+// position of edge id e of the cell held by `lane` in the warp's id scratch: 16 words per lane, the four
+// 16-byte chunks XOR-swizzled by the lane so that the 128-bit stores of 8 consecutive lanes hit 32 distinct banks
+SIMT_HD uint32_t scr_pos(uint32_t lane, uint32_t e) { return lane * 16u + ((((e >> 2) ^ (lane >> 1)) & 3u) << 2) + (e & 3u); }
+
+SIMT_HD uint32_t rank_id(uint64_t pair, uint32_t below) { return (uint32_t)(pair >> 32) + (uint32_t)popc32((uint32_t)pair & below); }
+
+// stage the records of one x-segment: rows lr0 .. lr0+Ge (slots 0..Ge) and the same rows one slice up (slots Ge+1 ..)
+template <typename CX>
+SIMT_FN void stage_records(const CX &cx, const Params &P, uint32_t lr0, uint32_t nr, uint32_t Ge, uint32_t w0, uint32_t nws, uint32_t Ws1,
+                           bool gz, uint32_t vb, uint32_t vbn, uint32_t *recS, uint32_t *recZ, uint64_t *recX, uint64_t *recY,
+                           uint64_t *recP)
+{
+	const uint32_t nq = nws >> 2, RS = 2 * (Ge + 1), nitems = RS * nq;
+	for (uint32_t it = cx.lane(); it < nitems; it += 32) {
+		const uint32_t rs = it / nq, qi = it - rs * nq;
+		const bool lower = rs <= Ge;
+		const uint32_t rp = lower ? rs : rs - Ge - 1;               // slot of the row (lower set) this record belongs to / sits above
+		const uint64_t lrow = (uint64_t)lr0 + rp + (lower ? 0u : P.NY);
+		const uint32_t o = rs * Ws1 + 4 * qi;
+		// Only the rows some visited cell of the group refers to are staged: the group's own rows, the row after a
+		// row with y < ny, and the rows one slice above those when the slice exists.  (Anything else could reach
+		// beyond the slices this slab holds.)
+		bool need = false;
+		uint32_t y = 0, z = 0;
+		if ((uint64_t)lr0 + rp < P.Lrows) {
+			const uint32_t lrl = lr0 + rp, zll = fastdiv(lrl, P.NY, P.mNY), yl = lrl - zll * P.NY;
+			need = rp < nr || (rp <= nr && yl != 0u);
+			y = yl; z = zll + P.zlo;
+			if (!lower) { need = need && z < P.nz && lrow < P.Lrows; z += 1; }
+		}
+		if (!need) {
+			for (int k = 0; k < 4; k++) { recS[o + k] = 0; recZ[o + k] = 0; recX[o + k] = 0; recY[o + k] = 0; recP[o + k] = 0; }
+			if (qi == nq - 1) { recS[o + 4] = 0; recZ[o + 4] = 0; }
+			continue;
+		}
+		const uint32_t w = w0 + 4 * qi;
+		const uint64_t i0 = lrow * P.WP + w;
+		const bool hasY = y < P.ny, hasZ = z < P.nz && lrow + P.NY < P.Lrows;
+		const Quad qs = load_quad(P.S, i0);
+		const Quad qy = hasY ? load_quad(P.S, i0 + P.WP) : qs;
+		const Quad qz = (lower && hasZ) ? load_quad(P.S, i0 + (uint64_t)P.NY * P.WP) : qs;
+		const uint32_t rb = P.rowBV[lrow] + (z == P.hz ? vbn : vb);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int k = 0; k < 4; k++) {
+			const uint32_t s = qs.s[k];
+			uint32_t mX = (s ^ shr1(s, qs.s[k + 1])) & mask_le(w + k, P.nx - 1), mY = s ^ qy.s[k], mZ = s ^ qz.s[k];
+			uint32_t zr = 0;
+			if (gz) {
+				zr = P.Z[i0 + k];
+				uint32_t dep = zr | (P.Z[i0 + k + 1] & 1u);
+				if (hasY) dep |= P.Z[i0 + P.WP + k];
+				if (hasZ) dep |= P.Z[i0 + (uint64_t)P.NY * P.WP + k];
+				if (dep && w + k < P.W) {
+					// an on-iso sample decides one of this word's masks: the generic rules, once per WORD
+					WordRec rec;
+					CellWords cw;
+					word_masks_generic(P, z, y, w + k, rec, cw);
+					mX = rec.X; mY = rec.Y; mZ = rec.Z;
+				}
+			}
+			const uint64_t pre = P.wpreV[i0 + k];
+			recS[o + k] = s; recZ[o + k] = zr;
+			recX[o + k] = (uint64_t)mX | ((uint64_t)(rb + fldV(pre, 0)) << 32);
+			recY[o + k] = (uint64_t)mY | ((uint64_t)(rb + fldV(pre, 1)) << 32);
+			recP[o + k] = (uint64_t)mZ | ((uint64_t)(rb + fldV(pre, 2)) << 32);
+		}
+		if (qi == nq - 1) { recS[o + 4] = qs.s[4]; recZ[o + 4] = gz ? P.Z[i0 + 4] : 0u; }
+	}
+}
+
+// the k-th (0-based) set bit of m
+SIMT_HD uint32_t nth_bit(uint32_t m, uint32_t k)
+{
+	for (uint32_t i = 0; i < k; i++) m &= m - 1;
+	return (uint32_t)ffs32(m);
+}
+
+template <typename Sample, bool KEYS, typename CX>
+SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, const EmitArgs &A, unsigned char *wsm)
+{
+	// per-warp shared memory
+	uint32_t *recS = reinterpret_cast<uint32_t *>(wsm), *recZ = recS + P2_RCAP;
+	uint64_t *recX = reinterpret_cast<uint64_t *>(wsm + P2_RCAP * 8), *recY = recX + P2_RCAP, *recP = recY + P2_RCAP;
+	RowInfo *rowi = reinterpret_cast<RowInfo *>(wsm + P2_RCAP * 32);
+	uint32_t *cq = reinterpret_cast<uint32_t *>(wsm + P2_RCAP * 32 + P2_GEMAX * 32);
+	uint32_t *scr = cq + P2_EM_CQ;
+	const unsigned lane = cx.lane();
+	const bool anyz = *P.anyZp == P.zepoch;
+	const uint32_t nShared = P.totals->nShared;
+	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
+	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
+	const uint32_t Ge = A.Ge, Ws1 = A.Ws + 1, WQ = 4 * P.Q;
+	const uint32_t nwarps = cx.nblocks() * P2_EM_WARPS;
+	const uint32_t lo_lane = (1u << lane) - 1u;
+	(void)lo_lane;
+
+	// units of P2_EM_UNIT row groups are handed out by a ticket counter (the work of a group follows the surface);
+	// every warp's first unit is its own index, the next ticket is fetched while the current unit runs
+	uint32_t unit = cx.block() * P2_EM_WARPS + cx.warp(), unext = 0;
+	for (; unit < A.nunits; unit = cx.shfl(unext, 0)) {
+		if (lane == 0) unext = nwarps + cx.atomic_add(&P.totals->ticket, 1u);
+		const uint32_t gend = (unit + 1) * P2_EM_UNIT < A.ngroups ? (unit + 1) * P2_EM_UNIT : A.ngroups;
+		for (uint32_t gi = unit * P2_EM_UNIT; gi < gend; gi++) {
+			const uint32_t lr0 = A.row_begin + gi * Ge;
+			const uint32_t lrE = lr0 + Ge < A.row_end ? lr0 + Ge : A.row_end, nr = lrE - lr0;
+			const bool gz = group_oniso(cx, P, anyz, lr0, Ge);
+			if (lane < nr) {
+				const uint32_t lr = lr0 + lane, zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+				const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? 1u : 0u;
+				RowInfo ri;
+				ri.o00 = lane * Ws1; ri.o10 = (lane + uy) * Ws1;
+				ri.o01 = uz ? (Ge + 1 + lane) * Ws1 : ri.o00; ri.o11 = uz ? (Ge + 1 + lane + uy) * Ws1 : ri.o10;
+				ri.y = y; ri.z = z;
+				ri.flags = (row_points_owned(P, z) ? 1u : 0u) | (row_cells_owned(P, z, y) ? 2u : 0u);
+				ri.g0 = z == P.hz ? vbn : vb;
+				rowi[lane] = ri;
+			}
+			const uint32_t tbase = P.rowBT[lr0], cloc0 = nShared + P.rowBC[lr0];
+			uint32_t runT = 0, runC = 0;                             // triangles / centres of the group so far
+			for (uint32_t seg = 0; seg < A.nseg; seg++) {
+				const uint32_t w0 = seg * A.Ws, nws = WQ - w0 < A.Ws ? WQ - w0 : A.Ws, nq = nws >> 2;
+				cx.syncwarp();                                       // (the previous segment's readers are done)
+				stage_records(cx, P, lr0, nr, Ge, w0, nws, Ws1, gz, vb, vbn, recS, recZ, recX, recY, recP);
+				cx.syncwarp();
+				const uint32_t nitems = nr * nq;
+				for (uint32_t p0 = 0; p0 < nitems; p0 += 32) {
+					// ---- fill: visited cells (active cells + grid points that own a vertex) in sweep order ----
+					const uint32_t it = p0 + lane;
+					uint32_t r = 0, qi = 0, act0 = 0, act1 = 0, act2 = 0, act3 = 0;
+					if (it < nitems) {
+						r = it / nq; qi = it - r * nq;
+						const uint64_t ia = (uint64_t)(lr0 + r) * P.WP + w0 + 4 * qi;
+#if defined(__CUDA_ARCH__)
+						const uint4 a = *reinterpret_cast<const uint4 *>(P.A + ia);
+						act0 = a.x; act1 = a.y; act2 = a.z; act3 = a.w;
+#else
+						act0 = P.A[ia]; act1 = P.A[ia + 1]; act2 = P.A[ia + 2]; act3 = P.A[ia + 3];
+#endif
+					}
+					const uint32_t na = (uint32_t)(popc32(act0) + popc32(act1) + popc32(act2) + popc32(act3));
+					uint32_t ncp;
+					const uint32_t pos0 = warp_exscan(cx, na, &ncp);
+					for (uint32_t cw0 = 0; cw0 < ncp; cw0 += P2_EM_CQ) {
+						if (na && pos0 < cw0 + P2_EM_CQ && pos0 + na > cw0) {
+							uint32_t slot = pos0 - cw0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+							for (int k = 0; k < 4; k++) {
+								uint32_t m = k == 0 ? act0 : (k == 1 ? act1 : (k == 2 ? act2 : act3));
+								while (m) {
+									const int b = ffs32(m);
+									m &= m - 1;
+									if (slot < P2_EM_CQ) cq[slot] = (((w0 + 4 * qi + (uint32_t)k) << 5) + (uint32_t)b) | (r << 16);
+									slot++;
+								}
+							}
+						}
+						cx.syncwarp();
+						const uint32_t ncw = ncp - cw0 < P2_EM_CQ ? ncp - cw0 : P2_EM_CQ;
+						for (uint32_t j0 = 0; j0 < ncw; j0 += 32) {
+							// ---- one lane per visited CELL ----
+							const bool on = j0 + lane < ncw;
+							uint32_t ntri = 0, centre = 0, sm = 0, keep = 0, x = 0, y = 0, z = 0;
+							if (on) {
+								const uint32_t e = cq[j0 + lane];
+								x = e & 0xFFFFu;
+								const uint32_t b = x & 31u, wl = (x >> 5) - w0, rr = e >> 16;
+								const RowInfo ri = rowi[rr];
+								y = ri.y; z = ri.z;
+								const uint32_t a00 = ri.o00 + wl, a10 = ri.o10 + wl, a01 = ri.o01 + wl, a11 = ri.o11 + wl;
+								const uint64_t X00 = recX[a00], Y00 = recY[a00], Z00 = recP[a00], X10 = recX[a10], Z10 = recP[a10];
+								const uint64_t X01 = recX[a01], Y01 = recY[a01], X11 = recX[a11];
+								const uint32_t below = (1u << b) - 1u;
+								uint32_t id[12];
+								// edges: 0:(0,1)y 1:(1,2)z 2:(3,2)y 3:(0,3)z 4:(4,5)y 5:(5,6)z 6:(7,6)y 7:(4,7)z 8..11 x
+								id[0] = rank_id(Y00, below); id[4] = id[0] + (((uint32_t)Y00 >> b) & 1u);
+								id[1] = rank_id(Z10, below); id[5] = id[1] + (((uint32_t)Z10 >> b) & 1u);
+								id[2] = rank_id(Y01, below); id[6] = id[2] + (((uint32_t)Y01 >> b) & 1u);
+								id[3] = rank_id(Z00, below); id[7] = id[3] + (((uint32_t)Z00 >> b) & 1u);
+								id[8] = rank_id(X00, below); id[9] = rank_id(X10, below);
+								id[10] = rank_id(X11, below); id[11] = rank_id(X01, below);
+								// vertex tasks of the planes the low corner point owns (ids before any on-iso redirection)
+								if (ri.flags & 1u) {
+									const uint32_t lr = lr0 + rr;
+									const bool pt = gz && ((recZ[a00] >> b) & 1u);
+									if (((uint32_t)X00 >> b) & 1u) put_vertex_task(P, id[8] - ri.g0, lr, x, 0u, pt);
+									if (((uint32_t)Y00 >> b) & 1u) put_vertex_task(P, id[0] - ri.g0, lr, x, 1u, false);
+									if (((uint32_t)Z00 >> b) & 1u) put_vertex_task(P, id[3] - ri.g0, lr, x, 2u, false);
+								}
+								const unsigned idx = corner_bits(recS[a00], recS[a00 + 1], recS[a10], recS[a10 + 1], recS[a11], recS[a11 + 1],
+								                                 recS[a01], recS[a01 + 1], b);
+								if ((ri.flags & 2u) && x < P.nx && idx != 0u && idx != 255u) {
+									const uint32_t ci = tb.cinfo[idx];
+									uint32_t start;
+									if ((ci & 0xFFFFu) != 0xFFFFu) {
+										start = ci & 0xFFFu; ntri = (ci >> 12) & 15u;
+									} else {
+										start = P.pcache[(uint64_t)(lr0 + rr) * (P.WP * 32u) + x];
+										const uint32_t pi = tb.pat[start];
+										ntri = pi & 0x7Fu; centre = pi >> 7;
+									}
+									sm = start | (((ci >> 16) & 1u) << 12);
+									if (gz) {
+										const unsigned zm = index_to_zmask(corner_bits(recZ[a00], recZ[a00 + 1], recZ[a10], recZ[a10 + 1], recZ[a11],
+										                                               recZ[a11 + 1], recZ[a01], recZ[a01 + 1], b));
+										if (zm) {
+											// on-iso corners: the edges that meet one refer to its POINT vertex (X plane of the corner's row at the
+											// corner's x), and triangles that collapse are dropped (marching_cubes_33.c:970-988, :1235)
+											uint32_t pid[8];
+											pid[0] = id[8]; pid[1] = id[9]; pid[2] = id[10]; pid[3] = id[11];
+											pid[4] = id[8] + (((uint32_t)X00 >> b) & 1u); pid[5] = id[9] + (((uint32_t)X10 >> b) & 1u);
+											pid[6] = id[10] + (((uint32_t)X11 >> b) & 1u); pid[7] = id[11] + (((uint32_t)X01 >> b) & 1u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+											for (unsigned ed = 0; ed < 12; ed++) {
+												const unsigned ea = edge_a(ed), eb = edge_b(ed);
+												if ((zm >> ea) & 1u) id[ed] = pid[ea];
+												else if ((zm >> eb) & 1u) id[ed] = pid[eb];
+											}
+											keep = keep_mask(tb, start, zm);
+											ntri = (uint32_t)popc32(keep);
+											sm |= 0x2000u;
+										}
+									}
+								}
+#if defined(__CUDA_ARCH__)
+								{
+									uint4 *d = reinterpret_cast<uint4 *>(scr + lane * 16u);
+									const uint32_t sw = (lane >> 1) & 3u;
+									d[0 ^ sw] = make_uint4(id[0], id[1], id[2], id[3]);
+									d[1 ^ sw] = make_uint4(id[4], id[5], id[6], id[7]);
+									d[2 ^ sw] = make_uint4(id[8], id[9], id[10], id[11]);
+								}
+#else
+								for (uint32_t ed = 0; ed < 12; ed++) scr[scr_pos(lane, ed)] = id[ed];
+#endif
+							}
+							// triangle / centre offsets of the round: shuffle scan in sweep order
+							uint32_t tot;
+							const uint32_t ex = warp_exscan(cx, ntri | (centre << 16), &tot);
+							const uint32_t e0 = ex & 0xFFFFu, ntot = tot & 0xFFFFu;
+							const uint32_t cl = cloc0 + runC + (ex >> 16);
+							const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
+							if (on && centre) {
+								if (cl < P.capV) {
+									emit_centre_vertex<Sample>(P, x, y, z, cl);
+									if (KEYS && P.vkey) P.vkey[cl] = cell * 4 + 3;
+								} else {
+									P.totals->overflow = 1;
+								}
+							}
+							if (on) scr[scr_pos(lane, 12)] = vb + cl;
+							cx.syncwarp();
+							// ---- one lane per TRIANGLE: consecutive lanes write consecutive triangles ----
+							for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
+								const uint32_t t = t0 + lane;
+								// owner = the last cell whose first triangle is not after t (e0 is non-decreasing over the lanes)
+								uint32_t c = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+								for (uint32_t step = 16; step; step >>= 1) {
+									const uint32_t v = cx.shfl(e0, (int)(c + step));
+									if (v <= t) c += step;
+								}
+								const uint32_t csm = cx.shfl(sm, (int)c), ce0 = cx.shfl(e0, (int)c), ckeep = cx.shfl(keep, (int)c);
+								uint64_t ccell = 0;
+								if (KEYS && P.tcell) ccell = cx.shfl(cell, (int)c);
+								if (t < ntot) {
+									uint32_t j = t - ce0;
+									if (csm & 0x2000u) j = nth_bit(ckeep, j);
+									const unsigned tw = tb.tri[(csm & 0xFFFu) + j];
+									uint32_t ti[3];
+									ti[0] = scr[scr_pos(c, (tw >> 8) & 15u)];
+									ti[1] = scr[scr_pos(c, (tw >> 4) & 15u)];
+									ti[2] = scr[scr_pos(c, tw & 15u)];
+									write_triangle<KEYS>(P, tbase + runT + t, ti, (csm >> 12) & 1u, ccell);
+								}
+							}
+							cx.syncwarp();
+							runT += ntot; runC += tot >> 16;
+						}
+					}
+				}
+			}
+		}
+	}
+}
+
+}  // namespace mc33

@@ -16,9 +16,9 @@
 
 namespace mc33 {
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------
-// device
+// device (nvcc, both passes: the members are __device__ only)
 // ---------------------------------------------------------------------------------------
 struct DevCtx {
 	unsigned char *smem_;

@@ -12,20 +12,36 @@
 #include <vector>
 
 #include "../../mc33_c_library_b200/csrc/mc33_core.cuh"
+#include "simt_emu.h"
+#include "../../mc33_c_library_b200/csrc/mc33_pipeline.cuh"
 #include "../../include/mc33cu.h"
 
 using namespace mc33;
 
+static const Tables &host_tables()
+{
+	static Tables tb;
+	static uint8_t pat[MC33_NTRI_WORDS];
+	static uint32_t cinfo[256];
+	static bool done = false;
+	if (!done) {
+		for (int i = 0; i < MC33_NTRI_WORDS; i++) pat[i] = (uint8_t)(MC33_PAT_NTRI[i] | (MC33_PAT_CENTRE[i] << 7));
+		for (int i = 0; i < 256; i++) cinfo[i] = (uint32_t)MC33_SIMPLE256[i] | ((uint32_t)((MC33_CASE256[i] >> 11) & 1u) << 16);
+		tb.case256 = MC33_CASE256; tb.simple256 = MC33_SIMPLE256; tb.tri = MC33_TRI; tb.pat = pat; tb.cinfo = cinfo;
+		done = true;
+	}
+	return tb;
+}
+
+// The real kernel bodies (mc33_pipeline.cuh) under the fiber scheduler: K2 count (queue of complex / on-iso cells,
+// decoupled look-back) and K4 cells (shared-memory records, one lane per cell / per triangle).  K1 is the plain
+// comparison loop below (the TMA ring is not emulated); K3 runs the vertex tasks one after the other.
 template <typename Sample>
 static void run(Params &P, bool emit)
 {
 	typedef typename Traits<Sample>::Real Real;
-	Tables tb;
-	static uint8_t pat[MC33_NTRI_WORDS];
-	for (int i = 0; i < MC33_NTRI_WORDS; i++) pat[i] = (uint8_t)(MC33_PAT_NTRI[i] | (MC33_PAT_CENTRE[i] << 7));
-	tb.case256 = MC33_CASE256; tb.simple256 = MC33_SIMPLE256; tb.tri = MC33_TRI; tb.pat = pat;
+	const Tables &tb = host_tables();
 	const Real iso = (Real)P.iso;
-	// K1 (the kernel takes the two bits by comparison; here as the reference does)
 	for (uint32_t lr = 0; lr < P.Lrows; lr++) {
 		const Sample *src = (const Sample *)P.data + (uint64_t)lr * P.NX;
 		bool anyz = false;
@@ -43,126 +59,36 @@ static void run(Params &P, bool emit)
 			anyz |= z != 0;
 		}
 		P.rowZ[lr] = anyz ? P.zepoch : 0u;
-		if (anyz) *P.anyZp = 1;
+		if (anyz) *P.anyZp = P.zepoch;
 	}
-	const bool gz = *P.anyZp != 0;
-	// per-word record of row (z,y): through the quad fast path when the word has no
-	// on-iso sample among the points it depends on (as the kernels do), else the generic walk
-	auto word_rec = [&](uint32_t z, uint32_t y, uint32_t w, WordRec &rec, CellWords &cw) {
-		if (gz && word_oniso(P, z, y, w)) { word_masks(P, z, y, w, true, rec, cw); return; }
-		const uint32_t lr = (z - P.zlo) * P.NY + y, q = w >> 2;
-		const bool hasY = y < P.ny, hasZ = z < P.nz;
-		const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u, i00 = (uint64_t)lr * P.WP + 4 * q;
-		const Quad q00 = load_quad(P.S, i00), q10 = load_quad(P.S, i00 + dY), q01 = load_quad(P.S, i00 + dZ),
-		           q11 = load_quad(P.S, i00 + dY + dZ);
-		quad_word(P, q00, q10, q01, q11, (int)(w & 3), w, hasY && hasZ, rec, cw.c);
-		cw.zany = 0;
-		for (int k = 0; k < 8; k++) cw.zc[k] = 0;
-	};
-	// K2 + K2b: word prefixes, row bases
+	// K2
 	{
-		uint64_t bv = 0, bc = 0, bt = 0;
-		const uint32_t owned_end = (P.pz1 - P.zlo) * P.NY;
-		for (uint32_t lr = 0; lr < P.Lrows; lr++) {
-			const uint32_t zl = lr / P.NY, y = lr - zl * P.NY, z = zl + P.zlo;
-			const bool own_p = row_points_owned(P, z) || row_points_halo(P, z);
-			const bool own_c = row_cells_owned(P, z, y);
-			uint64_t av = 0, ac = 0;
-			for (uint32_t w = 0; w < 4 * P.Q; w++) {
-				uint64_t cv = 0, cc = 0;
-				if ((own_p || own_c) && w < P.W) {
-					WordRec rec; CellWords cw;
-					word_rec(z, y, w, rec, cw);
-					if (!own_p) { rec.X = rec.Y = rec.Z = 0; }
-					if (!own_c) rec.act = 0;
-					// visit mask for the cell kernel: active cells, points owning a vertex emitted here
-					P.A[(uint64_t)lr * P.WP + w] = rec.act | (row_points_owned(P, z) ? (rec.X | rec.Y | rec.Z) : 0u);
-					cv = pack_planes(rec);
-					if (gz && word_oniso(P, z, y, w)) {
-						cc = count_cells<Sample>(P, tb, z, y, w, rec.act, cw.c, cw.zc, cw.zany);
-					} else {
-						// the kernel's merged walk over the quad: give it this word's cells only
-						uint32_t act4[4] = {0, 0, 0, 0};
-						// simple cells 32 at a time, the complex ones one by one (as k_count does)
-						uint32_t cxm = 0;
-						const uint32_t nts = rec.act ? count_simple_cells(cw.c, rec.act, cxm) : 0u;
-						act4[w & 3] = cxm;
-						const bool hasY = y < P.ny, hasZ = z < P.nz;
-						const uint64_t dY = hasY ? P.WP : 0u, dZ = hasZ ? (uint64_t)P.NY * P.WP : 0u, i00 = (uint64_t)lr * P.WP + (w & ~3u);
-						cc = count_cells_quad<Sample>(P, tb, z, y, w >> 2, act4[0], act4[1], act4[2], act4[3], i00, dY, dZ);
-						cc += nts;
-					}
-				}
-				P.wpreV[(uint64_t)lr * P.WP + w] = av;
-				av += cv; ac += cc;
-			}
-			P.wpreV[(uint64_t)lr * P.WP + 4 * P.Q] = av;
-			for (uint32_t w = 0; w <= 4 * P.Q; w++) P.wpreV[(uint64_t)lr * P.WP + w] += plane_offsets(av);
-			if (lr == owned_end) P.totals->nShared = (uint32_t)bv;
-			P.rowBV[lr] = (uint32_t)bv; P.rowBT[lr] = (uint32_t)bt; P.rowBC[lr] = (uint32_t)bc;
-			bv += fldV(av, 0) + fldV(av, 1) + fldV(av, 2); bt += ac & 0xFFFFFFFFu; bc += ac >> 32;
-		}
-		P.rowBV[P.Lrows] = (uint32_t)bv; P.rowBT[P.Lrows] = (uint32_t)bt; P.rowBC[P.Lrows] = (uint32_t)bc;
-		if (owned_end >= P.Lrows) P.totals->nShared = (uint32_t)bv;
-		P.totals->nCentre = (uint32_t)bc; P.totals->nT = (uint32_t)bt; P.totals->nSharedAll = (uint32_t)bv;
+		CountArgs A;
+		uint32_t rpw = 32;
+		A.GW = rpw / P.G ? rpw / P.G : 1;
+		const uint32_t RB = P2_CNT_WARPS * A.GW * P.G;
+		A.nblk = (P.Lrows + RB - 1) / RB;
+		std::vector<unsigned long long> lb((size_t)A.nblk * P2_LB_WORDS, 0);
+		uint32_t ticket[2] = {0, 0};
+		A.lb = lb.data(); A.lb_ticket = ticket; A.tag = 7;
+		A.owned_end_row = (P.pz1 - P.zlo) * P.NY;
+		A.export4 = nullptr;
+		mc33emu::launch(A.nblk, 256, P2_CNT_SMEM, [&](EmuCtx &cx) { count_body<Sample>(cx, P, tb, A); });
 	}
 	if (!emit) return;
-	// K4, cells: triangles (+ centre vertices) in sweep order, vertex tasks
-	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
-	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - P.totals->nShared;
-	const uint32_t zend = P.pz1 > P.cz1 ? P.pz1 : P.cz1;
-	for (uint32_t lr = (P.cz0 - P.zlo) * P.NY; lr < (zend - P.zlo) * P.NY; lr++) {
-		const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
-		const bool own_c = row_cells_owned(P, z, y), own_p = row_points_owned(P, z);
-		if (!own_c && !own_p) continue;
-		uint32_t tid = P.rowBT[lr], cl = P.totals->nShared + P.rowBC[lr];
-		for (uint32_t w = 0; w < P.W; w++) {
-			// visited: active cells and grid points that own a vertex (the mask k_count left)
-			uint32_t act = P.A[(uint64_t)lr * P.WP + w];
-			if (!act) continue;
-			const bool slow = gz && word_oniso(P, z, y, w);
-			while (act) {
-				int b = ffs32(act);
-				act &= act - 1;
-				const uint32_t x = (w << 5) + b;
-				const bool cellok = own_c && x < P.nx;
-				uint32_t ids[13];
-				unsigned zm = 0;
-				CellPattern cpat;
-				cpat.start = 0; cpat.m = 0; cpat.ntri = 0; cpat.centre = 0;
-				if (slow) {
-					cpat = cell_slow<Sample>(P, tb, x, y, z, own_p, cellok, ids, 1, zm);
-				} else {
-					unsigned own;
-					const uint32_t g0 = z == P.hz ? vbn : vb;
-					const unsigned idx = cell_fast(P, x, y, z, g0, z + 1 == P.hz ? vbn : vb, ids, own);
-					if (own_p) {
-						if (own & 1u) put_vertex_task(P, ids[8] - g0, lr, x, 0u, false);
-						if (own & 2u) put_vertex_task(P, ids[0] - g0, lr, x, 1u, false);
-						if (own & 4u) put_vertex_task(P, ids[3] - g0, lr, x, 2u, false);
-					}
-					if (cellok) cpat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
-				}
-				const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
-				if (cpat.centre) {
-					if (cl < P.capV) {
-						emit_centre_vertex<Sample>(P, x, y, z, cl);
-						if (P.vkey) P.vkey[cl] = cell * 4 + 3;
-					} else {
-						P.totals->overflow = 1;
-					}
-				}
-				if (!zm) {
-					ids[12] = vb + cl;
-					for (uint32_t j = 0; j < cpat.ntri; j++)
-						emit_triangle_fast(P, tb.tri[cpat.start + j], cpat.m, ids, 1, tid + j, cell);
-				} else {
-					cell_slow_triangles<Sample>(P, tb, x, y, z, cpat, zm, vb + cl, tid, cell);
-				}
-				tid += cpat.ntri;
-				cl += cpat.centre;
-			}
-		}
+	// K4
+	{
+		EmitArgs A;
+		const uint32_t zend = P.pz1 > P.cz1 ? P.pz1 : P.cz1;
+		A.row_begin = (P.cz0 - P.zlo) * P.NY; A.row_end = (zend - P.zlo) * P.NY;
+		emit_geometry(P.Q, A);
+		const uint32_t nrows = A.row_end - A.row_begin;
+		A.ngroups = (nrows + A.Ge - 1) / A.Ge;
+		A.nunits = (A.ngroups + P2_EM_UNIT - 1) / P2_EM_UNIT;
+		const uint32_t nblocks = 3;      // a few persistent CTAs: exercises the ticket hand-out too
+		mc33emu::launch(nblocks, 256, P2_EM_WARPS * P2_EM_WARP_BYTES, [&](EmuCtx &cx) {
+			emit_cells_body<Sample, true>(cx, P, tb, A, cx.smem() + cx.warp() * P2_EM_WARP_BYTES);
+		});
 	}
 	// K3, vertices: dense over the ids, each from the task left in its slot
 	for (uint32_t id = 0; id < P.totals->nShared && id < P.capV; id++) run_vertex_task<Sample>(P, id);
@@ -193,6 +119,8 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	std::vector<uint32_t> S((size_t)P.Lrows * P.WP, 0), Z((size_t)P.Lrows * P.WP, 0), rb(((size_t)P.Lrows + 1) * 3);
 	std::vector<uint32_t> rz(P.Lrows), A((size_t)P.Lrows * P.WP, 0);
 	P.A = A.data();
+	std::vector<uint16_t> pcache((size_t)P.Lrows * P.WP * 32, 0xFFFF);
+	P.pcache = pcache.data();
 	P.zepoch = 1;
 	std::vector<uint64_t> wv((size_t)P.Lrows * P.WP);
 	Totals tot;

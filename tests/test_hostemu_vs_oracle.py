@@ -104,3 +104,31 @@ def test_bit_parallel_triangle_count_matches_case_table():
         want_cx = int(sum(1 << b for b, i in enumerate(idx) if i not in (0, 255) and simple[i] == 0xFFFF))
         want_nt = int(sum(int(simple[i]) >> 12 for i in idx if i not in (0, 255) and simple[i] != 0xFFFF))
         assert cx.value == want_cx and nt == want_nt
+
+
+@pytest.mark.parametrize("variant,shape,iso,scale", [("f32", (3, 4, 1100), 0.0, 0), ("u8", (3, 3, 1300), 2.0, 5), ("f32", (3, 3, 2500), 0.2, 0),
+                                                      ("u8", (2, 3, 4500), 2.0, 5), ("f32", (4, 5, 129), 0.0, 0), ("u16", (5, 6, 257), 3.0, 7)])
+def test_kernel_bodies_on_long_rows(variant, shape, iso, scale):
+    """rows that the cell kernel walks in several x-segments (more than 32 words) and rows of more than 32 quads
+    (the count kernel's passes with a carry), through the real kernel bodies under the fiber scheduler"""
+    a = noise_grid(0, variant, scale=scale, shape=shape)
+    _same(oracle_extract(a, iso, variant), emu_extract(a, iso, variant))
+
+
+def test_kernel_bodies_on_ct_like_volume_with_on_iso_samples_everywhere():
+    from support import ct_grid
+    c = ct_grid(40)
+    for iso in (1500.0, 1500.5, 1234.0):
+        _same(oracle_extract(c, iso, "u16"), emu_extract(c, iso, "u16"))
+
+
+def test_kernel_bodies_plateaus_and_planted_on_iso_samples():
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 3, size=(11, 13, 67)).astype(np.uint8)
+    for iso in (0.0, 1.0, 2.0):
+        _same(oracle_extract(a, iso, "u8"), emu_extract(a, iso, "u8"))
+    g = gyroid_grid(40, periods=2).copy()
+    iso = np.float32(0.25)
+    g.reshape(-1)[rng.integers(0, g.size, size=30)] = iso
+    g[0, 0, 0] = iso; g[-1, -1, -1] = iso; g[0, 20, 39] = iso; g[39, 0, 33] = iso
+    _same(oracle_extract(g, float(iso)), emu_extract(g, float(iso)))
