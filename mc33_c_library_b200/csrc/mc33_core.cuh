@@ -137,7 +137,9 @@ struct Totals {                   // written by the scan kernel
 	uint32_t range;               // 1: more than 2^32-1 vertices or triangles
 	uint32_t anyZ;                // classify: some sample is exactly on the isovalue
 	uint32_t ticket;              // next row group of the cell kernel (dynamic distribution; the vertex kernel re-arms it)
-	uint32_t pad_[3];
+	uint32_t ticket2;             // ... of the vertex kernel (the cell kernel re-arms it)
+	uint32_t nslow_acc, nslow;    // quads with an on-iso sample in reach: accumulated by the count kernel, published by its last block
+
 };
 
 struct Tables {
@@ -855,8 +857,9 @@ MC_COLD Vtx<Real> store_spnc(const Geom &g, Vtx<Real> v)
 	return o;
 }
 
+// r[0..2] index-space position, r[3..5] = -grad F  ->  stored position Vo[3] and unit normal No[3]
 template <typename Real>
-MC_HD void store_vertex(const Params &P, const Real *r, uint32_t id)
+MC_HD void transform_vertex(const Params &P, const Real *r, Real *Vo, float *No)
 {
 	const Geom &g = P.geom;
 	Vtx<Real> v;
@@ -881,10 +884,20 @@ MC_HD void store_vertex(const Params &P, const Real *r, uint32_t id)
 	float t = rdiv(1.0f, sqrtf((float)s));
 #endif
 	if (g.normal_neg) t = -t;
+	Vo[0] = v.p0; Vo[1] = v.p1; Vo[2] = v.p2;
+	No[0] = rmul(t, (float)v.n0); No[1] = rmul(t, (float)v.n1); No[2] = rmul(t, (float)v.n2);
+}
+
+template <typename Real>
+MC_HD void store_vertex(const Params &P, const Real *r, uint32_t id)
+{
+	Real Vo[3];
+	float No[3];
+	transform_vertex<Real>(P, r, Vo, No);
 	Real *V = (Real *)P.V + 3 * (uint64_t)id;
 	float *N = P.N + 3 * (uint64_t)id;
-	V[0] = v.p0; V[1] = v.p1; V[2] = v.p2;
-	N[0] = rmul(t, (float)v.n0); N[1] = rmul(t, (float)v.n1); N[2] = rmul(t, (float)v.n2);
+	V[0] = Vo[0]; V[1] = Vo[1]; V[2] = Vo[2];
+	N[0] = No[0]; N[1] = No[1]; N[2] = No[2];
 	P.color[id] = P.color_value;
 }
 
@@ -896,7 +909,7 @@ MC_HD void store_vertex(const Params &P, const Real *r, uint32_t id)
 // does not diverge; only grid-boundary points take a separate branch.
 // ---------------------------------------------------------------------------
 template <typename Sample>
-MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, int a, uint32_t id)
+MC_HD void edge_vertex_r(const Params &P, uint32_t x, uint32_t y, uint32_t z, int a, typename Traits<Sample>::Real *r)
 {
 	typedef typename Traits<Sample>::Real Real;
 	const Real iso = (Real)P.iso;
@@ -939,24 +952,31 @@ MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z
 		}
 	}
 	const Real ga = rsub(vb, va), pa = radd((Real)qa, t);
-	Real r[6];
 	r[0] = a == 0 ? pa : (Real)x;
 	r[1] = a == 1 ? pa : (Real)y;
 	r[2] = a == 2 ? pa : (Real)z;
 	r[3] = a == 0 ? ga : (a == 1 ? g[1] : g[0]);
 	r[4] = a == 0 ? g[0] : (a == 1 ? ga : g[1]);
 	r[5] = a == 0 ? g[1] : (a == 1 ? g[0] : ga);
+}
+
+template <typename Sample>
+MC_HDN void emit_edge_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, int a, uint32_t id)
+{
+	typedef typename Traits<Sample>::Real Real;
+	Real r[6];
+	edge_vertex_r<Sample>(P, x, y, z, a, r);
 	store_vertex<Real>(P, r, id);
 }
 
 // POINT vertex: MC33_surfint (marching_cubes_33.c:628-649)
 template <typename Sample>
-MC_COLD void emit_point_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
+MC_COLD void point_vertex_r(const Params &P, uint32_t x, uint32_t y, uint32_t z, typename Traits<Sample>::Real *r)
 {
 	typedef typename Traits<Sample>::Real Real;
 	const int64_t sy = (int64_t)P.NX, sz = (int64_t)P.NX * P.NY;
 	const Sample *p = (const Sample *)P.data + ((uint64_t)(z - P.zlo) * P.NY + y) * P.NX + x;
-	Real r[6] = {(Real)x, (Real)y, (Real)z, 0, 0, 0};
+	r[0] = (Real)x; r[1] = (Real)y; r[2] = (Real)z; r[3] = 0; r[4] = 0; r[5] = 0;
 #pragma unroll
 	for (int c = 0; c < 3; c++) {
 		const int64_t sc = c == 0 ? (int64_t)1 : (c == 1 ? sy : sz);
@@ -967,6 +987,14 @@ MC_COLD void emit_point_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t
 		// 0.5f*(F - F): float product for float and integer grids, double for double
 		else r[3 + c] = (Real)rmul((Real)0.5f, rawdiff(p[-sc], p[sc]));
 	}
+}
+
+template <typename Sample>
+MC_COLD void emit_point_vertex(const Params &P, uint32_t x, uint32_t y, uint32_t z, uint32_t id)
+{
+	typedef typename Traits<Sample>::Real Real;
+	Real r[6];
+	point_vertex_r<Sample>(P, x, y, z, r);
 	store_vertex<Real>(P, r, id);
 }
 

@@ -855,16 +855,20 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
 #ifndef EMC_MINB
 #define EMC_MINB 4
 #endif
-#ifndef EMV_UNROLL
-#define EMV_UNROLL 1
-#endif
-constexpr int kEmvUnroll = EMV_UNROLL;
 #define EM_ROWT 64      // per-warp row table words: (y, z) of the group's rows (G <= 32)
 #define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR + EM_ROWT) * 4)
 
 // K3, dense: thread id computes vertex id from the task the cell kernel left in the
 // vertex's own slot of N (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
 // threads write consecutive V / N / color.
+// K3, dense: thread id computes vertex id from the task the cell kernel left in the
+// vertex's own slot (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
+// threads write consecutive V / N / color.
+// (Round 2 measured two alternatives and dropped both: 16-byte stores of four lanes' positions / normals after a
+// shuffle -- the kernel is bound by L1 wavefronts, ncu l1tex__throughput 87 %, and the twelve-byte stride touches every
+// sector three times -- ran 0.098 ms against 0.087: the warp-uniform loop it needs costs more than the stores save;
+// and a task-free form that rebuilds the plane masks per row group and stages the vertices in shared memory
+// ran 0.18 ms: the staging competes for the same L1 / shared-memory pipe.)
 template <typename Sample, bool KEYS>
 __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_constant__ Params P)
 {
@@ -873,14 +877,15 @@ __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_co
 		if (nS > P.capV) P.totals->overflow = 1;
 		P.totals->ticket = 0;                  // re-arm the cell kernel's group counter (it has finished: stream order)
 	}
-#pragma unroll kEmvUnroll
 	for (uint32_t id = blockIdx.x * 256u + threadIdx.x; id < n; id += gridDim.x * 256u) run_vertex_task<Sample, KEYS>(P, id);
 }
 
 template <typename Sample, bool KEYS>
 __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_constant__ Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups,
-                                                                uint32_t ncoarse, uint32_t gfine)
+                                                                uint32_t ncoarse, uint32_t gfine, uint32_t pick_nquads)
 {
+	// (round 2: launched next to k_emit_cells2; the count kernel's on-iso statistic decides which of the two runs)
+	if (pick_nquads && cells_pick_records(P, pick_nquads)) return;
 	extern __shared__ __align__(128) unsigned char smem[];
 	const Tables tb = load_tables(smem);
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -977,7 +982,17 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							const unsigned idx = cell_fast(P, x, y, z, g0, z + 1 == P.hz ? vbn : vb, id, own);
 #pragma unroll
 							for (int k = 0; k < 12; k++) scr[k * 32 + lane] = id[k];
-							if (cellok) pat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
+							if (cellok) {
+								if (P.pcache && tb.simple256[idx] == 0xFFFFu && idx != 0u && idx != 255u) {
+									// complex cell: the count kernel of round 2 ran the MC33 tests and kept the pattern
+									pat.start = P.pcache[(uint64_t)lr * (P.WP * 32u) + x];
+									pat.m = (tb.case256[idx] >> 11) & 1u;
+									const unsigned pi = tb.pat[pat.start];
+									pat.ntri = pi & 0x7Fu; pat.centre = pi >> 7;
+								} else {
+									pat = cell_pattern<Sample>(P, tb, x, y, z, idx, 0u);
+								}
+							}
 							if (ownp) {
 								if (own & 1u) put_vertex_task(P, id[8] - g0, lr, x, 0u, false);
 								if (own & 2u) put_vertex_task(P, id[0] - g0, lr, x, 1u, false);
@@ -1055,6 +1070,15 @@ __global__ void __launch_bounds__(256, CNT2_MINB) k_count2(const __grid_constant
 	count_body<Sample>(cx, P, global_tables(), A);
 }
 
+#define EMV2_SMEM (P2_VX_WARPS * P2_VX_WARP_BYTES)
+template <typename Sample, bool KEYS>
+__global__ void __launch_bounds__(256, 4) k_emit_vertices2(const __grid_constant__ Params P, const __grid_constant__ VertexArgs A)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	const DevCtx cx(smem);
+	emit_vertices_body<Sample, KEYS>(cx, P, A, smem + (threadIdx.x >> 5) * P2_VX_WARP_BYTES);
+}
+
 #define EMC2_SMEM (TBL2_BYTES + P2_EM_WARPS * P2_EM_WARP_BYTES)
 template <typename Sample, bool KEYS>
 __global__ void __launch_bounds__(256, 3) k_emit_cells2(const __grid_constant__ Params P, const __grid_constant__ EmitArgs A)
@@ -1110,7 +1134,9 @@ struct mc33cu_ctx {
 	bool timing; cudaEvent_t ev[6]; bool ev_valid;
 	uint64_t launches;
 	// resident CTAs per SM of the two emit kernels (persistent grids)
-	uint32_t emc_per_sm, emv_per_sm, emc2_per_sm;
+	uint32_t emc_per_sm, emv_per_sm, emc2_per_sm, emv2_per_sm;
+	int cells;                             // cell kernel: 0 both launched, the device picks by the on-iso statistic; 1 / 2 force one
+	int vtx;                               // 2: vertices straight from the bitmaps (no vertex tasks); 1: the round-1 task form
 	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
 	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
 	// bitmaps of the single-isovalue path (P.S / P.Z / P.rowZ point here or into a sweep set)
@@ -1244,6 +1270,11 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	c->d = *d;
 	c->device = device;
 	c->emc_per_sm = EMC_MINB; c->emv_per_sm = EMV_MINB; c->emc2_per_sm = 3;
+	c->emv2_per_sm = 4; c->vtx = 1;
+	if (const char *e = getenv("MC33_B200_EMV2_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emv2_per_sm = (uint32_t)v; }
+	if (const char *e = getenv("MC33_B200_VTX")) { if (atoi(e) == 2) c->vtx = 2; }
+	c->cells = 0;
+	if (const char *e = getenv("MC33_B200_CELLS")) { int v = atoi(e); if (v >= 0 && v <= 2) c->cells = v; }
 	if (const char *e = getenv("MC33_B200_EMC2_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emc2_per_sm = (uint32_t)v; }
 	c->P.dbg_noz = getenv("MC33_B200_DEBUG_NOZ") ? 1u : 0u;
 	c->fine_pct = 8; c->fine_rows = 4;
@@ -1358,7 +1389,7 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 			mc33cu_destroy(c);
 			return fail(MC33CU_ERR_NOMEM, "cudaMalloc (look-back words / pattern cache)");
 		}
-		P.pcache = c->pcache0; c->lb_cur = c->lb0; c->lbt_cur = c->lbt0;
+		P.pcache = c->pipe == 2 ? c->pcache0 : nullptr; c->lb_cur = c->lb0; c->lbt_cur = c->lbt0;
 		emit_geometry(P.Q, c->emit_shape);
 	}
 	*out = c;
@@ -1641,7 +1672,7 @@ static void select_state(mc33cu_ctx *c, int set)
 		P.A = c->A0; P.wpreV = c->wpreV0; P.rowBV = c->rowBV0; P.totals = c->totals0; c->blk_sum = c->blk0;
 		P.anyZp = &P.totals->anyZ;
 		P.zepoch = c->epoch0;
-		P.pcache = c->pcache0; c->lb_cur = c->lb0; c->lbt_cur = c->lbt0;
+		P.pcache = c->pipe == 2 ? c->pcache0 : nullptr; c->lb_cur = c->lb0; c->lbt_cur = c->lbt0;
 	} else {
 		const size_t bm = (size_t)P.Lrows * P.WP, nr = (size_t)P.Lrows + 1;
 		P.S = c->swS + (size_t)set * bm; P.Z = c->swZ + (size_t)set * bm; P.rowZ = c->swRowZ + (size_t)set * P.Lrows;
@@ -1650,7 +1681,7 @@ static void select_state(mc33cu_ctx *c, int set)
 		P.zepoch = c->sw_epoch;
 		P.A = c->swA + (size_t)set * bm; P.wpreV = c->swWpre + (size_t)set * bm; P.rowBV = c->swRowB + (size_t)set * nr * 3;
 		P.totals = c->swTotals + set; c->blk_sum = c->swBlk + (size_t)set * c->nblk * 3;
-		P.pcache = c->swPcache + (size_t)set * bm * 32; c->lb_cur = c->swLb + (size_t)set * c->nblk * P2_LB_WORDS; c->lbt_cur = c->swLbt + 2 * set;
+		P.pcache = c->pipe == 2 ? c->swPcache + (size_t)set * bm * 32 : nullptr; c->lb_cur = c->swLb + (size_t)set * c->nblk * P2_LB_WORDS; c->lbt_cur = c->swLbt + 2 * set;
 	}
 	P.rowBT = P.rowBV + (P.Lrows + 1); P.rowBC = P.rowBT + (P.Lrows + 1);
 }
@@ -1728,13 +1759,20 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		const uint32_t ngroups = ncoarse + (nrows - ncoarse * P.G + gfine - 1) / gfine;
 		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
-		if (c->pipe == 1) {
-			if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
-			else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine);
-		} else {
-			EmitArgs A = c->emit_shape;
+		const uint32_t nquads = P.Lrows * P.Q;
+		const int which = c->pipe == 1 ? 1 : c->cells;            // 1 direct kernel, 2 record kernel, 0 both (the device picks)
+		if (which != 2) {
+			const uint32_t pk = which == 0 ? nquads : 0u;
+			if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine, pk);
+			else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine, pk);
+			if (which == 0) c->launches++;
+		}
+		if (which != 1) {
+			EmitArgs A;
+			A.f = c->emit_shape.f; A.z = c->emit_shape.z;
+			A.pick = which == 0 ? 1u : 0u; A.nquads = nquads;
 			A.row_begin = rb; A.row_end = re;
-			A.ngroups = (nrows + A.Ge - 1) / A.Ge;
+			A.ngroups = (nrows + A.f.Ge - 1) / A.f.Ge;
 			A.nunits = (A.ngroups + P2_EM_UNIT - 1) / P2_EM_UNIT;
 			uint32_t g2 = (uint32_t)c->n_sm * c->emc2_per_sm;
 			if (g2 > (A.nunits + P2_EM_WARPS - 1) / P2_EM_WARPS) g2 = (A.nunits + P2_EM_WARPS - 1) / P2_EM_WARPS;
@@ -1755,9 +1793,22 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 	}
 	if (c->timing) CU(cudaEventRecord(c->ev[4], s));
 	{
-		// dense over the vertex ids (the count is only known on the device: persistent grid)
-		if (P.vkey) k_emit_vertices<Sample, true><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
-		else k_emit_vertices<Sample, false><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
+		if (c->pipe == 2 && c->vtx == 2) {
+			// shared vertices straight from the bitmaps, row group by row group
+			VertexArgs A;
+			A.row_begin = (P.pz0 - P.zlo) * P.NY; A.row_end = (P.pz1 - P.zlo) * P.NY;
+			A.Gv = vertex_group_rows(P.Q);
+			A.ngroups = (A.row_end - A.row_begin + A.Gv - 1) / A.Gv;
+			uint32_t g2 = (uint32_t)c->n_sm * c->emv2_per_sm;
+			if (g2 > (A.ngroups + P2_VX_WARPS - 1) / P2_VX_WARPS) g2 = (A.ngroups + P2_VX_WARPS - 1) / P2_VX_WARPS;
+			if (g2 < 1) g2 = 1;
+			if (P.vkey) k_emit_vertices2<Sample, true><<<g2, 256, EMV2_SMEM, s>>>(P, A);
+			else k_emit_vertices2<Sample, false><<<g2, 256, EMV2_SMEM, s>>>(P, A);
+		} else {
+			// dense over the vertex ids (the count is only known on the device: persistent grid)
+			if (P.vkey) k_emit_vertices<Sample, true><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
+			else k_emit_vertices<Sample, false><<<(uint32_t)c->n_sm * c->emv_per_sm, 256, 0, s>>>(P);
+		}
 		c->launches++;
 	}
 	if (c->timing) { CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
@@ -1818,7 +1869,8 @@ static void set_iso(mc33cu_ctx *c, double iso)
 static int set_out(mc33cu_ctx *c, const mc33cu_out *o)
 {
 	Params &P = c->P;
-	if (o->capV > c->vtask_cap) {
+	const bool need_tasks = !(c->pipe == 2 && c->vtx == 2);
+	if (need_tasks && o->capV > c->vtask_cap) {
 		// (first extraction, or a larger output than any before: not on the steady-state path)
 		CU(cudaStreamSynchronize(c->stream));
 		cudaFree(c->vtask);
@@ -1827,7 +1879,7 @@ static int set_out(mc33cu_ctx *c, const mc33cu_out *o)
 		CU(cudaMalloc((void **)&c->vtask, cap * sizeof(uint64_t)));
 		c->vtask_cap = cap;
 	}
-	P.vtask = c->vtask;
+	P.vtask = need_tasks ? c->vtask : nullptr;
 	P.V = o->V; P.N = o->N; P.color = o->color; P.T = o->T; P.vkey = o->vkey; P.tcell = o->tcell;
 	P.capV = o->capV; P.capT = o->capT;
 	P.vbase = o->vbase; P.vbase_next = o->vbase_next; P.dbases = o->dev_bases;

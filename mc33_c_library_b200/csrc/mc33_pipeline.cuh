@@ -265,6 +265,7 @@ SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const C
 						}
 					}
 					if (slow) {
+						cx.atomic_add(&P.totals->nslow_acc, 1u);          // (statistic for the choice of cell kernel; rare on float data)
 						const QuadZ rz = count_quad_z<Sample>(P, z, y, q, slow, own_p, own_c);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -329,8 +330,8 @@ SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const C
 
 			// ---- the cells that have to be looked at: compacted across the warp, 32 at a time ----
 			const uint32_t nw = (uint32_t)(popc32(wk0) + popc32(wk1) + popc32(wk2) + popc32(wk3));
-			uint32_t nwt;
-			const uint32_t wpos = warp_exscan(cx, nw, &nwt);
+			uint32_t nwt = 0, wpos = 0;
+			if (cx.any(nw != 0u)) wpos = warp_exscan(cx, nw, &nwt);      // (smooth data: most passes have nothing to walk)
 			for (uint32_t w0 = 0; w0 < nwt; w0 += P2_CNT_CQ) {
 				if (nw && wpos < w0 + P2_CNT_CQ && wpos + nw > w0) {
 					uint32_t slot = wpos - w0;                   // (may start "negative": wraps, compared unsigned below)
@@ -458,8 +459,9 @@ SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const C
 		if (done == A.nblk - 1) {
 			cx.threadfence();
 			A.lb_ticket[0] = 0; A.lb_ticket[1] = 0;
+			P.totals->nslow = cx.atomic_add(&P.totals->nslow_acc, 0u); P.totals->nslow_acc = 0;
 			P.totals->overflow = 0;
-			P.totals->ticket = 0;
+			P.totals->ticket = 0; P.totals->ticket2 = 0;
 			if (A.export4) {
 				const volatile Totals *tz = P.totals;
 				const uint32_t nS = tz->nShared, nC = tz->nCentre, nT = tz->nT;
@@ -471,105 +473,155 @@ SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const C
 
 // ---------------------------------------------------------------------------
 // K4: cells -> triangles, centre vertices, vertex tasks
+//
+// Records.  For every point row the group refers to and every word of the x-segment the warp keeps
+//   A = {sign word, id of the first X / Y / Z vertex of the word}            (16 bytes)
+// and, only when an on-iso sample is in reach of the group (gz),
+//   B = {on-iso word, X / Y / Z plane masks with the on-iso rules applied}   (16 bytes).
+// Without on-iso samples the plane masks are XORs of the sign words a cell loads anyway (X: the word
+// against itself shifted by one, Y: against the row y+1, Z: against the row z+1), so B is not needed and
+// twice as many rows fit: a group of Ge cell rows shares its 2 (Ge + 1) point rows.
 // ---------------------------------------------------------------------------
 #define P2_EM_WARPS 8
-#define P2_RCAP 144                            // records per warp
+#define P2_R16 288                             // 16-byte record slots per warp
 #define P2_EM_CQ 128                           // visited cells per queue window
 #define P2_GEMAX 16                            // cell rows per group
-#define P2_EM_WARP_BYTES (P2_RCAP * 32 + P2_GEMAX * 32 + P2_EM_CQ * 4 + 32 * 16 * 4)      // 7680
-#define P2_EM_UNIT 4                           // groups per ticket
+#define P2_SLOTS (2 * (P2_GEMAX + 1))
+#define P2_EM_WARP_BYTES (P2_R16 * 16 + P2_GEMAX * 32 + P2_SLOTS * 16 + P2_EM_CQ * 4 + 32 * 16 * 4)      // 8224
+#define P2_EM_UNIT 2                           // groups per ticket
 
+struct EmitShape { uint32_t Ge, Ws, nseg, mNQ; };   // cell rows per (sub-)group, words per x-segment (multiple of 4), segments per row
 struct EmitArgs {
+	uint32_t pick;                // 0: this kernel always runs; else it runs only if cells_pick_records() says so
+	uint32_t nquads;              // quads of the slab (for the pick)
 	uint32_t row_begin, row_end;  // local rows [row_begin, row_end): cell rows + owned point rows of the slab
-	uint32_t Ge;                  // cell rows per group
-	uint32_t Ws, nseg;            // words per x-segment (multiple of 4), segments per row
+	EmitShape f, z;               // group shape without / with on-iso samples in reach (z.Ge <= f.Ge: a group is walked in sub-groups)
 	uint32_t ngroups, nunits;
 };
 
 struct RowInfo { uint32_t o00, o10, o01, o11, y, z, flags, g0; };
+struct Rec16 { uint32_t a, b, c, d; };
 
-// group shape for rows of Q quads: as many cell rows as the record budget allows in one x-segment, or
-// one cell row in several segments when a row does not fit
+// shape for rows of Q quads with `cap` record slots: as many cell rows as fit in one x-segment, or one cell row in
+// several segments when a row does not fit
+SIMT_HD EmitShape emit_shape(uint32_t Q, uint32_t cap)
+{
+	EmitShape e;
+	const uint32_t W4 = 4 * Q;
+	const uint32_t rows = cap / (2 * (W4 + 1));                  // point rows per slice that fit
+	if (rows >= 2) {
+		e.Ge = rows - 1 < P2_GEMAX ? rows - 1 : P2_GEMAX; e.Ws = W4; e.nseg = 1;
+	} else {
+		e.Ge = 1; e.Ws = ((cap / 4 - 1) / 4) * 4; e.nseg = (W4 + e.Ws - 1) / e.Ws;
+	}
+	e.mNQ = e.Ws >= 8 ? (uint32_t)(0x100000000ull / (e.Ws >> 2)) : 0u;      // fastdiv by the quads of a full segment
+	return e;
+}
 SIMT_HD void emit_geometry(uint32_t Q, EmitArgs &A)
 {
-	const uint32_t W4 = 4 * Q;
-	const uint32_t rows = P2_RCAP / (2 * (W4 + 1));              // point rows per slice that fit
-	if (rows >= 2) {
-		A.Ge = rows - 1 < P2_GEMAX ? rows - 1 : P2_GEMAX; A.Ws = W4; A.nseg = 1;
-	} else {
-		A.Ge = 1; A.Ws = ((P2_RCAP / 4 - 1) / 4) * 4; A.nseg = (W4 + A.Ws - 1) / A.Ws;
-	}
+	A.f = emit_shape(Q, P2_R16);
+	A.z = emit_shape(Q, P2_R16 / 2);
 }
 
 // position of edge id e of the cell held by `lane` in the warp's id scratch: 16 words per lane, the four
 // 16-byte chunks XOR-swizzled by the lane so that the 128-bit stores of 8 consecutive lanes hit 32 distinct banks
 SIMT_HD uint32_t scr_pos(uint32_t lane, uint32_t e) { return lane * 16u + ((((e >> 2) ^ (lane >> 1)) & 3u) << 2) + (e & 3u); }
 
-SIMT_HD uint32_t rank_id(uint64_t pair, uint32_t below) { return (uint32_t)(pair >> 32) + (uint32_t)popc32((uint32_t)pair & below); }
+SIMT_HD uint32_t rank_of(uint32_t base, uint32_t mask, uint32_t below) { return base + (uint32_t)popc32(mask & below); }
 
-// stage the records of one x-segment: rows lr0 .. lr0+Ge (slots 0..Ge) and the same rows one slice up (slots Ge+1 ..)
+// Which point rows the (sub-)group refers to: slot rs <= Ge is row lr0 + rs, slot Ge+1+rp the row one slice above
+// row lr0 + rp.  Only the rows some visited cell refers to are staged -- the group's own rows, the row after a row
+// with y < ny, and the rows one slice above those when the slice exists; anything else could reach beyond the
+// slices this slab holds.  -> {local row or ~0, id base of the row (global ids), y, flags | z << 4}
+// flags: 1 lower set, 2 has a row y+1, 4 has a row z+1 (inside the slab)
 template <typename CX>
-SIMT_FN void stage_records(const CX &cx, const Params &P, uint32_t lr0, uint32_t nr, uint32_t Ge, uint32_t w0, uint32_t nws, uint32_t Ws1,
-                           bool gz, uint32_t vb, uint32_t vbn, uint32_t *recS, uint32_t *recZ, uint64_t *recX, uint64_t *recY,
-                           uint64_t *recP)
+SIMT_FN void stage_slots(const CX &cx, const Params &P, uint32_t lr0, uint32_t nr, uint32_t Ge, uint32_t vb, uint32_t vbn, Rec16 *slot)
+{
+	for (uint32_t rs = cx.lane(); rs < 2 * (Ge + 1); rs += 32) {
+		const bool lower = rs <= Ge;
+		const uint32_t rp = lower ? rs : rs - Ge - 1;
+		const uint64_t lrow = (uint64_t)lr0 + rp + (lower ? 0u : P.NY);
+		Rec16 si;
+		si.a = 0xFFFFFFFFu; si.b = 0; si.c = 0; si.d = 0;
+		if ((uint64_t)lr0 + rp < P.Lrows) {
+			const uint32_t lrl = lr0 + rp, zll = fastdiv(lrl, P.NY, P.mNY), y = lrl - zll * P.NY;
+			uint32_t z = zll + P.zlo;
+			bool need = rp < nr || (rp <= nr && y != 0u);
+			if (!lower) { need = need && z < P.nz && lrow < P.Lrows; z += 1; }
+			if (need) {
+				si.a = (uint32_t)lrow;
+				si.b = P.rowBV[lrow] + (z == P.hz ? vbn : vb);
+				si.c = y;
+				si.d = (lower ? 1u : 0u) | (y < P.ny ? 2u : 0u) | ((z < P.nz && lrow + P.NY < P.Lrows) ? 4u : 0u) | (z << 4);
+			}
+		}
+		slot[rs] = si;
+	}
+}
+
+// stage the records of one x-segment for the rows stage_slots named
+template <typename CX>
+SIMT_FN void stage_records(const CX &cx, const Params &P, uint32_t Ge, uint32_t w0, uint32_t nws, uint32_t Ws1, uint32_t mNQ,
+                           bool gz, const Rec16 *slot, Rec16 *recA, Rec16 *recB)
 {
 	const uint32_t nq = nws >> 2, RS = 2 * (Ge + 1), nitems = RS * nq;
 	for (uint32_t it = cx.lane(); it < nitems; it += 32) {
-		const uint32_t rs = it / nq, qi = it - rs * nq;
-		const bool lower = rs <= Ge;
-		const uint32_t rp = lower ? rs : rs - Ge - 1;               // slot of the row (lower set) this record belongs to / sits above
-		const uint64_t lrow = (uint64_t)lr0 + rp + (lower ? 0u : P.NY);
+		const uint32_t rs = fastdiv(it, nq, mNQ), qi = it - rs * nq;
 		const uint32_t o = rs * Ws1 + 4 * qi;
-		// Only the rows some visited cell of the group refers to are staged: the group's own rows, the row after a
-		// row with y < ny, and the rows one slice above those when the slice exists.  (Anything else could reach
-		// beyond the slices this slab holds.)
-		bool need = false;
-		uint32_t y = 0, z = 0;
-		if ((uint64_t)lr0 + rp < P.Lrows) {
-			const uint32_t lrl = lr0 + rp, zll = fastdiv(lrl, P.NY, P.mNY), yl = lrl - zll * P.NY;
-			need = rp < nr || (rp <= nr && yl != 0u);
-			y = yl; z = zll + P.zlo;
-			if (!lower) { need = need && z < P.nz && lrow < P.Lrows; z += 1; }
-		}
-		if (!need) {
-			for (int k = 0; k < 4; k++) { recS[o + k] = 0; recZ[o + k] = 0; recX[o + k] = 0; recY[o + k] = 0; recP[o + k] = 0; }
-			if (qi == nq - 1) { recS[o + 4] = 0; recZ[o + 4] = 0; }
+		const Rec16 si = slot[rs];
+		Rec16 zero;
+		zero.a = zero.b = zero.c = zero.d = 0;
+		if (si.a == 0xFFFFFFFFu) {
+			for (int k = 0; k < 4; k++) { recA[o + k] = zero; if (gz) recB[o + k] = zero; }
+			if (qi == nq - 1) { recA[o + 4] = zero; if (gz) recB[o + 4] = zero; }
 			continue;
 		}
 		const uint32_t w = w0 + 4 * qi;
-		const uint64_t i0 = lrow * P.WP + w;
-		const bool hasY = y < P.ny, hasZ = z < P.nz && lrow + P.NY < P.Lrows;
+		const uint64_t i0 = (uint64_t)si.a * P.WP + w;
 		const Quad qs = load_quad(P.S, i0);
-		const Quad qy = hasY ? load_quad(P.S, i0 + P.WP) : qs;
-		const Quad qz = (lower && hasZ) ? load_quad(P.S, i0 + (uint64_t)P.NY * P.WP) : qs;
-		const uint32_t rb = P.rowBV[lrow] + (z == P.hz ? vbn : vb);
+		const uint32_t rb = si.b;
+		uint64_t pre[4];
+#if defined(__CUDA_ARCH__)
+		{
+			const ulonglong2 p01 = *reinterpret_cast<const ulonglong2 *>(P.wpreV + i0), p23 = *reinterpret_cast<const ulonglong2 *>(P.wpreV + i0 + 2);
+			pre[0] = p01.x; pre[1] = p01.y; pre[2] = p23.x; pre[3] = p23.y;
+		}
+#else
+		for (int k = 0; k < 4; k++) pre[k] = P.wpreV[i0 + k];
+#endif
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
 		for (int k = 0; k < 4; k++) {
-			const uint32_t s = qs.s[k];
-			uint32_t mX = (s ^ shr1(s, qs.s[k + 1])) & mask_le(w + k, P.nx - 1), mY = s ^ qy.s[k], mZ = s ^ qz.s[k];
-			uint32_t zr = 0;
-			if (gz) {
-				zr = P.Z[i0 + k];
-				uint32_t dep = zr | (P.Z[i0 + k + 1] & 1u);
+			Rec16 ra;
+			ra.a = qs.s[k]; ra.b = rb + fldV(pre[k], 0); ra.c = rb + fldV(pre[k], 1); ra.d = rb + fldV(pre[k], 2);
+			recA[o + k] = ra;
+		}
+		if (qi == nq - 1) { Rec16 ra = zero; ra.a = qs.s[4]; recA[o + 4] = ra; }
+		if (gz) {
+			// plane masks with the on-iso rules, once per WORD (never per cell)
+			const bool lower = (si.d & 1u) != 0u, hasY = (si.d & 2u) != 0u, hasZ = (si.d & 4u) != 0u;
+			const uint32_t y = si.c, z = si.d >> 4;
+			const Quad qy = hasY ? load_quad(P.S, i0 + P.WP) : qs;
+			const Quad qz = (lower && hasZ) ? load_quad(P.S, i0 + (uint64_t)P.NY * P.WP) : qs;
+			for (int k = 0; k < 4; k++) {
+				const uint32_t sw = qs.s[k];
+				Rec16 rbk;
+				rbk.a = P.Z[i0 + k];
+				rbk.b = (sw ^ shr1(sw, qs.s[k + 1])) & mask_le(w + k, P.nx - 1); rbk.c = sw ^ qy.s[k]; rbk.d = sw ^ qz.s[k];
+				uint32_t dep = rbk.a | (P.Z[i0 + k + 1] & 1u);
 				if (hasY) dep |= P.Z[i0 + P.WP + k];
 				if (hasZ) dep |= P.Z[i0 + (uint64_t)P.NY * P.WP + k];
 				if (dep && w + k < P.W) {
-					// an on-iso sample decides one of this word's masks: the generic rules, once per WORD
 					WordRec rec;
 					CellWords cw;
 					word_masks_generic(P, z, y, w + k, rec, cw);
-					mX = rec.X; mY = rec.Y; mZ = rec.Z;
+					rbk.b = rec.X; rbk.c = rec.Y; rbk.d = rec.Z;
 				}
+				recB[o + k] = rbk;
 			}
-			const uint64_t pre = P.wpreV[i0 + k];
-			recS[o + k] = s; recZ[o + k] = zr;
-			recX[o + k] = (uint64_t)mX | ((uint64_t)(rb + fldV(pre, 0)) << 32);
-			recY[o + k] = (uint64_t)mY | ((uint64_t)(rb + fldV(pre, 1)) << 32);
-			recP[o + k] = (uint64_t)mZ | ((uint64_t)(rb + fldV(pre, 2)) << 32);
+			if (qi == nq - 1) { Rec16 rbk = zero; rbk.a = P.Z[i0 + 4]; recB[o + 4] = rbk; }
 		}
-		if (qi == nq - 1) { recS[o + 4] = qs.s[4]; recZ[o + 4] = gz ? P.Z[i0 + 4] : 0u; }
 	}
 }
 
@@ -580,24 +632,28 @@ SIMT_HD uint32_t nth_bit(uint32_t m, uint32_t k)
 	return (uint32_t)ffs32(m);
 }
 
+// Which cell kernel suits the data: the record kernel (this file) when more than about one quad in 64 has an on-iso
+// sample in reach (integer grids with an integer isovalue), the direct kernel of round 1 otherwise.
+SIMT_HD bool cells_pick_records(const Params &P, uint32_t nquads) { return (uint64_t)P.totals->nslow * 64u > nquads; }
+
 template <typename Sample, bool KEYS, typename CX>
 SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, const EmitArgs &A, unsigned char *wsm)
 {
+	if (A.pick && !cells_pick_records(P, A.nquads)) return;
 	// per-warp shared memory
-	uint32_t *recS = reinterpret_cast<uint32_t *>(wsm), *recZ = recS + P2_RCAP;
-	uint64_t *recX = reinterpret_cast<uint64_t *>(wsm + P2_RCAP * 8), *recY = recX + P2_RCAP, *recP = recY + P2_RCAP;
-	RowInfo *rowi = reinterpret_cast<RowInfo *>(wsm + P2_RCAP * 32);
-	uint32_t *cq = reinterpret_cast<uint32_t *>(wsm + P2_RCAP * 32 + P2_GEMAX * 32);
+	Rec16 *recA = reinterpret_cast<Rec16 *>(wsm), *recB = recA + P2_R16 / 2;
+	RowInfo *rowi = reinterpret_cast<RowInfo *>(wsm + P2_R16 * 16);
+	Rec16 *slot = reinterpret_cast<Rec16 *>(wsm + P2_R16 * 16 + P2_GEMAX * 32);      // per staged point row: {row, id base, y, flags | z << 4}
+	uint32_t *cq = reinterpret_cast<uint32_t *>(wsm + P2_R16 * 16 + P2_GEMAX * 32 + P2_SLOTS * 16);
 	uint32_t *scr = cq + P2_EM_CQ;
 	const unsigned lane = cx.lane();
 	const bool anyz = *P.anyZp == P.zepoch;
 	const uint32_t nShared = P.totals->nShared;
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
 	const uint32_t vbn = (P.dbases ? P.dbases[1] : P.vbase_next) - nShared;   // halo slice: ids of the next slab
-	const uint32_t Ge = A.Ge, Ws1 = A.Ws + 1, WQ = 4 * P.Q;
+	const uint32_t WQ = 4 * P.Q;
 	const uint32_t nwarps = cx.nblocks() * P2_EM_WARPS;
-	const uint32_t lo_lane = (1u << lane) - 1u;
-	(void)lo_lane;
+	if (cx.block() == 0 && cx.tid() == 0) P.totals->ticket2 = 0;     // re-arm the vertex kernel's counter (it is not running: stream order)
 
 	// units of P2_EM_UNIT row groups are handed out by a ticket counter (the work of a group follows the surface);
 	// every warp's first unit is its own index, the next ticket is fetched while the current unit runs
@@ -606,116 +662,135 @@ SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, co
 		if (lane == 0) unext = nwarps + cx.atomic_add(&P.totals->ticket, 1u);
 		const uint32_t gend = (unit + 1) * P2_EM_UNIT < A.ngroups ? (unit + 1) * P2_EM_UNIT : A.ngroups;
 		for (uint32_t gi = unit * P2_EM_UNIT; gi < gend; gi++) {
-			const uint32_t lr0 = A.row_begin + gi * Ge;
-			const uint32_t lrE = lr0 + Ge < A.row_end ? lr0 + Ge : A.row_end, nr = lrE - lr0;
-			const bool gz = group_oniso(cx, P, anyz, lr0, Ge);
-			if (lane < nr) {
-				const uint32_t lr = lr0 + lane, zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
-				const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? 1u : 0u;
-				RowInfo ri;
-				ri.o00 = lane * Ws1; ri.o10 = (lane + uy) * Ws1;
-				ri.o01 = uz ? (Ge + 1 + lane) * Ws1 : ri.o00; ri.o11 = uz ? (Ge + 1 + lane + uy) * Ws1 : ri.o10;
-				ri.y = y; ri.z = z;
-				ri.flags = (row_points_owned(P, z) ? 1u : 0u) | (row_cells_owned(P, z, y) ? 2u : 0u);
-				ri.g0 = z == P.hz ? vbn : vb;
-				rowi[lane] = ri;
-			}
-			const uint32_t tbase = P.rowBT[lr0], cloc0 = nShared + P.rowBC[lr0];
-			uint32_t runT = 0, runC = 0;                             // triangles / centres of the group so far
-			for (uint32_t seg = 0; seg < A.nseg; seg++) {
-				const uint32_t w0 = seg * A.Ws, nws = WQ - w0 < A.Ws ? WQ - w0 : A.Ws, nq = nws >> 2;
-				cx.syncwarp();                                       // (the previous segment's readers are done)
-				stage_records(cx, P, lr0, nr, Ge, w0, nws, Ws1, gz, vb, vbn, recS, recZ, recX, recY, recP);
+			const uint32_t glr0 = A.row_begin + gi * A.f.Ge;
+			const uint32_t glrE = glr0 + A.f.Ge < A.row_end ? glr0 + A.f.Ge : A.row_end;
+			// a group near an on-iso sample is walked in smaller sub-groups with the two-record layout
+			const bool gz = group_oniso(cx, P, anyz, glr0, A.f.Ge);
+			const EmitShape sh = gz ? A.z : A.f;
+			const uint32_t Ge = sh.Ge, Ws1 = sh.Ws + 1;
+			for (uint32_t lr0 = glr0; lr0 < glrE; lr0 += Ge) {
+				const uint32_t lrE = lr0 + Ge < glrE ? lr0 + Ge : glrE, nr = lrE - lr0;
 				cx.syncwarp();
-				const uint32_t nitems = nr * nq;
-				for (uint32_t p0 = 0; p0 < nitems; p0 += 32) {
-					// ---- fill: visited cells (active cells + grid points that own a vertex) in sweep order ----
-					const uint32_t it = p0 + lane;
-					uint32_t r = 0, qi = 0, act0 = 0, act1 = 0, act2 = 0, act3 = 0;
-					if (it < nitems) {
-						r = it / nq; qi = it - r * nq;
-						const uint64_t ia = (uint64_t)(lr0 + r) * P.WP + w0 + 4 * qi;
+				if (lane < nr) {
+					const uint32_t lr = lr0 + lane, zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+					const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? 1u : 0u;
+					RowInfo ri;
+					ri.o00 = lane * Ws1; ri.o10 = (lane + uy) * Ws1;
+					ri.o01 = uz ? (Ge + 1 + lane) * Ws1 : ri.o00; ri.o11 = uz ? (Ge + 1 + lane + uy) * Ws1 : ri.o10;
+					ri.y = y; ri.z = z;
+					ri.flags = (row_points_owned(P, z) ? 1u : 0u) | (row_cells_owned(P, z, y) ? 2u : 0u);
+					ri.g0 = z == P.hz ? vbn : vb;
+					rowi[lane] = ri;
+				}
+				stage_slots(cx, P, lr0, nr, Ge, vb, vbn, slot);
+				const uint32_t tbase = P.rowBT[lr0], cloc0 = nShared + P.rowBC[lr0];
+				uint32_t runT = 0, runC = 0;                             // triangles / centres of the sub-group so far
+				for (uint32_t seg = 0; seg < sh.nseg; seg++) {
+					const uint32_t w0 = seg * sh.Ws, nws = WQ - w0 < sh.Ws ? WQ - w0 : sh.Ws, nq = nws >> 2;
+					cx.syncwarp();                                       // (the previous segment's readers are done)
+					stage_records(cx, P, Ge, w0, nws, Ws1, nq == (sh.Ws >> 2) ? sh.mNQ : (nq >= 2 ? (uint32_t)(0x100000000ull / nq) : 0u), gz, slot, recA, recB);
+					cx.syncwarp();
+					const uint32_t nitems = nr * nq;
+					const uint32_t mNQs = nq == (sh.Ws >> 2) ? sh.mNQ : (nq >= 2 ? (uint32_t)(0x100000000ull / nq) : 0u);
+					for (uint32_t p0 = 0; p0 < nitems; p0 += 32) {
+						// ---- fill: visited cells (active cells + grid points that own a vertex) in sweep order ----
+						const uint32_t it = p0 + lane;
+						uint32_t r = 0, qi = 0, act0 = 0, act1 = 0, act2 = 0, act3 = 0;
+						if (it < nitems) {
+							r = fastdiv(it, nq, mNQs); qi = it - r * nq;
+							const uint64_t ia = (uint64_t)(lr0 + r) * P.WP + w0 + 4 * qi;
 #if defined(__CUDA_ARCH__)
-						const uint4 a = *reinterpret_cast<const uint4 *>(P.A + ia);
-						act0 = a.x; act1 = a.y; act2 = a.z; act3 = a.w;
+							const uint4 a = *reinterpret_cast<const uint4 *>(P.A + ia);
+							act0 = a.x; act1 = a.y; act2 = a.z; act3 = a.w;
 #else
-						act0 = P.A[ia]; act1 = P.A[ia + 1]; act2 = P.A[ia + 2]; act3 = P.A[ia + 3];
+							act0 = P.A[ia]; act1 = P.A[ia + 1]; act2 = P.A[ia + 2]; act3 = P.A[ia + 3];
 #endif
-					}
-					const uint32_t na = (uint32_t)(popc32(act0) + popc32(act1) + popc32(act2) + popc32(act3));
-					uint32_t ncp;
-					const uint32_t pos0 = warp_exscan(cx, na, &ncp);
-					for (uint32_t cw0 = 0; cw0 < ncp; cw0 += P2_EM_CQ) {
-						if (na && pos0 < cw0 + P2_EM_CQ && pos0 + na > cw0) {
-							uint32_t slot = pos0 - cw0;
+						}
+						const uint32_t na = (uint32_t)(popc32(act0) + popc32(act1) + popc32(act2) + popc32(act3));
+						uint32_t ncp;
+						const uint32_t pos0 = warp_exscan(cx, na, &ncp);
+						for (uint32_t cw0 = 0; cw0 < ncp; cw0 += P2_EM_CQ) {
+							if (na && pos0 < cw0 + P2_EM_CQ && pos0 + na > cw0) {
+								uint32_t slot = pos0 - cw0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-							for (int k = 0; k < 4; k++) {
-								uint32_t m = k == 0 ? act0 : (k == 1 ? act1 : (k == 2 ? act2 : act3));
-								while (m) {
-									const int b = ffs32(m);
-									m &= m - 1;
-									if (slot < P2_EM_CQ) cq[slot] = (((w0 + 4 * qi + (uint32_t)k) << 5) + (uint32_t)b) | (r << 16);
-									slot++;
+								for (int k = 0; k < 4; k++) {
+									uint32_t m = k == 0 ? act0 : (k == 1 ? act1 : (k == 2 ? act2 : act3));
+									while (m) {
+										const int b = ffs32(m);
+										m &= m - 1;
+										if (slot < P2_EM_CQ) cq[slot] = (((w0 + 4 * qi + (uint32_t)k) << 5) + (uint32_t)b) | (r << 16);
+										slot++;
+									}
 								}
 							}
-						}
-						cx.syncwarp();
-						const uint32_t ncw = ncp - cw0 < P2_EM_CQ ? ncp - cw0 : P2_EM_CQ;
-						for (uint32_t j0 = 0; j0 < ncw; j0 += 32) {
-							// ---- one lane per visited CELL ----
-							const bool on = j0 + lane < ncw;
-							uint32_t ntri = 0, centre = 0, sm = 0, keep = 0, x = 0, y = 0, z = 0;
-							if (on) {
-								const uint32_t e = cq[j0 + lane];
-								x = e & 0xFFFFu;
-								const uint32_t b = x & 31u, wl = (x >> 5) - w0, rr = e >> 16;
-								const RowInfo ri = rowi[rr];
-								y = ri.y; z = ri.z;
-								const uint32_t a00 = ri.o00 + wl, a10 = ri.o10 + wl, a01 = ri.o01 + wl, a11 = ri.o11 + wl;
-								const uint64_t X00 = recX[a00], Y00 = recY[a00], Z00 = recP[a00], X10 = recX[a10], Z10 = recP[a10];
-								const uint64_t X01 = recX[a01], Y01 = recY[a01], X11 = recX[a11];
-								const uint32_t below = (1u << b) - 1u;
-								uint32_t id[12];
-								// edges: 0:(0,1)y 1:(1,2)z 2:(3,2)y 3:(0,3)z 4:(4,5)y 5:(5,6)z 6:(7,6)y 7:(4,7)z 8..11 x
-								id[0] = rank_id(Y00, below); id[4] = id[0] + (((uint32_t)Y00 >> b) & 1u);
-								id[1] = rank_id(Z10, below); id[5] = id[1] + (((uint32_t)Z10 >> b) & 1u);
-								id[2] = rank_id(Y01, below); id[6] = id[2] + (((uint32_t)Y01 >> b) & 1u);
-								id[3] = rank_id(Z00, below); id[7] = id[3] + (((uint32_t)Z00 >> b) & 1u);
-								id[8] = rank_id(X00, below); id[9] = rank_id(X10, below);
-								id[10] = rank_id(X11, below); id[11] = rank_id(X01, below);
-								// vertex tasks of the planes the low corner point owns (ids before any on-iso redirection)
-								if (ri.flags & 1u) {
-									const uint32_t lr = lr0 + rr;
-									const bool pt = gz && ((recZ[a00] >> b) & 1u);
-									if (((uint32_t)X00 >> b) & 1u) put_vertex_task(P, id[8] - ri.g0, lr, x, 0u, pt);
-									if (((uint32_t)Y00 >> b) & 1u) put_vertex_task(P, id[0] - ri.g0, lr, x, 1u, false);
-									if (((uint32_t)Z00 >> b) & 1u) put_vertex_task(P, id[3] - ri.g0, lr, x, 2u, false);
-								}
-								const unsigned idx = corner_bits(recS[a00], recS[a00 + 1], recS[a10], recS[a10 + 1], recS[a11], recS[a11 + 1],
-								                                 recS[a01], recS[a01 + 1], b);
-								if ((ri.flags & 2u) && x < P.nx && idx != 0u && idx != 255u) {
-									const uint32_t ci = tb.cinfo[idx];
-									uint32_t start;
-									if ((ci & 0xFFFFu) != 0xFFFFu) {
-										start = ci & 0xFFFu; ntri = (ci >> 12) & 15u;
+							cx.syncwarp();
+							const uint32_t ncw = ncp - cw0 < P2_EM_CQ ? ncp - cw0 : P2_EM_CQ;
+							for (uint32_t j0 = 0; j0 < ncw; j0 += 32) {
+								// ---- one lane per visited CELL ----
+								const bool on = j0 + lane < ncw;
+								uint32_t ntri = 0, centre = 0, sm = 0, keep = 0, x = 0, y = 0, z = 0;
+								if (on) {
+									const uint32_t e = cq[j0 + lane];
+									x = e & 0xFFFFu;
+									const uint32_t b = x & 31u, wl = (x >> 5) - w0, rr = e >> 16;
+									const RowInfo ri = rowi[rr];
+									y = ri.y; z = ri.z;
+									const uint32_t a00 = ri.o00 + wl, a10 = ri.o10 + wl, a01 = ri.o01 + wl, a11 = ri.o11 + wl;
+									const Rec16 R00 = recA[a00], R10 = recA[a10], R01 = recA[a01], R11 = recA[a11];
+									const uint32_t n00 = recA[a00 + 1].a, n10 = recA[a10 + 1].a, n01 = recA[a01 + 1].a, n11 = recA[a11 + 1].a;
+									uint32_t mX00, mY00, mZ00, mX10, mZ10, mX01, mY01, mX11, zown = 0;
+									unsigned zm = 0;
+									if (!gz) {
+										// no on-iso sample in reach: the plane masks are XORs of the sign words (bits beyond the
+										// row's last point are zero in S; the last point has no X edge)
+										mX00 = (R00.a ^ shr1(R00.a, n00)); mX10 = (R10.a ^ shr1(R10.a, n10));
+										mX01 = (R01.a ^ shr1(R01.a, n01)); mX11 = (R11.a ^ shr1(R11.a, n11));
+										mY00 = R00.a ^ R10.a; mZ00 = R00.a ^ R01.a; mZ10 = R10.a ^ R11.a; mY01 = R01.a ^ R11.a;
+										if (x >= P.nx) mX00 &= ~(1u << b);
 									} else {
-										start = P.pcache[(uint64_t)(lr0 + rr) * (P.WP * 32u) + x];
-										const uint32_t pi = tb.pat[start];
-										ntri = pi & 0x7Fu; centre = pi >> 7;
+										const Rec16 B00 = recB[a00], B10 = recB[a10], B01 = recB[a01], B11 = recB[a11];
+										mX00 = B00.b; mY00 = B00.c; mZ00 = B00.d; mX10 = B10.b; mZ10 = B10.d; mX01 = B01.b; mY01 = B01.c; mX11 = B11.b;
+										zown = B00.a;
+										zm = index_to_zmask(corner_bits(B00.a, recB[a00 + 1].a, B10.a, recB[a10 + 1].a, B11.a, recB[a11 + 1].a,
+										                                B01.a, recB[a01 + 1].a, b));
 									}
-									sm = start | (((ci >> 16) & 1u) << 12);
-									if (gz) {
-										const unsigned zm = index_to_zmask(corner_bits(recZ[a00], recZ[a00 + 1], recZ[a10], recZ[a10 + 1], recZ[a11],
-										                                               recZ[a11 + 1], recZ[a01], recZ[a01 + 1], b));
+									const uint32_t below = (1u << b) - 1u;
+									uint32_t id[12];
+									// edges: 0:(0,1)y 1:(1,2)z 2:(3,2)y 3:(0,3)z 4:(4,5)y 5:(5,6)z 6:(7,6)y 7:(4,7)z 8..11 x
+									id[0] = rank_of(R00.c, mY00, below); id[4] = id[0] + ((mY00 >> b) & 1u);
+									id[1] = rank_of(R10.d, mZ10, below); id[5] = id[1] + ((mZ10 >> b) & 1u);
+									id[2] = rank_of(R01.c, mY01, below); id[6] = id[2] + ((mY01 >> b) & 1u);
+									id[3] = rank_of(R00.d, mZ00, below); id[7] = id[3] + ((mZ00 >> b) & 1u);
+									id[8] = rank_of(R00.b, mX00, below); id[9] = rank_of(R10.b, mX10, below);
+									id[10] = rank_of(R11.b, mX11, below); id[11] = rank_of(R01.b, mX01, below);
+									// vertex tasks of the planes the low corner point owns (ids before any on-iso redirection)
+									if ((ri.flags & 1u) && P.vtask) {
+										const uint32_t lr = lr0 + rr;
+										if ((mX00 >> b) & 1u) put_vertex_task(P, id[8] - ri.g0, lr, x, 0u, ((zown >> b) & 1u) != 0u);
+										if ((mY00 >> b) & 1u) put_vertex_task(P, id[0] - ri.g0, lr, x, 1u, false);
+										if ((mZ00 >> b) & 1u) put_vertex_task(P, id[3] - ri.g0, lr, x, 2u, false);
+									}
+									const unsigned idx = corner_bits(R00.a, n00, R10.a, n10, R11.a, n11, R01.a, n01, b);
+									if ((ri.flags & 2u) && x < P.nx && idx != 0u && idx != 255u) {
+										const uint32_t ci = tb.cinfo[idx];
+										uint32_t start;
+										if ((ci & 0xFFFFu) != 0xFFFFu) {
+											start = ci & 0xFFFu; ntri = (ci >> 12) & 15u;
+										} else {
+											start = P.pcache[(uint64_t)(lr0 + rr) * (P.WP * 32u) + x];
+											const uint32_t pi = tb.pat[start];
+											ntri = pi & 0x7Fu; centre = pi >> 7;
+										}
+										sm = start | (((ci >> 16) & 1u) << 12);
 										if (zm) {
 											// on-iso corners: the edges that meet one refer to its POINT vertex (X plane of the corner's row at the
 											// corner's x), and triangles that collapse are dropped (marching_cubes_33.c:970-988, :1235)
 											uint32_t pid[8];
 											pid[0] = id[8]; pid[1] = id[9]; pid[2] = id[10]; pid[3] = id[11];
-											pid[4] = id[8] + (((uint32_t)X00 >> b) & 1u); pid[5] = id[9] + (((uint32_t)X10 >> b) & 1u);
-											pid[6] = id[10] + (((uint32_t)X11 >> b) & 1u); pid[7] = id[11] + (((uint32_t)X01 >> b) & 1u);
+											pid[4] = id[8] + ((mX00 >> b) & 1u); pid[5] = id[9] + ((mX10 >> b) & 1u);
+											pid[6] = id[10] + ((mX11 >> b) & 1u); pid[7] = id[11] + ((mX01 >> b) & 1u);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -729,66 +804,223 @@ SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, co
 											sm |= 0x2000u;
 										}
 									}
-								}
 #if defined(__CUDA_ARCH__)
-								{
-									uint4 *d = reinterpret_cast<uint4 *>(scr + lane * 16u);
-									const uint32_t sw = (lane >> 1) & 3u;
-									d[0 ^ sw] = make_uint4(id[0], id[1], id[2], id[3]);
-									d[1 ^ sw] = make_uint4(id[4], id[5], id[6], id[7]);
-									d[2 ^ sw] = make_uint4(id[8], id[9], id[10], id[11]);
-								}
+									{
+										uint4 *d = reinterpret_cast<uint4 *>(scr + lane * 16u);
+										const uint32_t sw = (lane >> 1) & 3u;
+										d[0 ^ sw] = make_uint4(id[0], id[1], id[2], id[3]);
+										d[1 ^ sw] = make_uint4(id[4], id[5], id[6], id[7]);
+										d[2 ^ sw] = make_uint4(id[8], id[9], id[10], id[11]);
+									}
 #else
-								for (uint32_t ed = 0; ed < 12; ed++) scr[scr_pos(lane, ed)] = id[ed];
+									for (uint32_t ed = 0; ed < 12; ed++) scr[scr_pos(lane, ed)] = id[ed];
 #endif
-							}
-							// triangle / centre offsets of the round: shuffle scan in sweep order
-							uint32_t tot;
-							const uint32_t ex = warp_exscan(cx, ntri | (centre << 16), &tot);
-							const uint32_t e0 = ex & 0xFFFFu, ntot = tot & 0xFFFFu;
-							const uint32_t cl = cloc0 + runC + (ex >> 16);
-							const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
-							if (on && centre) {
-								if (cl < P.capV) {
-									emit_centre_vertex<Sample>(P, x, y, z, cl);
-									if (KEYS && P.vkey) P.vkey[cl] = cell * 4 + 3;
-								} else {
-									P.totals->overflow = 1;
 								}
-							}
-							if (on) scr[scr_pos(lane, 12)] = vb + cl;
-							cx.syncwarp();
-							// ---- one lane per TRIANGLE: consecutive lanes write consecutive triangles ----
-							for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
-								const uint32_t t = t0 + lane;
-								// owner = the last cell whose first triangle is not after t (e0 is non-decreasing over the lanes)
-								uint32_t c = 0;
+								// triangle / centre offsets of the round: shuffle scan in sweep order
+								uint32_t tot;
+								const uint32_t ex = warp_exscan(cx, ntri | (centre << 16), &tot);
+								const uint32_t e0 = ex & 0xFFFFu, ntot = tot & 0xFFFFu;
+								const uint32_t cl = cloc0 + runC + (ex >> 16);
+								const uint64_t cell = ((uint64_t)z * P.ny + y) * P.nx + x;
+								if (on && centre) {
+									if (cl < P.capV) {
+										emit_centre_vertex<Sample>(P, x, y, z, cl);
+										if (KEYS && P.vkey) P.vkey[cl] = cell * 4 + 3;
+									} else {
+										P.totals->overflow = 1;
+									}
+								}
+								if (on) scr[scr_pos(lane, 12)] = vb + cl;
+								cx.syncwarp();
+								// ---- one lane per TRIANGLE: consecutive lanes write consecutive triangles ----
+								for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
+									const uint32_t t = t0 + lane;
+									// owner = the last cell whose first triangle is not after t (e0 is non-decreasing over the lanes)
+									uint32_t c = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-								for (uint32_t step = 16; step; step >>= 1) {
-									const uint32_t v = cx.shfl(e0, (int)(c + step));
-									if (v <= t) c += step;
+									for (uint32_t step = 16; step; step >>= 1) {
+										const uint32_t v = cx.shfl(e0, (int)(c + step));
+										if (v <= t) c += step;
+									}
+									const uint32_t csm = cx.shfl(sm, (int)c), ce0 = cx.shfl(e0, (int)c), ckeep = cx.shfl(keep, (int)c);
+									uint64_t ccell = 0;
+									if (KEYS && P.tcell) ccell = cx.shfl(cell, (int)c);
+									if (t < ntot) {
+										uint32_t j = t - ce0;
+										if (csm & 0x2000u) j = nth_bit(ckeep, j);
+										const unsigned tw = tb.tri[(csm & 0xFFFu) + j];
+										uint32_t ti[3];
+										ti[0] = scr[scr_pos(c, (tw >> 8) & 15u)];
+										ti[1] = scr[scr_pos(c, (tw >> 4) & 15u)];
+										ti[2] = scr[scr_pos(c, tw & 15u)];
+										write_triangle<KEYS>(P, tbase + runT + t, ti, (csm >> 12) & 1u, ccell);
+									}
 								}
-								const uint32_t csm = cx.shfl(sm, (int)c), ce0 = cx.shfl(e0, (int)c), ckeep = cx.shfl(keep, (int)c);
-								uint64_t ccell = 0;
-								if (KEYS && P.tcell) ccell = cx.shfl(cell, (int)c);
-								if (t < ntot) {
-									uint32_t j = t - ce0;
-									if (csm & 0x2000u) j = nth_bit(ckeep, j);
-									const unsigned tw = tb.tri[(csm & 0xFFFu) + j];
-									uint32_t ti[3];
-									ti[0] = scr[scr_pos(c, (tw >> 8) & 15u)];
-									ti[1] = scr[scr_pos(c, (tw >> 4) & 15u)];
-									ti[2] = scr[scr_pos(c, tw & 15u)];
-									write_triangle<KEYS>(P, tbase + runT + t, ti, (csm >> 12) & 1u, ccell);
-								}
+								cx.syncwarp();
+								runT += ntot; runC += tot >> 16;
 							}
-							cx.syncwarp();
-							runT += ntot; runC += tot >> 16;
 						}
 					}
 				}
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K3: shared vertices (edge / on-iso point vertices), straight from the bitmaps.
+//
+// The vertex ids of a run of point rows are consecutive, and the count kernel left, per word and plane, the
+// row-local index of the plane's first vertex (wpreV).  A warp takes a run of rows, rebuilds the three plane
+// masks of every word (XORs of sign words; the on-iso rules per word where an on-iso sample is in reach) and
+// drops one 4-byte entry per vertex at its own position of a shared-memory window -- no scan, no per-vertex
+// task in global memory (round 1 wrote and re-read 8 bytes per vertex).  Lane t of a round then computes the
+// vertex at position t; positions, normals and colours leave through a staging buffer as consecutive words,
+// so that every store instruction fills whole sectors (3 x 4-byte components per lane used to touch each
+// sector three times).
+// ---------------------------------------------------------------------------
+#define P2_VX_WARPS 8
+#define P2_VQ 512                              // vertices per window
+#define P2_VX_WARP_BYTES (P2_VQ * 4 + 32 * 6 * 4)     // window + staging for 32 x 3 components (float or double)
+
+struct VertexArgs {
+	uint32_t row_begin, row_end;  // local point rows whose shared vertices this slab owns
+	uint32_t Gv;                  // rows per group
+	uint32_t ngroups;
+};
+
+// rows per group: about two passes of 32 quads
+SIMT_HD uint32_t vertex_group_rows(uint32_t Q) { return Q >= 64 ? 1u : 64u / Q; }
+
+template <typename Sample, bool KEYS, typename CX>
+SIMT_FN void emit_vertices_body(const CX &cx, const Params &P, const VertexArgs &A, unsigned char *wsm)
+{
+	typedef typename Traits<Sample>::Real Real;
+	uint32_t *vq = reinterpret_cast<uint32_t *>(wsm);
+	uint32_t *st = vq + P2_VQ;
+	const unsigned lane = cx.lane();
+	const bool anyz = *P.anyZp == P.zepoch;
+	const uint32_t nwarps = cx.nblocks() * P2_VX_WARPS;
+	const uint32_t nq = P.Q;
+	if (cx.block() == 0 && cx.tid() == 0) P.totals->ticket = 0;      // re-arm the cell kernel's counter (it has finished: stream order)
+
+	uint32_t g = cx.block() * P2_VX_WARPS + cx.warp(), gnext = 0;
+	for (; g < A.ngroups; g = cx.shfl(gnext, 0)) {
+		if (lane == 0) gnext = nwarps + cx.atomic_add(&P.totals->ticket2, 1u);
+		const uint32_t lr0 = A.row_begin + g * A.Gv, lrE = lr0 + A.Gv < A.row_end ? lr0 + A.Gv : A.row_end, nr = lrE - lr0;
+		const uint32_t id0 = P.rowBV[lr0], nvg = P.rowBV[lrE] - id0;   // the group's vertices are [id0, id0 + nvg)
+		if (nvg == 0) continue;
+		const bool gz = group_oniso(cx, P, anyz, lr0, A.Gv);
+		const uint32_t nitems = nr * nq;
+		for (uint32_t v0 = 0; v0 < nvg; v0 += P2_VQ) {
+			// ---- entries of the window [v0, v0 + VQ): every (row, quad) drops its vertices at their own positions ----
+			cx.syncwarp();
+			for (uint32_t it = lane; it < nitems; it += 32) {
+				const uint32_t r = it / nq, q = it - r * nq;
+				const uint32_t lr = lr0 + r;
+				const uint64_t i0 = (uint64_t)lr * P.WP + 4 * q;
+#if defined(__CUDA_ARCH__)
+				const uint4 av = *reinterpret_cast<const uint4 *>(P.A + i0);
+				const uint32_t anyv = av.x | av.y | av.z | av.w;
+#else
+				const uint32_t anyv = P.A[i0] | P.A[i0 + 1] | P.A[i0 + 2] | P.A[i0 + 3];
+#endif
+				if (!anyv) continue;                                  // no visited point in this quad: no vertex either
+				const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+				const bool hasY = y < P.ny, hasZ = z < P.nz;
+				const Quad qs = load_quad(P.S, i0);
+				const Quad qy = hasY ? load_quad(P.S, i0 + P.WP) : qs;
+				const Quad qz = hasZ ? load_quad(P.S, i0 + (uint64_t)P.NY * P.WP) : qs;
+				const uint32_t rbase = P.rowBV[lr] - id0;
+				for (int k = 0; k < 4; k++) {
+					const uint32_t w = 4 * q + (uint32_t)k;
+					if (w >= P.W) break;
+					const uint32_t sw = qs.s[k];
+					uint32_t m[3], zw = 0;
+					m[0] = (sw ^ shr1(sw, qs.s[k + 1])) & mask_le(w, P.nx - 1); m[1] = sw ^ qy.s[k]; m[2] = sw ^ qz.s[k];
+					if (gz) {
+						zw = P.Z[i0 + k];
+						uint32_t dep = zw | (P.Z[i0 + k + 1] & 1u);
+						if (hasY) dep |= P.Z[i0 + P.WP + k];
+						if (hasZ) dep |= P.Z[i0 + (uint64_t)P.NY * P.WP + k];
+						if (dep) {
+							WordRec rec;
+							CellWords cw;
+							word_masks_generic(P, z, y, w, rec, cw);
+							m[0] = rec.X; m[1] = rec.Y; m[2] = rec.Z;
+						}
+					}
+					if (!(m[0] | m[1] | m[2])) continue;
+					const uint64_t pre = P.wpreV[i0 + k];
+					for (int a = 0; a < 3; a++) {
+						uint32_t mm = m[a];
+						uint32_t slot = rbase + fldV(pre, a) - v0;          // (wraps below the window: compared unsigned)
+						while (mm) {
+							const int b = ffs32(mm);
+							mm &= mm - 1;
+							if (slot < P2_VQ)
+								vq[slot] = ((w << 5) + (uint32_t)b) | ((uint32_t)a << 16) | ((a == 0 && ((zw >> b) & 1u)) ? 1u << 18 : 0u) | (r << 19);
+							slot++;
+						}
+					}
+				}
+			}
+			cx.syncwarp();
+			// ---- one lane per vertex, consecutive ids ----
+			const uint32_t nvw = nvg - v0 < P2_VQ ? nvg - v0 : P2_VQ;
+			for (uint32_t j0 = 0; j0 < nvw; j0 += 32) {
+				const bool on = j0 + lane < nvw;
+				const uint32_t idr = id0 + v0 + j0;                        // id of lane 0's vertex
+				Real Vo[3] = {0, 0, 0};
+				float No[3] = {0, 0, 0};
+				if (on) {
+					const uint32_t e = vq[j0 + lane];
+					const uint32_t x = e & 0xFFFFu, a = (e >> 16) & 3u, lr = lr0 + (e >> 19);
+					const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+					Real r[6];
+					if ((e >> 18) & 1u) point_vertex_r<Sample>(P, x, y, z, r);
+					else edge_vertex_r<Sample>(P, x, y, z, (int)a, r);
+					transform_vertex<Real>(P, r, Vo, No);
+					if (KEYS && P.vkey && idr + lane < P.capV) P.vkey[idr + lane] = (((uint64_t)z * P.NY + y) * P.NX + x) * 4 + a;
+				}
+				const uint32_t nround = nvw - j0 < 32u ? nvw - j0 : 32u;
+				if (idr + nround > P.capV) { if (lane == 0) P.totals->overflow = 1; }
+				const uint64_t vcap = (uint64_t)P.capV * 3u, wb = (uint64_t)idr * 3u;
+				// positions
+				if (sizeof(Real) == 4) {
+					float *sf = reinterpret_cast<float *>(st);
+					sf[3 * lane] = (float)Vo[0]; sf[3 * lane + 1] = (float)Vo[1]; sf[3 * lane + 2] = (float)Vo[2];
+					cx.syncwarp();
+					float *Vg = reinterpret_cast<float *>(P.V);
+					for (uint32_t k = 0; k < 3; k++) {
+						const uint32_t w = lane + 32u * k;
+						if (w < 3u * nround && wb + w < vcap) Vg[wb + w] = sf[w];
+					}
+				} else {
+					double *sd = reinterpret_cast<double *>(st);
+					sd[3 * lane] = (double)Vo[0]; sd[3 * lane + 1] = (double)Vo[1]; sd[3 * lane + 2] = (double)Vo[2];
+					cx.syncwarp();
+					double *Vg = reinterpret_cast<double *>(P.V);
+					for (uint32_t k = 0; k < 3; k++) {
+						const uint32_t w = lane + 32u * k;
+						if (w < 3u * nround && wb + w < vcap) Vg[wb + w] = sd[w];
+					}
+				}
+				cx.syncwarp();
+				// normals
+				{
+					float *sf = reinterpret_cast<float *>(st);
+					sf[3 * lane] = No[0]; sf[3 * lane + 1] = No[1]; sf[3 * lane + 2] = No[2];
+					cx.syncwarp();
+					for (uint32_t k = 0; k < 3; k++) {
+						const uint32_t w = lane + 32u * k;
+						if (w < 3u * nround && wb + w < vcap) P.N[wb + w] = sf[w];
+					}
+				}
+				if (on && idr + lane < P.capV) P.color[idr + lane] = P.color_value;
+				cx.syncwarp();
 			}
 		}
 	}

@@ -79,19 +79,30 @@ static void run(Params &P, bool emit)
 	// K4
 	{
 		EmitArgs A;
+		A.pick = 0; A.nquads = 0;
 		const uint32_t zend = P.pz1 > P.cz1 ? P.pz1 : P.cz1;
 		A.row_begin = (P.cz0 - P.zlo) * P.NY; A.row_end = (zend - P.zlo) * P.NY;
 		emit_geometry(P.Q, A);
 		const uint32_t nrows = A.row_end - A.row_begin;
-		A.ngroups = (nrows + A.Ge - 1) / A.Ge;
+		A.ngroups = (nrows + A.f.Ge - 1) / A.f.Ge;
 		A.nunits = (A.ngroups + P2_EM_UNIT - 1) / P2_EM_UNIT;
 		const uint32_t nblocks = 3;      // a few persistent CTAs: exercises the ticket hand-out too
 		mc33emu::launch(nblocks, 256, P2_EM_WARPS * P2_EM_WARP_BYTES, [&](EmuCtx &cx) {
 			emit_cells_body<Sample, true>(cx, P, tb, A, cx.smem() + cx.warp() * P2_EM_WARP_BYTES);
 		});
 	}
-	// K3, vertices: dense over the ids, each from the task left in its slot
-	for (uint32_t id = 0; id < P.totals->nShared && id < P.capV; id++) run_vertex_task<Sample>(P, id);
+	// K3, vertices: straight from the bitmaps (MC33_EMU_VTASK=1: the round-1 form, one task per vertex left by K4)
+	if (P.vtask) {
+		for (uint32_t id = 0; id < P.totals->nShared && id < P.capV; id++) run_vertex_task<Sample>(P, id);
+	} else {
+		VertexArgs A;
+		A.row_begin = (P.pz0 - P.zlo) * P.NY; A.row_end = (P.pz1 - P.zlo) * P.NY;
+		A.Gv = vertex_group_rows(P.Q);
+		A.ngroups = (A.row_end - A.row_begin + A.Gv - 1) / A.Gv;
+		mc33emu::launch(2, 256, P2_VX_WARPS * P2_VX_WARP_BYTES, [&](EmuCtx &cx) {
+			emit_vertices_body<Sample, true>(cx, P, A, cx.smem() + cx.warp() * P2_VX_WARP_BYTES);
+		});
+	}
 }
 
 extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, const mc33cu_out *o,
@@ -131,7 +142,7 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.anyZp = &tot.anyZ;
 	bool emit = o != nullptr;
 	std::vector<uint64_t> vtask(emit ? (size_t)o->capV + 1 : 1);
-	P.vtask = vtask.data();
+	P.vtask = getenv("MC33_EMU_VTASK") ? vtask.data() : nullptr;
 	if (emit) {
 		P.V = o->V; P.N = o->N; P.color = o->color; P.T = o->T; P.vkey = o->vkey; P.tcell = o->tcell;
 		P.capV = o->capV; P.capT = o->capT; P.vbase = o->vbase; P.vbase_next = o->vbase_next; P.dbases = o->dev_bases;

@@ -7,10 +7,11 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "tools"))
 import numpy as np
 import torch
 
-import bench
+import workloads
 from mc33_c_library_b200 import _cabi as cabi
 from mc33_c_library_b200.device import Extractor
 
@@ -19,7 +20,7 @@ n_iso = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 kind = sys.argv[3] if len(sys.argv) > 3 else "gyroid"
 dev = torch.device("cuda", 0)
 if kind == "gyroid":
-    grid = bench.gyroid_device(n, 0, n, n, dev)
+    grid = workloads.make("cfg2", n=n).device_slab(0, n, dev)
     isos = [0.0, -0.9, 0.6, -1.2][:n_iso]
 elif kind == "ct":
     # cfg3-like: u16 blobs + texture + noise 0..15, INTEGER isovalue (on-iso samples everywhere near the surface)
