@@ -1060,7 +1060,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 // round-2 kernels: the bodies live in mc33_pipeline.cuh (shared with the CPU test harness)
 // ---------------------------------------------------------------------------
 #ifndef CNT2_MINB
-#define CNT2_MINB 3
+#define CNT2_MINB 4     // 64 registers, 4 CTAs per SM (A/B at cfg2 / cfg3 / cfg5: 0.076 / 1.51 / 9.99 ms against 0.081 / 1.66 / 10.6 at 3 and 0.092 / 2.02 / 13.3 at 2)
 #endif
 template <typename Sample>
 __global__ void __launch_bounds__(256, CNT2_MINB) k_count2(const __grid_constant__ Params P, const __grid_constant__ CountArgs A)
@@ -1727,7 +1727,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 		}
 		CountArgs A;
 		A.nblk = c->nblk; A.GW = c->cnt_gw; A.lb = c->lb_cur; A.lb_ticket = c->lbt_cur; A.tag = c->lb_tag;
-		A.owned_end_row = owned_end; A.export4 = c->export4;
+		A.owned_end_row = owned_end; A.export4 = c->export4; A.dbg_noprefix = 0;
 		k_count2<Sample><<<c->nblk, 256, P2_CNT_SMEM, s>>>(P, A);
 		c->launches++;
 		if (c->timing) CU(cudaEventRecord(c->ev[2], s));

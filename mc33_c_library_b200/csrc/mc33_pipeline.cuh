@@ -107,6 +107,7 @@ MC_COLD uint32_t keep_mask(const Tables &tb, unsigned start, unsigned zm)
 #define P2_CNT_CQ 256                          // queue entries per warp
 #define P2_CNT_SMEM (3 * 1024 + 2 * 1024 + 128 + 64 + P2_CNT_WARPS * P2_CNT_CQ * 4)
 #define P2_LB_WORDS 6                          // look-back words per block
+#define P2_LB_K 1                              // predecessors per lane and look-back window (4 measured 0.005 ms slower at cfg2)
 
 struct CountArgs {
 	uint32_t nblk, GW;
@@ -115,6 +116,8 @@ struct CountArgs {
 	uint32_t tag;                 // 16-bit tag of this launch (1..65535): stale words of earlier launches do not match
 	uint32_t owned_end_row;       // first row after the point rows this slab owns
 	uint32_t *export4;            // optional DEVICE {nV, nT, nShared, nCentre} for the all-gather across slabs
+	uint32_t dbg_noprefix;        // test hook (CPU emulation): only block 0 publishes an inclusive prefix, so every block walks
+	                              // back over aggregates all the way (on the device the walk normally ends at the first window)
 };
 
 struct QuadZ { uint64_t pv[4]; uint32_t vis[4], walk[4]; uint32_t nts; };
@@ -396,37 +399,49 @@ SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const C
 			cx.st_release(&me[0], tagw | aggV);
 		}
 		uint64_t exV = 0, exT = 0, exC = 0;
-		for (int64_t base = (int64_t)blk - 1; base >= 0; base -= 32) {      // (warp uniform)
-			const int64_t j = base - (int64_t)lane;             // lane 0 looks at the nearest predecessor of the window
-			unsigned long long v0 = 0, t1 = 0, c2 = 0;
-			bool isP = false;
-			if (j >= 0) {
-				const unsigned long long *o = A.lb + (uint64_t)j * P2_LB_WORDS;
-				for (;;) {
-					const unsigned long long p0 = cx.ld_acquire(&o[3]);
-					if ((p0 >> 48) == A.tag) { v0 = p0; t1 = o[4]; c2 = o[5]; isP = true; break; }
-					const unsigned long long a0 = cx.ld_acquire(&o[0]);
-					if ((a0 >> 48) == A.tag) { v0 = a0; t1 = o[1]; c2 = o[2]; break; }
-					cx.backoff();                                // neither published yet: that block is still counting
+		// A window is 32 x P2_LB_K predecessors: every lane has P2_LB_K independent loads in flight, so the blocks of one
+		// wave -- which finish counting together and therefore all have to add up a wave's worth of aggregates --
+		// need wave / 128 round trips to L2 instead of wave / 32.
+		for (int64_t base = (int64_t)blk - 1; base >= 0; base -= 32 * P2_LB_K) {      // (warp uniform)
+			unsigned long long v0[P2_LB_K], t1[P2_LB_K], c2[P2_LB_K];
+			uint32_t dmin = 0xFFFFFFFFu;                        // distance of the nearest predecessor (of this lane's) with an inclusive prefix
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+			for (int k = 0; k < P2_LB_K; k++) {
+				const int64_t j = base - (int64_t)(lane + 32u * (unsigned)k);
+				v0[k] = 0; t1[k] = 0; c2[k] = 0;
+				if (j >= 0) {
+					const unsigned long long *o = A.lb + (uint64_t)j * P2_LB_WORDS;
+					for (;;) {
+						const unsigned long long p0 = cx.ld_acquire(&o[3]);
+						if ((p0 >> 48) == A.tag) { v0[k] = p0; t1[k] = o[4]; c2[k] = o[5]; if (dmin == 0xFFFFFFFFu) dmin = lane + 32u * (unsigned)k; break; }
+						const unsigned long long a0 = cx.ld_acquire(&o[0]);
+						if ((a0 >> 48) == A.tag) { v0[k] = a0; t1[k] = o[1]; c2[k] = o[2]; break; }
+						cx.backoff();                                // neither published yet: that block is still counting
+					}
 				}
 			}
 			// the nearest predecessor that already has an inclusive prefix ends the walk; the ones nearer than it
 			// contribute their aggregates
-			const uint32_t pmask = cx.ballot(j >= 0 && isP);
-			const int first = pmask ? ffs32(pmask) : 32;
-			const bool use = j >= 0 && (int)lane <= first;
-			uint64_t sV = use ? (v0 & FIELD) : 0, sT = use ? t1 : 0, sC = use ? c2 : 0;
+			const uint32_t first = cx.reduce_min(dmin);
+			uint64_t sV = 0, sT = 0, sC = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+			for (int k = 0; k < P2_LB_K; k++)
+				if (lane + 32u * (unsigned)k <= first) { sV += v0[k] & FIELD; sT += t1[k]; sC += c2[k]; }    // (slots before block 0 hold zeros)
 			for (unsigned d = 16; d; d >>= 1) {
 				sV += cx.shfl(sV, (int)(lane ^ d));
 				sT += cx.shfl(sT, (int)(lane ^ d));
 				sC += cx.shfl(sC, (int)(lane ^ d));
 			}
 			exV += sV; exT += sT; exC += sC;
-			if (pmask) break;
+			if (first != 0xFFFFFFFFu) break;
 		}
 		if (lane == 0) {
 			me[4] = exT + aggT; me[5] = exC + aggC;
-			cx.st_release(&me[3], tagw | ((exV + aggV) & FIELD));
+			if (!A.dbg_noprefix || blk == 0) cx.st_release(&me[3], tagw | ((exV + aggV) & FIELD));
 			s_base[0] = exV; s_base[1] = exT; s_base[2] = exC;
 		}
 	}

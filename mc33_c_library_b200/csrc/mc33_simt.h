@@ -40,6 +40,7 @@ struct DevCtx {
 	__device__ __forceinline__ uint32_t reduce_or(uint32_t v) const { return __reduce_or_sync(0xFFFFFFFFu, v); }
 	__device__ __forceinline__ uint32_t reduce_add(uint32_t v) const { return __reduce_add_sync(0xFFFFFFFFu, v); }
 	__device__ __forceinline__ uint32_t reduce_max(uint32_t v) const { return __reduce_max_sync(0xFFFFFFFFu, v); }
+	__device__ __forceinline__ uint32_t reduce_min(uint32_t v) const { return __reduce_min_sync(0xFFFFFFFFu, v); }
 	__device__ __forceinline__ void syncwarp() const { __syncwarp(); }
 	__device__ __forceinline__ void syncthreads() const { __syncthreads(); }
 	__device__ __forceinline__ uint32_t atomic_add(uint32_t *p, uint32_t v) const { return atomicAdd(p, v); }
@@ -89,6 +90,7 @@ struct EmuCtx {
 	uint32_t reduce_or(uint32_t v) const { return (uint32_t)collective(2, v, 0, false); }
 	uint32_t reduce_add(uint32_t v) const { return (uint32_t)collective(3, v, 0, false); }
 	uint32_t reduce_max(uint32_t v) const { return (uint32_t)collective(4, v, 0, false); }
+	uint32_t reduce_min(uint32_t v) const { return ~(uint32_t)collective(4, (uint32_t)~v, 0, false); }
 	void syncwarp() const { collective(5, 0, 0, false); }
 	void syncthreads() const { collective(5, 0, 0, true); }
 	uint32_t atomic_add(uint32_t *p, uint32_t v) const { uint32_t o = *p; *p = o + v; return o; }

@@ -73,6 +73,7 @@ static void run(Params &P, bool emit)
 		A.lb = lb.data(); A.lb_ticket = ticket; A.tag = 7;
 		A.owned_end_row = (P.pz1 - P.zlo) * P.NY;
 		A.export4 = nullptr;
+		A.dbg_noprefix = getenv("MC33_EMU_LB_NOPREFIX") ? 1u : 0u;
 		mc33emu::launch(A.nblk, 256, P2_CNT_SMEM, [&](EmuCtx &cx) { count_body<Sample>(cx, P, tb, A); });
 	}
 	if (!emit) return;

@@ -132,3 +132,18 @@ def test_kernel_bodies_plateaus_and_planted_on_iso_samples():
     g.reshape(-1)[rng.integers(0, g.size, size=30)] = iso
     g[0, 0, 0] = iso; g[-1, -1, -1] = iso; g[0, 20, 39] = iso; g[39, 0, 33] = iso
     _same(oracle_extract(g, float(iso)), emu_extract(g, float(iso)))
+
+
+def test_kernel_bodies_lookback_over_many_blocks():
+    """enough rows for hundreds of count blocks: the decoupled look-back walks several 128-block windows"""
+    import os
+    a = noise_grid(0, "u8", scale=4, shape=(210, 200, 9))
+    want = oracle_extract(a, 2.0, "u8")
+    _same(want, emu_extract(a, 2.0, "u8"))
+    # ... and with the walk forced over aggregates all the way back to block 0 (on the device it normally ends
+    # within the first window; the CPU emulation runs the blocks in order, so every prefix is there already)
+    os.environ["MC33_EMU_LB_NOPREFIX"] = "1"
+    try:
+        _same(want, emu_extract(a, 2.0, "u8"))
+    finally:
+        del os.environ["MC33_EMU_LB_NOPREFIX"]

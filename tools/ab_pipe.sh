@@ -7,7 +7,7 @@ while [ $# -gt 0 ] && [ "$1" != "--" ]; do envs+=("$1"); shift; done
 shift
 for w in "$@"; do
   for e in "${envs[@]}"; do
-    tag=$(echo "$e" | tr ' =' '__')
+    tag=$(echo "$e" | sed 's#[^A-Za-z0-9]#_#g' | tail -c 60)
     env $e timeout 600 python tools/time_workload.py $w > gpurun_out/tw_${w}_${tag}.json 2> gpurun_out/tw_${w}_${tag}.err
     echo "$w [$e] $(head -c 700 gpurun_out/tw_${w}_${tag}.json)" >> gpurun_out/ab_pipe.txt
   done
