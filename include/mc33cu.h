@@ -191,10 +191,10 @@ int  mc33cu_host_alloc(size_t bytes, void **out);
 int  mc33cu_host_free(void *p);
 
 /* per-kernel device times of the most recent extraction, in milliseconds:
- * [0] classify [1] count [2] row scan [3] emit cells (triangles + centre vertices)
- * [4] emit vertices.  Only measured while timing is enabled: event records between
- * the kernels, and the two emit kernels then run one after the other instead of
- * side by side on two streams. */
+ * [0] classify [1] count (with its look-back scan) [2] the gap the round-1 row-scan kernel used to fill (~0)
+ * [3] emit cells (triangles + centre vertices; both cell kernels when the device picks) [4] emit vertices.
+ * Only measured while timing is enabled (event records between the kernels, which always run one after
+ * the other on the context's stream). */
 int  mc33cu_enable_timing(mc33cu_ctx *ctx, int on);
 int  mc33cu_kernel_times(mc33cu_ctx *ctx, float ms[5]);
 /* number of kernel launches issued by this context so far */

@@ -1135,6 +1135,10 @@ struct mc33cu_ctx {
 	uint64_t launches;
 	// resident CTAs per SM of the two emit kernels (persistent grids)
 	uint32_t emc_per_sm, emv_per_sm, emc2_per_sm, emv2_per_sm;
+	// what the device picked for an isovalue of a state (from the totals of an earlier extraction that was synchronised):
+	// the same isovalue on the same state launches only that kernel (unconditionally: a stale entry costs time, never correctness)
+	double pick_iso[SWEEP_MAX + 1][4]; int8_t pick_val[SWEEP_MAX + 1][4]; uint8_t pick_pos[SWEEP_MAX + 1];
+	double state_iso[SWEEP_MAX + 1];       // isovalue of the last count of each state
 	int cells;                             // cell kernel: 0 both launched, the device picks by the on-iso statistic; 1 / 2 force one
 	int vtx;                               // 2: vertices straight from the bitmaps (no vertex tasks); 1: the round-1 task form
 	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
@@ -1704,6 +1708,7 @@ template <typename Sample> static int launch_count_phase(mc33cu_ctx *c, int set)
 		launch_classify<Sample>(c);
 	}
 	c->counted_set = set; c->emits_since_count[set + 1] = 0;
+	c->state_iso[set + 1] = P.iso;
 	c->h_totals = c->h_all + (set + 1);
 	c->counted_mask |= 1u << (set + 1); c->pending_mask |= 1u << (set + 1); c->hvalid_mask &= ~(1u << (set + 1));
 	if (c->timing) CU(cudaEventRecord(c->ev[1], s));
@@ -1760,7 +1765,10 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
 		if (grid > (ngroups + EM_WARPS - 1) / EM_WARPS) grid = (ngroups + EM_WARPS - 1) / EM_WARPS;
 		const uint32_t nquads = P.Lrows * P.Q;
-		const int which = c->pipe == 1 ? 1 : c->cells;            // 1 direct kernel, 2 record kernel, 0 both (the device picks)
+		int which = c->pipe == 1 ? 1 : c->cells;                  // 1 direct kernel, 2 record kernel, 0 both (the device picks)
+		if (which == 0)
+			for (int i = 0; i < 4; i++)
+				if (c->pick_val[c->cur_state + 1][i] && c->pick_iso[c->cur_state + 1][i] == P.iso) which = c->pick_val[c->cur_state + 1][i];
 		if (which != 2) {
 			const uint32_t pk = which == 0 ? nquads : 0u;
 			if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine, pk);
@@ -1909,6 +1917,14 @@ static int fetch_totals(mc33cu_ctx *c, uint32_t *flags = nullptr)
 			const Totals &t = c->h_all[st + 1];
 			if (t.range) f |= 1u;
 			if (t.overflow) f |= 2u;
+			if (c->pipe == 2 && ((c->counted_mask >> (st + 1)) & 1u)) {
+				// remember which cell kernel the device statistic picks for this state's isovalue
+				const int8_t pv = (uint64_t)t.nslow * 64u > (uint64_t)c->P.Lrows * c->P.Q ? 2 : 1;
+				int slot = -1;
+				for (int i = 0; i < 4; i++) if (c->pick_val[st + 1][i] && c->pick_iso[st + 1][i] == c->state_iso[st + 1]) slot = i;
+				if (slot < 0) { slot = c->pick_pos[st + 1]; c->pick_pos[st + 1] = (uint8_t)((slot + 1) & 3); }
+				c->pick_iso[st + 1][slot] = c->state_iso[st + 1]; c->pick_val[st + 1][slot] = pv;
+			}
 		}
 	c->hvalid_mask |= want;
 	c->pending_mask = 0;
@@ -2074,6 +2090,7 @@ extern "C" int mc33cu_classify_sweep(mc33cu_ctx *c, const double *isos, int n)
 	if (rc) return rc;
 	c->sw_n = n;
 	c->counted_mask &= 1u;            // the sets' earlier counts belong to the previous sweep's bitmaps
+	// (pick entries are keyed by isovalue, so a set that gets another isovalue simply misses)
 	c->hvalid_mask &= 1u;
 	for (int j = 0; j < n; j++) c->sw_iso[j] = isos[j];
 	c->ev_valid = false;
