@@ -848,7 +848,13 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
 // ---------------------------------------------------------------------------
 #define EM_WARPS 8
 #define CQ 256
-#define EM_SCR 512      // per-warp scratch words: 13 ids x 32 lanes, or 8 (mask, base) pairs x 32 lanes
+#ifndef EMC_TRI_STAGED
+#define EMC_TRI_STAGED 0     // 1: every cell lane writes its own triangles into a shared-memory window that goes out as whole words.
+                            // Measured slower (cfg2 0.184 against 0.175 ms, cfg5 25.0 against 20.6): the per-lane pattern walk runs
+                            // as long as the busiest lane of the warp.  Kept for A/B.
+#endif
+#define EM_TW 96         // triangles per staging window
+#define EM_SCR (13 * 32 + 3 * EM_TW)      // per-warp scratch words: 13 ids x 32 lanes + the triangle window (or 8 (mask, base) pairs x 32 lanes)
 #ifndef EMV_MINB
 #define EMV_MINB 5      // resident CTAs per SM the emit kernels are compiled for (register cap)
 #endif
@@ -1021,6 +1027,41 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							P.totals->overflow = 1;
 						}
 					}
+#if EMC_TRI_STAGED
+					{
+						// Triangles of this round.  Every cell lane writes its own triangles (pattern walk, ids from its own
+						// column of the scratch, winding) into a shared-memory window at their positions of the round, then the
+						// warp copies the window out as consecutive words: whole-sector stores, and no search for the owner cell
+						// of a triangle (round 1: one lane per triangle with a byte map of the owners, 16 % of the kernel's
+						// instructions).  Cells with an on-iso corner write their own triangles afterwards, over their slots.
+						const uint32_t e0 = ex & 0xFFFFu, ntot = tot & 0xFFFFu;
+						uint32_t *tst = scr + 13 * 32;
+						if (on) scr[12 * 32 + lane] = vb + cl;
+						const bool swp = (pat.m != 0u) != (P.geom.normal_neg != 0);
+						for (uint32_t t0 = 0; t0 < ntot; t0 += EM_TW) {
+							if (on && !zm && e0 < t0 + EM_TW && e0 + pat.ntri > t0) {
+								const uint32_t jlo = t0 > e0 ? t0 - e0 : 0u, jhi = min(pat.ntri, t0 + EM_TW - e0);
+								for (uint32_t j = jlo; j < jhi; j++) {
+									const unsigned tw = tb.tri[pat.start + j];
+									// winding: marching_cubes_33.c:1246-1250 (nibble 2, nibble 1, nibble 0; m swaps the first two)
+									const uint32_t i0 = scr[((tw >> 8) & 15u) * 32 + lane], i1 = scr[((tw >> 4) & 15u) * 32 + lane];
+									uint32_t *d = tst + 3 * (e0 + j - t0);
+									d[0] = swp ? i0 : i1; d[1] = swp ? i1 : i0; d[2] = scr[(tw & 15u) * 32 + lane];
+									if (KEYS && P.tcell) { const uint32_t tj = tbase + runT + e0 + j; if (tj < P.capT) P.tcell[tj] = cell; }
+								}
+							}
+							__syncwarp();
+							const uint32_t nw = 3u * min((uint32_t)EM_TW, ntot - t0);
+							const uint64_t wbase = (uint64_t)(tbase + runT + t0) * 3u, wcap = (uint64_t)P.capT * 3u;
+							for (uint32_t w = lane; w < nw; w += 32) {
+								if (wbase + w < wcap) P.T[wbase + w] = tst[w];
+								else P.totals->overflow = 1;
+							}
+							__syncwarp();
+						}
+						if (zm) cell_slow_triangles<Sample>(P, tb, x, y, z, pat, zm, vb + cl, tid, cell);
+					}
+#else
 					{
 						// Triangles of this round, one lane per TRIANGLE: each owner lane marks its
 						// slots in the round's triangle range, then lane t fetches the owner's pattern
@@ -1048,6 +1089,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 						__syncwarp();
 						if (zm) cell_slow_triangles<Sample>(P, tb, x, y, z, pat, zm, vb + cl, tid, cell);
 					}
+#endif
 					runT += tot & 0xFFFFu; runC += tot >> 16;
 				}
 				__syncwarp();

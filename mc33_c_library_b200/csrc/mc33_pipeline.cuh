@@ -498,11 +498,12 @@ SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const C
 // twice as many rows fit: a group of Ge cell rows shares its 2 (Ge + 1) point rows.
 // ---------------------------------------------------------------------------
 #define P2_EM_WARPS 8
-#define P2_R16 288                             // 16-byte record slots per warp
+#define P2_R16 240                             // 16-byte record slots per warp
+#define P2_TW 96                               // triangles per staging window
 #define P2_EM_CQ 128                           // visited cells per queue window
 #define P2_GEMAX 16                            // cell rows per group
 #define P2_SLOTS (2 * (P2_GEMAX + 1))
-#define P2_EM_WARP_BYTES (P2_R16 * 16 + P2_GEMAX * 32 + P2_SLOTS * 16 + P2_EM_CQ * 4 + 32 * 16 * 4)      // 8224
+#define P2_EM_WARP_BYTES (P2_R16 * 16 + P2_GEMAX * 32 + P2_SLOTS * 16 + P2_EM_CQ * 4 + (13 * 32 + 3 * P2_TW) * 4)      // 8224
 #define P2_EM_UNIT 2                           // groups per ticket
 
 struct EmitShape { uint32_t Ge, Ws, nseg, mNQ; };   // cell rows per (sub-)group, words per x-segment (multiple of 4), segments per row
@@ -538,9 +539,9 @@ SIMT_HD void emit_geometry(uint32_t Q, EmitArgs &A)
 	A.z = emit_shape(Q, P2_R16 / 2);
 }
 
-// position of edge id e of the cell held by `lane` in the warp's id scratch: 16 words per lane, the four
-// 16-byte chunks XOR-swizzled by the lane so that the 128-bit stores of 8 consecutive lanes hit 32 distinct banks
-SIMT_HD uint32_t scr_pos(uint32_t lane, uint32_t e) { return lane * 16u + ((((e >> 2) ^ (lane >> 1)) & 3u) << 2) + (e & 3u); }
+// position of edge id e of the cell held by `lane` in the warp's id scratch: one row of 32 words per edge, so that the
+// lanes of a warp hit 32 distinct banks whatever edges they ask for (a lane only ever reads its own column)
+SIMT_HD uint32_t scr_pos(uint32_t lane, uint32_t e) { return e * 32u + lane; }
 
 SIMT_HD uint32_t rank_of(uint32_t base, uint32_t mask, uint32_t below) { return base + (uint32_t)popc32(mask & below); }
 
@@ -661,6 +662,7 @@ SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, co
 	Rec16 *slot = reinterpret_cast<Rec16 *>(wsm + P2_R16 * 16 + P2_GEMAX * 32);      // per staged point row: {row, id base, y, flags | z << 4}
 	uint32_t *cq = reinterpret_cast<uint32_t *>(wsm + P2_R16 * 16 + P2_GEMAX * 32 + P2_SLOTS * 16);
 	uint32_t *scr = cq + P2_EM_CQ;
+	uint32_t *tst = scr + 13 * 32;                              // the round's triangles, 3 words each, before they go out as whole words
 	const unsigned lane = cx.lane();
 	const bool anyz = *P.anyZp == P.zepoch;
 	const uint32_t nShared = P.totals->nShared;
@@ -820,16 +822,9 @@ SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, co
 										}
 									}
 #if defined(__CUDA_ARCH__)
-									{
-										uint4 *d = reinterpret_cast<uint4 *>(scr + lane * 16u);
-										const uint32_t sw = (lane >> 1) & 3u;
-										d[0 ^ sw] = make_uint4(id[0], id[1], id[2], id[3]);
-										d[1 ^ sw] = make_uint4(id[4], id[5], id[6], id[7]);
-										d[2 ^ sw] = make_uint4(id[8], id[9], id[10], id[11]);
-									}
-#else
-									for (uint32_t ed = 0; ed < 12; ed++) scr[scr_pos(lane, ed)] = id[ed];
+#pragma unroll
 #endif
+									for (uint32_t ed = 0; ed < 12; ed++) scr[scr_pos(lane, ed)] = id[ed];
 								}
 								// triangle / centre offsets of the round: shuffle scan in sweep order
 								uint32_t tot;
@@ -846,31 +841,31 @@ SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, co
 									}
 								}
 								if (on) scr[scr_pos(lane, 12)] = vb + cl;
-								cx.syncwarp();
-								// ---- one lane per TRIANGLE: consecutive lanes write consecutive triangles ----
-								for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
-									const uint32_t t = t0 + lane;
-									// owner = the last cell whose first triangle is not after t (e0 is non-decreasing over the lanes)
-									uint32_t c = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-									for (uint32_t step = 16; step; step >>= 1) {
-										const uint32_t v = cx.shfl(e0, (int)(c + step));
-										if (v <= t) c += step;
-									}
-									const uint32_t csm = cx.shfl(sm, (int)c), ce0 = cx.shfl(e0, (int)c), ckeep = cx.shfl(keep, (int)c);
-									uint64_t ccell = 0;
-									if (KEYS && P.tcell) ccell = cx.shfl(cell, (int)c);
-									if (t < ntot) {
-										uint32_t j = t - ce0;
-										if (csm & 0x2000u) j = nth_bit(ckeep, j);
-										const unsigned tw = tb.tri[(csm & 0xFFFu) + j];
-										uint32_t ti[3];
-										ti[0] = scr[scr_pos(c, (tw >> 8) & 15u)];
-										ti[1] = scr[scr_pos(c, (tw >> 4) & 15u)];
-										ti[2] = scr[scr_pos(c, tw & 15u)];
-										write_triangle<KEYS>(P, tbase + runT + t, ti, (csm >> 12) & 1u, ccell);
+								// ---- triangles: every cell lane writes its own (pattern walk, ids from its own column, winding; cells with
+								// an on-iso corner skip the triangles their keep mask drops) into a shared-memory window at their positions
+								// of the round, then the warp copies the window out as consecutive words (whole-sector stores) ----
+								{
+									const bool swp = (((sm >> 12) & 1u) != 0u) != (P.geom.normal_neg != 0);
+									for (uint32_t t0 = 0; t0 < ntot; t0 += P2_TW) {
+										if (on && e0 < t0 + P2_TW && e0 + ntri > t0) {
+											const uint32_t jlo = t0 > e0 ? t0 - e0 : 0u, jhi = ntri < t0 + P2_TW - e0 ? ntri : t0 + P2_TW - e0;
+											for (uint32_t j = jlo; j < jhi; j++) {
+												const unsigned tw = tb.tri[(sm & 0xFFFu) + ((sm & 0x2000u) ? nth_bit(keep, j) : j)];
+												const uint32_t i0 = scr[scr_pos(lane, (tw >> 8) & 15u)], i1 = scr[scr_pos(lane, (tw >> 4) & 15u)];
+												uint32_t *d = tst + 3 * (e0 + j - t0);
+												// winding: marching_cubes_33.c:1246-1250 (nibble 2, nibble 1, nibble 0; m swaps the first two)
+												d[0] = swp ? i0 : i1; d[1] = swp ? i1 : i0; d[2] = scr[scr_pos(lane, tw & 15u)];
+												if (KEYS && P.tcell) { const uint32_t tj = tbase + runT + e0 + j; if (tj < P.capT) P.tcell[tj] = cell; }
+											}
+										}
+										cx.syncwarp();
+										const uint32_t nw = 3u * (ntot - t0 < (uint32_t)P2_TW ? ntot - t0 : (uint32_t)P2_TW);
+										const uint64_t wbase = (uint64_t)(tbase + runT + t0) * 3u, wcap = (uint64_t)P.capT * 3u;
+										for (uint32_t w = lane; w < nw; w += 32) {
+											if (wbase + w < wcap) P.T[wbase + w] = tst[w];
+											else P.totals->overflow = 1;
+										}
+										cx.syncwarp();
 									}
 								}
 								cx.syncwarp();

@@ -92,7 +92,8 @@ static void run(Params &P, bool emit)
 			emit_cells_body<Sample, true>(cx, P, tb, A, cx.smem() + cx.warp() * P2_EM_WARP_BYTES);
 		});
 	}
-	// K3, vertices: straight from the bitmaps (MC33_EMU_VTASK=1: the round-1 form, one task per vertex left by K4)
+	// K3, vertices: one task per vertex left by K4 (what the product launches); MC33_EMU_VTX2=1: the task-free body
+	// that rebuilds the plane masks per row group (MC33_B200_VTX=2 in the product)
 	if (P.vtask) {
 		for (uint32_t id = 0; id < P.totals->nShared && id < P.capV; id++) run_vertex_task<Sample>(P, id);
 	} else {
@@ -143,7 +144,7 @@ extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, c
 	P.anyZp = &tot.anyZ;
 	bool emit = o != nullptr;
 	std::vector<uint64_t> vtask(emit ? (size_t)o->capV + 1 : 1);
-	P.vtask = getenv("MC33_EMU_VTASK") ? vtask.data() : nullptr;
+	P.vtask = getenv("MC33_EMU_VTX2") ? nullptr : vtask.data();
 	if (emit) {
 		P.V = o->V; P.N = o->N; P.color = o->color; P.T = o->T; P.vkey = o->vkey; P.tcell = o->tcell;
 		P.capV = o->capV; P.capT = o->capT; P.vbase = o->vbase; P.vbase_next = o->vbase_next; P.dbases = o->dev_bases;

@@ -147,3 +147,14 @@ def test_kernel_bodies_lookback_over_many_blocks():
         _same(want, emu_extract(a, 2.0, "u8"))
     finally:
         del os.environ["MC33_EMU_LB_NOPREFIX"]
+
+
+def test_kernel_bodies_task_free_vertex_kernel(monkeypatch):
+    """the alternative vertex kernel body (MC33_B200_VTX=2): vertices straight from the bitmaps, no per-vertex task"""
+    monkeypatch.setenv("MC33_EMU_VTX2", "1")
+    a = noise_grid(0, "u8", scale=4, shape=(9, 11, 70))
+    _same(oracle_extract(a, 2.0, "u8"), emu_extract(a, 2.0, "u8"))
+    f = noise_grid(0, "f32", shape=(7, 9, 130))
+    _same(oracle_extract(f, 0.0, "f32"), emu_extract(f, 0.0, "f32"))
+    g = inclined_geom()
+    _same(oracle_extract(f, 0.0, "f32", g), emu_extract(f, 0.0, "f32", g))

@@ -11,20 +11,6 @@ rep, kn = sys.argv[1], sys.argv[2]
 fsel = sys.argv[3] if len(sys.argv) > 3 else "pipeline"
 minn = float(sys.argv[4]) if len(sys.argv) > 4 else 2e5
 txt = {}
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
-cur = None
-for row in csv.reader(io.StringIO(raw)):
-    if not row:
-        continue
-    if row[0] == "File Name":
-        cur = row[1].split("/")[-1]
-        continue
-    if row[0] == "Line No":
-        continue
-    try:
-        txt[(cur, int(row[0]))] = row[1]
-    except (ValueError, IndexError):
-        pass
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 blocks, cur, fpath = [], None, ""
 for row in csv.reader(io.StringIO(raw)):
@@ -55,6 +41,7 @@ for b in blocks:
         except ValueError:
             continue
         agg[(b["file"], ln)] += n
+        txt[(b["file"], ln)] = r[1]
         smp[(b["file"], ln)] += s
 tot = sum(agg.values())
 print(f"{kn}: {tot / 1e6:.1f} M warp instructions (all captured launches)")
