@@ -146,7 +146,10 @@ struct Tables {
 	const uint16_t *case256, *simple256, *tri;
 	const uint8_t *pat;           // ntri | centre << 7, at pattern starts
 	const uint32_t *cinfo;        // per case index: simple256 entry (start | ntri << 12, or 0xFFFF) | winding flag m << 16
+	const uint16_t *pord;         // [pattern start] ordinal of the pattern (0 .. MC33_NPATTERNS-1)
+	const uint16_t *keep;         // [ordinal][on-iso corner mask]: which triangles of the pattern survive the zero-area drop
 };
+#define MC33_NPATTERNS 383
 
 struct Params {
 	const void *data;             // samples of slices [zlo,zhi), x fastest

@@ -88,7 +88,7 @@ SIMT_HD unsigned index_to_zmask(unsigned i)
 
 // which triangles of the pattern survive the zero-area drop (marching_cubes_33.c:1235) for on-iso corner mask zm:
 // bit j = triangle j is kept
-MC_COLD uint32_t keep_mask(const Tables &tb, unsigned start, unsigned zm)
+MC_COLD uint32_t keep_mask_walk(const Tables &tb, unsigned start, unsigned zm)
 {
 	uint32_t keep = 0;
 	for (unsigned j = 0;; j++) {
@@ -99,6 +99,10 @@ MC_COLD uint32_t keep_mask(const Tables &tb, unsigned start, unsigned zm)
 	}
 	return keep;
 }
+
+// ... the same from the table built once per process (383 patterns x 256 corner masks): the walk above costs ~100
+// instructions with the lanes of a warp in different iterations
+SIMT_HD uint32_t keep_mask(const Tables &tb, unsigned start, unsigned zm) { return tb.keep[(uint32_t)tb.pord[start] * 256u + zm]; }
 
 // ---------------------------------------------------------------------------
 // K2: count
@@ -413,12 +417,13 @@ SIMT_FN void count_body(const CX &cx, const Params &P, const Tables &tb, const C
 				v0[k] = 0; t1[k] = 0; c2[k] = 0;
 				if (j >= 0) {
 					const unsigned long long *o = A.lb + (uint64_t)j * P2_LB_WORDS;
+					unsigned ns = 32;
 					for (;;) {
 						const unsigned long long p0 = cx.ld_acquire(&o[3]);
 						if ((p0 >> 48) == A.tag) { v0[k] = p0; t1[k] = o[4]; c2[k] = o[5]; if (dmin == 0xFFFFFFFFu) dmin = lane + 32u * (unsigned)k; break; }
 						const unsigned long long a0 = cx.ld_acquire(&o[0]);
 						if ((a0 >> 48) == A.tag) { v0[k] = a0; t1[k] = o[1]; c2[k] = o[2]; break; }
-						cx.backoff();                                // neither published yet: that block is still counting
+						cx.backoff(ns);                              // neither published yet: that block is still counting
 					}
 				}
 			}

@@ -58,7 +58,10 @@ struct DevCtx {
 		asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 		return v;
 	}
-	__device__ __forceinline__ void backoff() const { __nanosleep(20); }
+	// a predecessor has not published yet: sleep, longer every time (blocks over the surface take many times longer than
+	// empty ones, so a fast block can wait for a slow predecessor for a long time: ncu showed a quarter of the count
+	// kernel's instructions in this loop on CT-like data with a fixed 20 ns sleep)
+	__device__ __forceinline__ void backoff(unsigned &ns) const { __nanosleep(ns); if (ns < 2048u) ns <<= 1; }
 };
 typedef DevCtx SimtCtx;
 #define SIMT_FN __device__
@@ -99,7 +102,7 @@ struct EmuCtx {
 	void threadfence() const {}
 	void st_release(unsigned long long *p, unsigned long long v) const { *p = v; }
 	unsigned long long ld_acquire(const unsigned long long *p) const { return *p; }
-	void backoff() const;               // a spin that cannot make progress here is a bug: the scheduler aborts
+	void backoff(unsigned &ns) const;   // a spin that cannot make progress here is a bug: the scheduler aborts
 };
 typedef EmuCtx SimtCtx;
 #define SIMT_FN

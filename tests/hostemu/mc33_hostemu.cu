@@ -23,11 +23,22 @@ static const Tables &host_tables()
 	static Tables tb;
 	static uint8_t pat[MC33_NTRI_WORDS];
 	static uint32_t cinfo[256];
+	static uint16_t pord[MC33_NTRI_WORDS], keep[MC33_NPATTERNS * 256];
 	static bool done = false;
 	if (!done) {
 		for (int i = 0; i < MC33_NTRI_WORDS; i++) pat[i] = (uint8_t)(MC33_PAT_NTRI[i] | (MC33_PAT_CENTRE[i] << 7));
 		for (int i = 0; i < 256; i++) cinfo[i] = (uint32_t)MC33_SIMPLE256[i] | ((uint32_t)((MC33_CASE256[i] >> 11) & 1u) << 16);
 		tb.case256 = MC33_CASE256; tb.simple256 = MC33_SIMPLE256; tb.tri = MC33_TRI; tb.pat = pat; tb.cinfo = cinfo;
+		tb.pord = pord; tb.keep = keep;
+		unsigned n = 0;
+		for (int i = 0; i < MC33_NTRI_WORDS; i++) {
+			pord[i] = 0;
+			if (MC33_PAT_NTRI[i]) {
+				pord[i] = (uint16_t)n;
+				for (unsigned zm = 0; zm < 256; zm++) keep[n * 256 + zm] = (uint16_t)keep_mask_walk(tb, (unsigned)i, zm);
+				n++;
+			}
+		}
 		done = true;
 	}
 	return tb;

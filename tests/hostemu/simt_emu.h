@@ -147,7 +147,7 @@ inline uint64_t mc33::EmuCtx::collective(int kind, uint64_t v, int arg, bool cta
 {
 	return ((mc33emu::Block *)sched_)->collective(tid_, kind, v, arg, cta);
 }
-inline void mc33::EmuCtx::backoff() const
+inline void mc33::EmuCtx::backoff(unsigned &) const
 {
 	fprintf(stderr, "simt_emu: a spin loop cannot make progress here (blocks run in order)\n");
 	abort();
