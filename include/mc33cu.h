@@ -131,6 +131,10 @@ int  mc33cu_grid_rows_block(mc33cu_ctx *ctx, const void *const *const *F, const 
  * block, process wide).  The upload calls never register memory on their own; the drop-in
  * registers the grid's sample block at its first upload and releases it in free_MC33.  The
  * block must stay mapped until it is unregistered. */
+/* order what is issued on ctx's stream from now on behind everything issued so far on `after`'s stream (a CUDA
+ * event, no host wait; the two contexts may sit on different devices).  The drop-in chains the uploads of the
+ * z-chunks that share a device so that they cross the link one after the other. */
+int  mc33cu_stream_wait(mc33cu_ctx *ctx, mc33cu_ctx *after);
 int  mc33cu_host_register(const void *p, size_t bytes);
 int  mc33cu_host_unregister(const void *p);
 

@@ -38,7 +38,7 @@ class Out(C.Structure):
 EXPORTS = ["mc33cu_last_error", "mc33cu_device_count", "mc33cu_create", "mc33cu_destroy", "mc33cu_set_stream", "mc33cu_set_geometry",
            "mc33cu_grid_device", "mc33cu_grid_upload", "mc33cu_grid_upload_rows", "mc33cu_count", "mc33cu_count_async",
            "mc33cu_slab_bases", "mc33cu_slab_bases_strided", "mc33cu_emit_set_device", "mc33cu_emit_device", "mc33cu_extract_device", "mc33cu_classify_sweep", "mc33cu_count_set_async", "mc33cu_extract_set_device", "mc33cu_sync", "mc33cu_get_counts",
-           "mc33cu_emit_host", "mc33cu_emit_host_async", "mc33cu_grid_upload_async", "mc33cu_grid_upload_rows_async", "mc33cu_grid_rows_block", "mc33cu_host_register", "mc33cu_host_unregister", "mc33cu_host_alloc", "mc33cu_host_free", "mc33cu_enable_timing", "mc33cu_kernel_times", "mc33cu_launch_count"]
+           "mc33cu_emit_host", "mc33cu_emit_host_async", "mc33cu_grid_upload_async", "mc33cu_grid_upload_rows_async", "mc33cu_grid_rows_block", "mc33cu_host_register", "mc33cu_host_unregister", "mc33cu_host_alloc", "mc33cu_host_free", "mc33cu_enable_timing", "mc33cu_kernel_times", "mc33cu_launch_count", "mc33cu_stream_wait"]
 
 _lib = None
 

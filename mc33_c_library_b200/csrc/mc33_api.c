@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "mc33_internal.h"
 #include "../../include/mc33cu.h"
@@ -52,19 +53,25 @@ int DefaultColorMC = (int)DEFAULT_SURFACE_COLOR;
  * the per-slab counts exchanged through the host -- they are needed there anyway to size the
  * surface.  Every GPU pulls its slab over its own PCIe link and pushes its part of the mesh
  * straight into the final host arrays. */
-#define MC33_MAX_SLABS 16
+#define MC33_MAX_SLABS 64
 typedef struct {
 	MC33 pub;
 	int nslab;
 	mc33cu_ctx *ctx[MC33_MAX_SLABS];
+	int dev[MC33_MAX_SLABS];     /* device of every slab */
+	int ngpu;                    /* distinct devices in use */
 	int grid_uploaded;
 	const void *registered;      /* the grid's sample block, page-locked by us at the first upload */
 	int reg_tried;
+	/* largest mesh this extractor has produced so far: sizes the result arrays of the next call before
+	 * its counts are complete (calculate_isosurface) */
+	unsigned long long hist_nV, hist_nT;
 } mc33_private;
 
-static int g_last_nslab = 0;
-/* how many GPUs the most recently created MC33 uses (reporting hook of bench.py) */
-int mc33_dropin_gpus_last(void) { return g_last_nslab; }
+static int g_last_ngpu = 0, g_last_nslab = 0;
+/* how many GPUs / z-slabs the most recently created MC33 uses (reporting hooks of bench.py) */
+int mc33_dropin_gpus_last(void) { return g_last_ngpu; }
+int mc33_dropin_slabs_last(void) { return g_last_nslab; }
 
 /* ------------------------------------------------------------------------- */
 /* 3x3 helpers: reference MC33_util_grd.c:86-121                              */
@@ -404,21 +411,39 @@ MC33 *create_MC33(_GRD *G)
 	M->F = (const GRD_data_type ***)G->F;
 	if (!M->nx || !M->ny || !M->nz) { free(p); return 0; }
 	/* how many GPUs: MC33_B200_GPUS (default: all visible), never more than cell layers; without an
-	 * explicit request a slab is not made smaller than 64 MB of samples (below that the per-call
+	 * explicit request a GPU's share is not made smaller than 64 MB of samples (below that the per-call
 	 * overheads of one more device outweigh its share of the copy) */
+	const double bytes = ((double)M->nx + 1) * ((double)M->ny + 1) * ((double)M->nz + 1) * sizeof(GRD_data_type);
 	int ndev = mc33cu_device_count(), want = ndev;
 	const char *e = getenv("MC33_B200_GPUS");
 	if (e && atoi(e) > 0) want = atoi(e);
 	else {
-		const double bytes = ((double)M->nx + 1) * ((double)M->ny + 1) * ((double)M->nz + 1) * sizeof(GRD_data_type);
 		const int by_size = (int)(bytes / (64.0 * 1024 * 1024));
 		if (want > by_size) want = by_size;
 	}
 	if (want > ndev) want = ndev;
-	/* MC33_B200_DEVICES="2,3" names the device of every slab explicitly (a device may appear more than
-	 * once: slabs are independent contexts) and overrides the count above */
+	if (want > MC33_MAX_SLABS) want = MC33_MAX_SLABS;
+	if (want < 1) want = 1;
+	/* z-chunks per GPU (MC33_B200_CHUNKS, default: about 128 MB of samples each, at most 8): the link is the
+	 * bottleneck of a call (the samples go up, the mesh comes down), so a GPU's share is cut further and its
+	 * chunks are uploaded one after the other -- chunk k is counted, emitted and its part of the mesh
+	 * downloaded while chunk k+1 is still arriving (PCIe is full duplex).  Chunks are dealt round-robin:
+	 * slab i sits on GPU i % ngpu, so that all GPUs advance through z together and the vertex base of a slab
+	 * (the counts of every slab below it) is known as early as possible. */
+	int chunks = 1;
+	const char *ce = getenv("MC33_B200_CHUNKS");
+	if (ce && atoi(ce) > 0) chunks = atoi(ce);
+	else {
+		chunks = (int)(bytes / want / (128.0 * 1024 * 1024));
+		if (chunks > 8) chunks = 8;
+	}
+	if (chunks < 1) chunks = 1;
+	if (want * chunks > MC33_MAX_SLABS) chunks = MC33_MAX_SLABS / want;
+	int nslab = want * chunks;
 	int devs[MC33_MAX_SLABS];
-	for (int i = 0; i < MC33_MAX_SLABS; i++) devs[i] = i;
+	for (int i = 0; i < MC33_MAX_SLABS; i++) devs[i] = i % want;
+	/* MC33_B200_DEVICES="2,3" names the device of every slab explicitly (a device may appear more than
+	 * once: slabs are independent contexts) and overrides the two counts above */
 	const char *dl = getenv("MC33_B200_DEVICES");
 	if (dl && *dl) {
 		int n = 0;
@@ -429,14 +454,13 @@ MC33 *create_MC33(_GRD *G)
 			devs[n++] = (int)v;
 			q = *end == ',' ? end + 1 : end;
 		}
-		if (n > 0) want = n;
+		if (n > 0) nslab = n;
 	}
-	if (want > MC33_MAX_SLABS) want = MC33_MAX_SLABS;
-	if ((unsigned int)want > M->nz) want = (int)M->nz;
-	if (want < 1) want = 1;
-	for (int i = 0; i < want; i++) {
+	if ((unsigned int)nslab > M->nz) nslab = (int)M->nz;
+	if (nslab < 1) nslab = 1;
+	for (int i = 0; i < nslab; i++) {
 		mc33cu_desc d;
-		describe(M, &d, i, want);
+		describe(M, &d, i, nslab);
 		if (d.tsa < 0) d.tsa = 0;
 		if (mc33cu_create(&d, devs[i], &p->ctx[i]) != MC33CU_OK) {
 			if (getenv("MC33_B200_VERBOSE")) fprintf(stderr, "create_MC33: %s\n", mc33cu_last_error());
@@ -444,8 +468,16 @@ MC33 *create_MC33(_GRD *G)
 			free(p);
 			return 0;
 		}
+		p->dev[i] = devs[i];
 		p->nslab = i + 1;
 	}
+	p->ngpu = 0;
+	for (int i = 0; i < p->nslab; i++) {
+		int seen = 0;
+		for (int j = 0; j < i; j++) seen |= p->dev[j] == p->dev[i];
+		p->ngpu += !seen;
+	}
+	g_last_ngpu = p->ngpu;
 	g_last_nslab = p->nslab;
 	return M;
 }
@@ -462,9 +494,10 @@ static const void *whole_block(const MC33 *M, size_t *bytes)
 	return first;
 }
 
-/* shared front half of calculate_isosurface / size_of_isosurface: bring the samples to the
- * devices and count; k[i] = counts of slab i, *tot = their sums */
-static int count_on_devices(MC33 *M, MC33_real iso, mc33cu_counts *k, mc33cu_counts *tot)
+/* shared front half of calculate_isosurface / size_of_isosurface: start the upload of every slab and its
+ * count behind it; nothing waits here.  Slabs that share a device upload one after the other (each
+ * slab's copy is chained behind the previous one's), so slab k is counted while slab k+1 arrives. */
+static int start_counts(MC33 *M, MC33_real iso)
 {
 	mc33_private *p = (mc33_private *)M;
 	int rc;
@@ -478,43 +511,61 @@ static int count_on_devices(MC33 *M, MC33_real iso, mc33cu_counts *k, mc33cu_cou
 	/* The reference reads the samples at calculate time (c:1792, c:1820), so they are uploaded on
 	 * every call; MC33_B200_CACHE_GRID=1 promises they do not change between calls on the same MC33
 	 * and uploads them once.  A grid that is one block is page-locked at its first upload (DMA at
-	 * link speed, all slabs in flight together) and released in free_MC33: G and its samples must
+	 * link speed, all GPUs in flight together) and released in free_MC33: G and its samples must
 	 * outlive M, as for the reference (M borrows G->F, c:1792).  MC33_B200_NO_PIN=1 turns that off. */
 	const char *cache = getenv("MC33_B200_CACHE_GRID");
-	if (!(p->grid_uploaded && cache && cache[0] == '1')) {
-		if (!p->reg_tried) {
-			p->reg_tried = 1;
-			size_t bytes = 0;
-			const void *blk = getenv("MC33_B200_NO_PIN") ? 0 : whole_block(M, &bytes);
-			if (blk && mc33cu_host_register(blk, bytes) == MC33CU_OK) p->registered = blk;
-		}
-		for (int i = 0; i < p->nslab; i++) {
-			rc = mc33cu_grid_upload_rows_async(p->ctx[i], (const void *const *const *)M->F);
-			if (rc) return rc;
-		}
-		p->grid_uploaded = 1;
+	const int upload = !(p->grid_uploaded && cache && cache[0] == '1');
+	if (upload && !p->reg_tried) {
+		p->reg_tried = 1;
+		size_t bytes = 0;
+		const void *blk = getenv("MC33_B200_NO_PIN") ? 0 : whole_block(M, &bytes);
+		if (blk && mc33cu_host_register(blk, bytes) == MC33CU_OK) p->registered = blk;
 	}
 	M->iso = iso;
 	for (int i = 0; i < p->nslab; i++) {
+		if (upload) {
+			rc = mc33cu_grid_upload_rows_async(p->ctx[i], (const void *const *const *)M->F);
+			if (rc) return rc;
+			for (int j = i + 1; j < p->nslab; j++)
+				if (p->dev[j] == p->dev[i]) {          /* the next slab of this device: its copy follows this one */
+					rc = mc33cu_stream_wait(p->ctx[j], p->ctx[i]);
+					if (rc) return rc;
+					break;
+				}
+		}
 		rc = mc33cu_count_async(p->ctx[i], (double)iso, 0);
 		if (rc) return rc;
 	}
-	memset(tot, 0, sizeof *tot);
-	for (int i = 0; i < p->nslab; i++) {
-		rc = mc33cu_sync(p->ctx[i]);
-		if (rc) return rc;
-		rc = mc33cu_get_counts(p->ctx[i], &k[i]);
-		if (rc) return rc;
-		tot->nV += k[i].nV; tot->nT += k[i].nT; tot->nShared += k[i].nShared; tot->nCentre += k[i].nCentre;
-	}
-	if (tot->nV >= 0xFFFFFFFFull || tot->nT >= 0xFFFFFFFFull) return MC33CU_ERR_RANGE;   /* unsigned int indices, h:140 */
+	if (upload) p->grid_uploaded = 1;
 	return MC33CU_OK;
+}
+
+/* wait for the count of slab i and fetch it */
+static int slab_counts(mc33_private *p, int i, mc33cu_counts *k)
+{
+	int rc = mc33cu_sync(p->ctx[i]);
+	if (rc) return rc;
+	return mc33cu_get_counts(p->ctx[i], k);
+}
+
+static void drain(mc33_private *p)
+{
+	for (int i = 0; i < p->nslab; i++) mc33cu_sync(p->ctx[i]);
 }
 
 unsigned long long size_of_isosurface(MC33 *M, MC33_real iso, unsigned int *nV, unsigned int *nT)
 {
-	mc33cu_counts ks[MC33_MAX_SLABS], k;
-	if (!M || count_on_devices(M, iso, ks, &k) != MC33CU_OK) {
+	mc33_private *p = (mc33_private *)M;
+	mc33cu_counts k, ki;
+	memset(&k, 0, sizeof k);
+	int rc = M ? start_counts(M, iso) : MC33CU_ERR_ARG;
+	for (int i = 0; rc == MC33CU_OK && i < p->nslab; i++) {
+		rc = slab_counts(p, i, &ki);
+		k.nV += ki.nV; k.nT += ki.nT;
+	}
+	if (rc == MC33CU_OK && (k.nV >= 0xFFFFFFFFull || k.nT >= 0xFFFFFFFFull)) rc = MC33CU_ERR_RANGE;   /* unsigned int indices, h:140 */
+	if (rc != MC33CU_OK) {
+		if (M) drain(p);
 		if (nV) *nV = 0;
 		if (nT) *nT = 0;
 		return 0;
@@ -526,50 +577,158 @@ unsigned long long size_of_isosurface(MC33 *M, MC33_real iso, unsigned int *nV, 
 	return k.nV * (6 * sizeof(MC33_real) + sizeof(int)) + k.nT * (3 * sizeof(int)) + sizeof(surface);
 }
 
+/* estimated capacities are rounded up to four steps per octave, so that the calls of an iso sweep ask the
+ * page-locked pool for the same few block sizes again and again */
+static unsigned long long round_cap(unsigned long long n)
+{
+	unsigned long long step = 1;
+	while (step * 8 <= n) step *= 2;               /* step = 2^(floor(log2 n) - 2) */
+	return (n + step - 1) / step * step;
+}
+
+static int alloc_result(surface *S, unsigned long long capv, unsigned long long capt)
+{
+	if (capv > 0xFFFFFFFFull) capv = 0xFFFFFFFFull;
+	if (capt > 0xFFFFFFFFull) capt = 0xFFFFFFFFull;
+	if (!capt) capt = 1;
+	S->capv = (unsigned int)capv; S->capt = (unsigned int)capt;
+	S->T = (unsigned int (*)[3])mc33_result_alloc((size_t)capt * 3 * sizeof(int));
+	S->V = (MC33_real (*)[3])mc33_result_alloc((size_t)capv * 3 * sizeof(MC33_real));
+	S->N = (float (*)[3])mc33_result_alloc((size_t)capv * 3 * sizeof(float));
+	S->color = (int *)mc33_result_alloc((size_t)capv * sizeof(int));
+	return S->T && S->V && S->N && S->color ? 0 : -1;
+}
+
+/* how much room the result arrays get when they must be sized before every slab has been counted: what the
+ * extractor has seen so far on this grid (an iso sweep), else the slabs counted so far scaled to the whole grid,
+ * with head room (capv / capt > nV / nT, as after the reference's block-wise growth, c:489-510).
+ * MC33_B200_SPECULATE=<factor> changes the head room (default 1.5); 0 waits for all the counts instead. */
+/* MC33_B200_TRACE=1: host-clock time line of a call on stderr (when each slab's count was in, when the call ended) */
+static double now_ms(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
+static double speculate_factor(void)
+{
+	const char *e = getenv("MC33_B200_SPECULATE");
+	return e && *e ? atof(e) : 1.5;
+}
+
 surface *calculate_isosurface(MC33 *M, MC33_real iso)
 {
 	if (!M) return 0;
 	mc33_private *p = (mc33_private *)M;
 	surface *S = (surface *)calloc(1, sizeof(surface));
 	if (!S) return 0;
-	mc33cu_counts ks[MC33_MAX_SLABS], k;
+	mc33cu_counts ks[MC33_MAX_SLABS];
 	M->memoryfault = 0;
-	int rc = count_on_devices(M, iso, ks, &k);
+	const int trace = getenv("MC33_B200_TRACE") != 0;
+	const double t_begin = trace ? now_ms() : 0;
+	int rc = start_counts(M, iso);
+	if (trace) fprintf(stderr, "[mc33 trace] iso %g: %d slab(s) started at +%.3f ms\n", (double)iso, p->nslab, now_ms() - t_begin);
+	/* Slab i's vertices are [vb, vb + nV_i) and its triangles [tb, tb + nT_i) of the result (the running nV / nT of
+	 * the reference's sweep, c:487, c:1245, across slabs); every device writes its range straight into the final host
+	 * arrays.  A slab's place only depends on the slabs below it, so it is emitted as soon as it has been counted
+	 * -- while the slabs above it are still being uploaded -- into arrays sized from an estimate; slabs that do
+	 * not fit the estimate wait until every count is in, the arrays are replaced by exact ones (the part already
+	 * there is copied over) and the rest follows. */
+	const double fac = speculate_factor();
+	unsigned long long vb = 0, tb = 0;             /* totals of the slabs counted so far */
+	unsigned long long dvb = 0, dtb = 0;           /* ... of the slabs emitted so far */
+	int first_deferred = -1, allocated = 0;
+	for (int i = 0; rc == MC33CU_OK && i < p->nslab; i++) {
+		rc = slab_counts(p, i, &ks[i]);
+		if (rc != MC33CU_OK) break;
+		if (trace) fprintf(stderr, "[mc33 trace]   slab %d counted at +%.3f ms (nV %llu nT %llu)\n", i, now_ms() - t_begin,
+		                   (unsigned long long)ks[i].nV, (unsigned long long)ks[i].nT);
+		const unsigned long long nvb = vb + ks[i].nV, ntb = tb + ks[i].nT;
+		if (nvb >= 0xFFFFFFFFull || ntb >= 0xFFFFFFFFull) { rc = MC33CU_ERR_RANGE; break; }   /* unsigned int indices, h:140 */
+		if (first_deferred < 0 && ks[i].nV) {
+			if (!allocated) {
+				unsigned long long cv, ct;
+				if (i == p->nslab - 1) { cv = nvb; ct = ntb; }                /* everything is known: exact */
+				else if (fac <= 0) cv = ct = 0;
+				else {
+					const double up = (double)p->nslab / (i + 1);
+					const double ev = (double)nvb * up, et = (double)ntb * up;
+					cv = round_cap((unsigned long long)(fac * ((double)p->hist_nV > ev ? (double)p->hist_nV : ev)) + 1024);
+					ct = round_cap((unsigned long long)(fac * ((double)p->hist_nT > et ? (double)p->hist_nT : et)) + 1024);
+				}
+				if (cv >= nvb && ct >= ntb) {
+					if (alloc_result(S, cv, ct)) { rc = MC33CU_ERR_NOMEM; break; }
+					allocated = 1;
+				}
+			}
+			if (allocated && nvb <= S->capv && ntb <= S->capt) {
+				rc = mc33cu_emit_host_async(p->ctx[i], &S->V[vb], (float *)&S->N[vb], S->color + vb, (unsigned int *)&S->T[tb],
+				                            (uint32_t)vb, (uint32_t)nvb, DefaultColorMC);
+				if (rc != MC33CU_OK) break;
+				if (trace) fprintf(stderr, "[mc33 trace]   slab %d emit issued at +%.3f ms\n", i, now_ms() - t_begin);
+				dvb = nvb; dtb = ntb;
+			} else {
+				first_deferred = i;
+			}
+		}
+		vb = nvb; tb = ntb;
+	}
 	if (rc != MC33CU_OK) goto fail;
-	if (k.nV == 0) {
+	if (vb == 0) {
 		/* empty isosurface: zero-filled struct, iso included (reference c:1880-1883) */
+		drain(p);
 		M->nV = M->nT = 0;
 		return S;
 	}
-	S->nV = (unsigned int)k.nV; S->nT = (unsigned int)k.nT;
-	S->capv = S->nV; S->capt = S->nT ? S->nT : 1;
-	S->iso = iso;
-	S->T = (unsigned int (*)[3])mc33_result_alloc((size_t)S->capt * 3 * sizeof(int));
-	S->V = (MC33_real (*)[3])mc33_result_alloc((size_t)S->capv * 3 * sizeof(MC33_real));
-	S->N = (float (*)[3])mc33_result_alloc((size_t)S->capv * 3 * sizeof(float));
-	S->color = (int *)mc33_result_alloc((size_t)S->capv * sizeof(int));
-	if (!S->T || !S->V || !S->N || !S->color) goto fail;
-	{
-		/* slab i's vertices are [vb, vb + nV_i) and its triangles [tb, tb + nT_i) of the result (the running nV / nT
-		 * of the reference's sweep, c:487, c:1245, across slabs); every device writes its range in place */
-		size_t vb = 0, tb = 0;
-		for (int i = 0; i < p->nslab; i++) {
-			rc = mc33cu_emit_host_async(p->ctx[i], &S->V[vb], (float *)&S->N[vb], S->color + vb, (unsigned int *)&S->T[tb],
-			                            (uint32_t)vb, (uint32_t)(vb + ks[i].nV), DefaultColorMC);
+	if (first_deferred >= 0) {
+		/* the estimate was too small (or there was none): exact arrays now, the part already downloaded moves over */
+		surface old = *S;
+		if (alloc_result(S, vb, tb)) {
+			rc = MC33CU_ERR_NOMEM;
+			drain(p);
+			if (allocated) { mc33_result_free(old.T); mc33_result_free(old.V); mc33_result_free(old.N); mc33_result_free(old.color); }
+			goto fail;
+		}
+		if (allocated) {
+			for (int i = 0; i < first_deferred; i++) {
+				const int r2 = mc33cu_sync(p->ctx[i]);
+				if (r2 != MC33CU_OK) rc = r2;
+			}
+			memcpy(S->V, old.V, (size_t)dvb * 3 * sizeof(MC33_real));
+			memcpy(S->N, old.N, (size_t)dvb * 3 * sizeof(float));
+			memcpy(S->color, old.color, (size_t)dvb * sizeof(int));
+			memcpy(S->T, old.T, (size_t)dtb * 3 * sizeof(int));
+			mc33_result_free(old.T); mc33_result_free(old.V); mc33_result_free(old.N); mc33_result_free(old.color);
 			if (rc != MC33CU_OK) goto fail;
-			vb += ks[i].nV; tb += ks[i].nT;
 		}
+		unsigned long long v0 = 0, t0 = 0;
 		for (int i = 0; i < p->nslab; i++) {
-			const int r2 = mc33cu_sync(p->ctx[i]);
-			if (r2 != MC33CU_OK) rc = r2;
+			if (i >= first_deferred && ks[i].nV) {
+				rc = mc33cu_emit_host_async(p->ctx[i], &S->V[v0], (float *)&S->N[v0], S->color + v0, (unsigned int *)&S->T[t0],
+				                            (uint32_t)v0, (uint32_t)(v0 + ks[i].nV), DefaultColorMC);
+				if (rc != MC33CU_OK) goto fail;
+			}
+			v0 += ks[i].nV; t0 += ks[i].nT;
 		}
-		if (rc != MC33CU_OK) goto fail;
 	}
+	for (int i = 0; i < p->nslab; i++) {
+		const int r2 = mc33cu_sync(p->ctx[i]);
+		if (r2 != MC33CU_OK) rc = r2;
+	}
+	if (rc != MC33CU_OK) goto fail;
+	if (trace) fprintf(stderr, "[mc33 trace]   done at +%.3f ms (capv %u capt %u, first deferred slab %d)\n", now_ms() - t_begin,
+	                   S->capv, S->capt, first_deferred);
+	S->nV = (unsigned int)vb; S->nT = (unsigned int)tb;
+	S->iso = iso;
+	if (vb > p->hist_nV) p->hist_nV = vb;
+	if (tb > p->hist_nT) p->hist_nT = tb;
 	/* the MC33 mirrors the surface head, as in the reference (c:1873) */
 	memcpy(M, S, offsetof(MC33, memoryfault));
 	return S;
 fail:
 	if (getenv("MC33_B200_VERBOSE")) fprintf(stderr, "calculate_isosurface: %s\n", mc33cu_last_error());
+	drain(p);                    /* nothing may still be writing into the arrays that are about to be released */
 	M->memoryfault = 1;
 	free_surface_memory(S);
 	return 0;

@@ -38,6 +38,9 @@ using namespace mc33;
 
 // one image: case256 | simple256 | tri | pat | cinfo, copied to shared memory with 16-byte loads
 __device__ __align__(16) unsigned char d_tables[TBL_BYTES];
+// pattern ordinals and the keep masks of every (pattern, on-iso corner mask): read in place (only cells with an on-iso corner)
+__device__ uint16_t d_pord[MC33_NTRI_WORDS];
+__device__ uint16_t d_keep[MC33_NPATTERNS * 256];
 
 // the same tables read in place (kernels that only index them on cold paths)
 __device__ __forceinline__ Tables global_tables()
@@ -48,6 +51,7 @@ __device__ __forceinline__ Tables global_tables()
 	tb.tri = tb.simple256 + 256;
 	tb.pat = (const uint8_t *)tb.tri + TBL_TRI_BYTES;
 	tb.cinfo = (const uint32_t *)(tb.pat + TBL_PAT_BYTES);
+	tb.pord = d_pord; tb.keep = d_keep;
 	return tb;
 }
 
@@ -64,6 +68,7 @@ __device__ __forceinline__ Tables load_tables2(unsigned char *smem)
 	tb.tri = (const uint16_t *)smem;
 	tb.pat = (const uint8_t *)smem + TBL_TRI_BYTES;
 	tb.cinfo = (const uint32_t *)(smem + TBL_TRI_BYTES + TBL_PAT_BYTES);
+	tb.pord = d_pord; tb.keep = d_keep;
 	return tb;
 }
 
@@ -79,6 +84,7 @@ __device__ __forceinline__ Tables load_tables(unsigned char *smem)
 	tb.tri = tb.simple256 + 256;
 	tb.pat = (const uint8_t *)tb.tri + TBL_TRI_BYTES;
 	tb.cinfo = (const uint32_t *)(tb.pat + TBL_PAT_BYTES);
+	tb.pord = d_pord; tb.keep = d_keep;
 	return tb;
 }
 
@@ -1159,6 +1165,7 @@ struct mc33cu_ctx {
 	void *grid_owned;        // device copy made by the upload calls
 	// second stream: the triangle download of mc33cu_emit_host_async runs on it next to the vertex kernel
 	cudaStream_t copy_stream; cudaEvent_t ev_cells, ev_copy; bool copy_pending;
+	cudaEvent_t ev_chain;    // mc33cu_stream_wait: "everything issued on this context's stream so far"
 	uint32_t *dlT; uint64_t dlT_words;     // where the triangles go on the host (set by mc33cu_emit_host_async for one emit)
 	void *pinned; size_t pinned_bytes;   // staging for row-wise uploads
 	// k_count blocks (CNT_WARPS * G rows each) and their (V, T, C) sums
@@ -1235,6 +1242,24 @@ static int upload_tables()
 	uint32_t *cinfo = (uint32_t *)(pat + TBL_PAT_BYTES);
 	for (int i = 0; i < 256; i++) cinfo[i] = (uint32_t)MC33_SIMPLE256[i] | ((uint32_t)((MC33_CASE256[i] >> 11) & 1u) << 16);
 	CU(cudaMemcpyToSymbol(d_tables, img, sizeof img));
+	{
+		// keep masks: the zero-area drop (marching_cubes_33.c:1235) of every pattern under every on-iso corner mask
+		static uint16_t pord[MC33_NTRI_WORDS], keep[MC33_NPATTERNS * 256];
+		Tables tb;
+		tb.case256 = MC33_CASE256; tb.simple256 = MC33_SIMPLE256; tb.tri = MC33_TRI; tb.pat = pat; tb.cinfo = cinfo; tb.pord = pord; tb.keep = keep;
+		unsigned n = 0;
+		for (int i = 0; i < MC33_NTRI_WORDS; i++) {
+			pord[i] = 0;
+			if (MC33_PAT_NTRI[i] && n < MC33_NPATTERNS) {
+				pord[i] = (uint16_t)n;
+				for (unsigned zm = 0; zm < 256; zm++) keep[n * 256 + zm] = (uint16_t)keep_mask_walk(tb, (unsigned)i, zm);
+				n++;
+			}
+		}
+		if (n != MC33_NPATTERNS) return fail(MC33CU_ERR_ARG, "pattern table: unexpected number of patterns");
+		CU(cudaMemcpyToSymbol(d_pord, pord, sizeof pord));
+		CU(cudaMemcpyToSymbol(d_keep, keep, sizeof keep));
+	}
 	return MC33CU_OK;
 }
 
@@ -1263,6 +1288,7 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
 	if (c->ev_cells) cudaEventDestroy(c->ev_cells);
 	if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+	if (c->ev_chain) cudaEventDestroy(c->ev_chain);
 	cudaFree(c->oV); cudaFree(c->oN); cudaFree(c->oC); cudaFree(c->oT);
 	if (c->pinned) cudaFreeHost(c->pinned);
 	if (c->h_all) cudaFreeHost(c->h_all);
@@ -1511,9 +1537,10 @@ extern "C" int mc33cu_grid_upload_async(mc33cu_ctx *c, const void *host) { retur
 #include <mutex>
 #include <vector>
 namespace {
-struct HostBlock { void *p; size_t cap; bool used; };
+struct HostBlock { void *p; size_t cap; bool used; uint64_t stamp; };    // stamp: when the block was handed back
 std::mutex g_pool_mx;
 std::vector<HostBlock> g_pool;
+uint64_t g_pool_clock = 0;
 const size_t POOL_MAX_FREE = 16;
 }
 
@@ -1530,11 +1557,11 @@ extern "C" int mc33cu_host_alloc(size_t bytes, void **out)
 	if (best >= 0) { g_pool[(size_t)best].used = true; *out = g_pool[(size_t)best].p; return MC33CU_OK; }
 	const size_t cap = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
 	void *p = nullptr;
-	if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+	if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) {
 		cudaGetLastError();
 		return fail(MC33CU_ERR_NOMEM, "cudaHostAlloc failed");
 	}
-	g_pool.push_back({p, cap, true});
+	g_pool.push_back({p, cap, true, 0});
 	*out = p;
 	return MC33CU_OK;
 }
@@ -1544,17 +1571,22 @@ extern "C" int mc33cu_host_free(void *p)
 	if (!p) return MC33CU_OK;
 	std::lock_guard<std::mutex> lk(g_pool_mx);
 	size_t nfree = 0;
-	int found = -1;
+	int found = -1, oldest = -1;
 	for (size_t i = 0; i < g_pool.size(); i++) {
 		if (g_pool[i].p == p) found = (int)i;
-		else if (!g_pool[i].used) nfree++;
+		else if (!g_pool[i].used) {
+			nfree++;
+			if (oldest < 0 || g_pool[i].stamp < g_pool[(size_t)oldest].stamp) oldest = (int)i;
+		}
 	}
 	if (found < 0) return MC33CU_ERR_ARG;               // not ours: the caller frees it with free()
+	g_pool[(size_t)found].used = false;
+	g_pool[(size_t)found].stamp = ++g_pool_clock;
 	if (nfree >= POOL_MAX_FREE) {
-		cudaFreeHost(p);
-		g_pool.erase(g_pool.begin() + found);
-	} else {
-		g_pool[(size_t)found].used = false;
+		// too many idle blocks: release the one that has been idle longest (sizes no caller asks for any more must
+		// not crowd out the sizes in use -- page-locking a fresh block costs ~0.3 ms per MB)
+		cudaFreeHost(g_pool[(size_t)oldest].p);
+		g_pool.erase(g_pool.begin() + oldest);
 	}
 	return MC33CU_OK;
 }
@@ -2328,6 +2360,21 @@ extern "C" int mc33cu_emit_host_async(mc33cu_ctx *c, void *V, float *N, int32_t 
                                       uint32_t vbase_next, int32_t color_value)
 {
 	return emit_host_impl(c, V, N, color, T, vbase, vbase_next, color_value, false);
+}
+
+// Order what is issued on c's stream from now on behind everything issued so far on `after`'s stream (an event: the
+// host does not wait).  The drop-in chains the uploads of the z-chunks that share a device, so that they cross the
+// link one after the other and chunk k is counted, emitted and downloaded while chunk k+1 is still arriving.
+extern "C" int mc33cu_stream_wait(mc33cu_ctx *c, mc33cu_ctx *after)
+{
+	if (!c || !after) return fail(MC33CU_ERR_ARG, "null context");
+	if (c == after) return MC33CU_OK;
+	CU(cudaSetDevice(after->device));
+	if (!after->ev_chain) CU(cudaEventCreateWithFlags(&after->ev_chain, cudaEventDisableTiming));
+	CU(cudaEventRecord(after->ev_chain, after->stream));
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamWaitEvent(c->stream, after->ev_chain, 0));
+	return MC33CU_OK;
 }
 
 extern "C" int mc33cu_enable_timing(mc33cu_ctx *c, int on)

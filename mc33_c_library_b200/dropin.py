@@ -168,6 +168,28 @@ class MC33Lib:
             self.set_tsa(0)
         return mesh
 
+    def extract_many(self, data, isos, geom=None):
+        """several calculate_isosurface calls on ONE MC33 (an iso sweep through the reference API) -> list of Mesh"""
+        G, data = self.make_grid(data, geom)
+        M = self.lib.create_MC33(G)
+        assert M
+        out = []
+        for iso in isos:
+            S = self.lib.calculate_isosurface(M, self.real_c(iso))
+            assert S, "calculate_isosurface returned NULL"
+            s = S.contents
+            nV, nT = int(s.nV), int(s.nT)
+            assert int(s.capv) >= nV and int(s.capt) >= nT
+            mesh = Mesh(_np_from(s.V, nV, self.real, (nV, 3)), _np_from(s.N, nV, np.float32, (nV, 3)),
+                        _np_from(s.T, nT, np.uint32, (nT, 3)), color=_np_from(s.color, nV, np.int32, (nV,)))
+            mesh.iso = float(s.iso)
+            mesh.capv, mesh.capt = int(s.capv), int(s.capt)
+            out.append(mesh)
+            self.lib.free_surface_memory(S)
+        self.lib.free_MC33(M)
+        self.lib.free_memory_grd(G)
+        return out
+
     def size(self, data, iso, geom=None):
         G, data = self.make_grid(data, geom)
         M = self.lib.create_MC33(G)

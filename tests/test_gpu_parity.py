@@ -627,7 +627,8 @@ def test_dropin_multi_slab_matches_single_slab_and_the_oracle(variant, iso, scal
     monkeypatch.setenv("MC33_B200_DEVICES", ",".join(str(i % ndev) for i in range(nslab)))      # one slab per GPU where there are several
     lib = dropin(variant)
     many = lib.extract(a, iso)
-    assert lib.lib.mc33_dropin_gpus_last() == nslab
+    assert lib.lib.mc33_dropin_slabs_last() == nslab
+    assert lib.lib.mc33_dropin_gpus_last() == min(nslab, ndev)
     assert (many.nV, many.nT) == (one.nV, one.nT)
     # same triangles in the same order; the vertex numbering differs (per slab: shared vertices, then centres), so
     # corner k of triangle j induces the id map, which must be a bijection carrying positions / normals / colours over
@@ -645,3 +646,47 @@ def test_dropin_multi_slab_matches_single_slab_and_the_oracle(variant, iso, scal
         sorted(map(tuple, np.round(np.delete(many.V, fwd[used], axis=0).astype(np.float64), 5)))
     sz, nV, nT = lib.size(a, iso)
     assert (nV, nT) == (one.nV, one.nT)
+
+
+def _same_mesh_up_to_slab_numbering(one, many):
+    assert (many.nV, many.nT) == (one.nV, one.nT)
+    if one.nT == 0:
+        return
+    fwd = np.full(one.nV, -1, np.int64)
+    fwd[one.T.reshape(-1).astype(np.int64)] = many.T.reshape(-1).astype(np.int64)
+    used = fwd >= 0
+    assert np.array_equal(fwd[one.T.reshape(-1).astype(np.int64)], many.T.reshape(-1).astype(np.int64))
+    assert len(np.unique(fwd[used])) == used.sum()
+    assert np.array_equal(one.V[used], many.V[fwd[used]])
+    fa = np.isfinite(one.N[used])
+    assert np.array_equal(np.where(fa, one.N[used], 0), np.where(fa, many.N[fwd[used]], 0))
+    assert (many.color == -10724260).all()
+
+
+@pytest.mark.parametrize("spec,chunks", [("1.5", 4), ("0", 4), ("0.4", 5), ("1.5", 1), ("3", 7)])
+def test_dropin_chunked_upload_and_result_arrays_sized_from_an_estimate(spec, chunks, monkeypatch):
+    """MC33_B200_CHUNKS z-chunks per GPU: a chunk is emitted as soon as it has been counted, into result arrays sized
+    before the counts are complete (from the slabs counted so far / the meshes this MC33 produced before).  Head room 0
+    waits for all the counts (the round-1 flow), 0.4 makes every estimate too small (the arrays are replaced by exact
+    ones and the part already downloaded is carried over); the sphere puts nothing into the first chunks, so the
+    extrapolation starts late.  Several isovalues on ONE MC33, growing and shrinking meshes."""
+    a = noise_grid(0, "f32", shape=(40, 24, 97))
+    zz, yy, xx = np.meshgrid(*(np.arange(n, dtype=np.float32) for n in a.shape), indexing="ij")
+    sphere = (np.sqrt((zz - 20) ** 2 + (yy - 12) ** 2 + (xx - 48) ** 2) - 9.0).astype(np.float32)
+    isos = [0.3, -0.2, 0.0, 0.9, 0.0]
+    monkeypatch.setenv("MC33_B200_DEVICES", "0")
+    lib1 = dropin("f32")
+    ones = lib1.extract_many(a, isos) + lib1.extract_many(sphere, [0.0, 5.0])
+    for m, iso in zip(ones[:2], isos[:2]):
+        compare_exact(oracle_extract(a, iso, "f32"), m, nrm_atol=1e-6)
+    monkeypatch.delenv("MC33_B200_DEVICES")
+    monkeypatch.setenv("MC33_B200_GPUS", "1")
+    monkeypatch.setenv("MC33_B200_CHUNKS", str(chunks))
+    monkeypatch.setenv("MC33_B200_SPECULATE", spec)
+    lib = dropin("f32")
+    manys = lib.extract_many(a, isos) + lib.extract_many(sphere, [0.0, 5.0])
+    assert lib.lib.mc33_dropin_slabs_last() == chunks and lib.lib.mc33_dropin_gpus_last() == 1
+    for one, many in zip(ones, manys):
+        _same_mesh_up_to_slab_numbering(one, many)
+        if spec == "0" or chunks == 1:
+            assert (many.capv, many.capt) == (many.nV, max(many.nT, 1))
