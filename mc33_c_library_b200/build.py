@@ -54,7 +54,8 @@ def nvcc_path():
 def build_cuda(force=False, extra=()):
     LIB.mkdir(exist_ok=True)
     out = LIB / "libmc33cu.so"
-    srcs = [CSRC / "mc33_kernels.cu", CSRC / "mc33_core.cuh", CSRC / "mc33_tables.h", ROOT / "include" / "mc33cu.h"]
+    srcs = [CSRC / "mc33_kernels.cu", CSRC / "mc33_core.cuh", CSRC / "mc33_pipeline.cuh", CSRC / "mc33_simt.h", CSRC / "mc33_tables.h",
+            ROOT / "include" / "mc33cu.h"]
     if force or not _newer(out, srcs):
         _run([nvcc_path(), *NVCC_FLAGS, *extra, CSRC / "mc33_kernels.cu", "-o", out])
     return out

@@ -8,16 +8,20 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import torch
 import bench
+sys.path.insert(0, str(ROOT / 'tools'))
+import workloads
 from mc33_c_library_b200 import _cabi as cabi
 from mc33_c_library_b200.device import Extractor
 
 n = 512
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 dev = torch.device("cuda", 0)
-grid = bench.gyroid_device(n, 0, n, n, dev)
-isos = bench.ISOS
-exs = [Extractor(cabi.make_desc(cabi.F32, n - 1, n - 1, n - 1), 0) for _ in range(2)]
-streams = [torch.cuda.Stream() for _ in range(2)]
+W = workloads.make('cfg2')
+grid = W.device_slab(0, n, dev)
+isos = list(W.isos)
+nstreams = int(os.environ.get('DUAL_STREAMS', '2'))
+exs = [Extractor(cabi.make_desc(cabi.F32, n - 1, n - 1, n - 1), 0) for _ in range(nstreams)]
+streams = [torch.cuda.Stream() for _ in range(nstreams)]
 bufs = []
 for ex, s in zip(exs, streams):
     ex.bind(grid)
@@ -29,7 +33,7 @@ torch.cuda.synchronize()
 
 def sweep():
     for j, iso in enumerate(isos):
-        exs[j & 1].extract_async(iso, bufs[j & 1])
+        exs[j % nstreams].extract_async(iso, bufs[j % nstreams])
 
 for _ in range(2):
     sweep()
@@ -51,4 +55,4 @@ torch.cuda.synchronize()
 for ex in exs:
     ex.sync()
 env = {k: v for k, v in os.environ.items() if k.startswith("MC33_B200_")}
-print(json.dumps({"env": env, "dual_ms_per_iso": round(e0.elapsed_time(e1) / (reps * len(isos)), 4)}))
+print(json.dumps({"env": env, "streams": nstreams, "dual_ms_per_iso": round(e0.elapsed_time(e1) / (reps * len(isos)), 4)}))
