@@ -577,12 +577,12 @@ unsigned long long size_of_isosurface(MC33 *M, MC33_real iso, unsigned int *nV, 
 	return k.nV * (6 * sizeof(MC33_real) + sizeof(int)) + k.nT * (3 * sizeof(int)) + sizeof(surface);
 }
 
-/* estimated capacities are rounded up to four steps per octave, so that the calls of an iso sweep ask the
+/* estimated capacities are rounded up to eight steps per octave, so that the calls of an iso sweep ask the
  * page-locked pool for the same few block sizes again and again */
 static unsigned long long round_cap(unsigned long long n)
 {
 	unsigned long long step = 1;
-	while (step * 8 <= n) step *= 2;               /* step = 2^(floor(log2 n) - 2) */
+	while (step * 16 <= n) step *= 2;              /* step = 2^(floor(log2 n) - 3) */
 	return (n + step - 1) / step * step;
 }
 
@@ -601,8 +601,9 @@ static int alloc_result(surface *S, unsigned long long capv, unsigned long long 
 
 /* how much room the result arrays get when they must be sized before every slab has been counted: what the
  * extractor has seen so far on this grid (an iso sweep), else the slabs counted so far scaled to the whole grid,
- * with head room (capv / capt > nV / nT, as after the reference's block-wise growth, c:489-510).
- * MC33_B200_SPECULATE=<factor> changes the head room (default 1.5); 0 waits for all the counts instead. */
+ * with head room (capv / capt > nV / nT, as after the reference's block-wise growth, c:489-510): factor 1.5 on the
+ * extrapolation (MC33_B200_SPECULATE=<factor> changes it; 0 waits for all the counts instead), 0.8 of that on the
+ * history (the largest mesh so far is a better guide than the first slabs of this one). */
 /* MC33_B200_TRACE=1: host-clock time line of a call on stderr (when each slab's count was in, when the call ended) */
 static double now_ms(void)
 {
@@ -654,8 +655,9 @@ surface *calculate_isosurface(MC33 *M, MC33_real iso)
 				else {
 					const double up = (double)p->nslab / (i + 1);
 					const double ev = (double)nvb * up, et = (double)ntb * up;
-					cv = round_cap((unsigned long long)(fac * ((double)p->hist_nV > ev ? (double)p->hist_nV : ev)) + 1024);
-					ct = round_cap((unsigned long long)(fac * ((double)p->hist_nT > et ? (double)p->hist_nT : et)) + 1024);
+					const double hv = 0.8 * (double)p->hist_nV, ht = 0.8 * (double)p->hist_nT;
+					cv = round_cap((unsigned long long)(fac * (hv > ev ? hv : ev)) + 1024);
+					ct = round_cap((unsigned long long)(fac * (ht > et ? ht : et)) + 1024);
 				}
 				if (cv >= nvb && ct >= ntb) {
 					if (alloc_result(S, cv, ct)) { rc = MC33CU_ERR_NOMEM; break; }
