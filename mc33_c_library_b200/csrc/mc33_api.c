@@ -424,7 +424,7 @@ MC33 *create_MC33(_GRD *G)
 	if (want > ndev) want = ndev;
 	if (want > MC33_MAX_SLABS) want = MC33_MAX_SLABS;
 	if (want < 1) want = 1;
-	/* z-chunks per GPU (MC33_B200_CHUNKS, default: about 128 MB of samples each, at most 8): the link is the
+	/* z-chunks per GPU (MC33_B200_CHUNKS, default: about 64 MB of samples each, at most 8): the link is the
 	 * bottleneck of a call (the samples go up, the mesh comes down), so a GPU's share is cut further and its
 	 * chunks are uploaded one after the other -- chunk k is counted, emitted and its part of the mesh
 	 * downloaded while chunk k+1 is still arriving (PCIe is full duplex).  Chunks are dealt round-robin:
@@ -434,7 +434,7 @@ MC33 *create_MC33(_GRD *G)
 	const char *ce = getenv("MC33_B200_CHUNKS");
 	if (ce && atoi(ce) > 0) chunks = atoi(ce);
 	else {
-		chunks = (int)(bytes / want / (128.0 * 1024 * 1024));
+		chunks = (int)(bytes / want / (64.0 * 1024 * 1024));
 		if (chunks > 8) chunks = 8;
 	}
 	if (chunks < 1) chunks = 1;
