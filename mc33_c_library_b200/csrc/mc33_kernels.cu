@@ -1191,6 +1191,7 @@ struct mc33cu_ctx {
 	int cells;                             // cell kernel: 0 both launched, the device picks by the on-iso statistic; 1 / 2 force one
 	int vtx;                               // 2: vertices straight from the bitmaps (no vertex tasks); 1: the round-1 task form
 	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
+	bool fine_env;                         // ... set by the environment (A/B runs): no automatic choice for small grids
 	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
 	// bitmaps of the single-isovalue path (P.S / P.Z / P.rowZ point here or into a sweep set)
 	uint32_t *S0, *Z0, *rowZ0, *D0;
@@ -1350,8 +1351,8 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	if (const char *e = getenv("MC33_B200_EMC2_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emc2_per_sm = (uint32_t)v; }
 	c->P.dbg_noz = getenv("MC33_B200_DEBUG_NOZ") ? 1u : 0u;
 	c->fine_pct = 8; c->fine_rows = 4;
-	if (const char *e = getenv("MC33_B200_FINE_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) c->fine_pct = (uint32_t)v; }
-	if (const char *e = getenv("MC33_B200_FINE_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 32) c->fine_rows = (uint32_t)v; }
+	if (const char *e = getenv("MC33_B200_FINE_PCT")) { int v = atoi(e); if (v >= 0 && v <= 100) { c->fine_pct = (uint32_t)v; c->fine_env = true; } }
+	if (const char *e = getenv("MC33_B200_FINE_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 32) { c->fine_rows = (uint32_t)v; c->fine_env = true; } }
 	if (const char *e = getenv("MC33_B200_EMC_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emc_per_sm = (uint32_t)v; }
 	if (const char *e = getenv("MC33_B200_EMV_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->emv_per_sm = (uint32_t)v; }
 	int rc = upload_tables();
@@ -1832,8 +1833,15 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		// work units: whole groups of G rows first, the last rows (about one group per resident
 		// warp's worth ... c->fine_pct per cent) in units of gfine rows
 		const uint32_t nrows = re - rb;
-		const uint32_t gfine = P.G >= 4 ? (c->fine_rows < P.G ? c->fine_rows : P.G) : P.G;
+		uint32_t gfine = P.G >= 4 ? (c->fine_rows < P.G ? c->fine_rows : P.G) : P.G;
 		uint32_t ncoarse = (uint32_t)((uint64_t)nrows * (100u - c->fine_pct) / 100u) / P.G;
+		// a small grid has fewer whole groups than the GPU has warps to run them (201^3: 2525 groups of 16 rows against
+		// 4736 warp slots), and the kernel takes as long as its busiest warp: hand out all of it in small units
+		// (cfg1: cells 0.037 -> 0.029 ms with units of 8 rows)
+		if (!c->fine_env && nrows / P.G < 4u * (uint32_t)c->n_sm * c->emc_per_sm * EM_WARPS && P.G >= 4) {
+			gfine = P.G < 8u ? P.G : 8u;
+			ncoarse = 0;
+		}
 		if (gfine == P.G) ncoarse = nrows / P.G;
 		const uint32_t ngroups = ncoarse + (nrows - ncoarse * P.G + gfine - 1) / gfine;
 		uint32_t grid = (uint32_t)c->n_sm * c->emc_per_sm;
