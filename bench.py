@@ -262,6 +262,15 @@ class Rig:
         self.gath1 = [torch.zeros((world, 4), dtype=torch.int32, device=self.dev) for _ in range(n)]
         self.bases_dev = torch.zeros((n, 2), dtype=torch.int32, device=self.dev)
         self.npts_owned = (sl.cell_z1 - sl.cell_z0 + (1 if sl.is_last else 0)) * NY * NX
+        # An iso sweep on one GPU: once the sweep classify has run its isovalues are independent (every set keeps its own
+        # count state, the context one vertex-task buffer per stream), so they alternate between this rank's stream and a
+        # second one, each with its own output buffers: the tail of one extraction's kernels overlaps the next one's
+        # (tools/time_overlap.py: 0.360 -> 0.344 ms per isosurface at cfg2; more than two streams do not help).
+        self.side, self.side_buf = None, None
+        if world == 1 and W.sweep and n > 1 and int(os.environ.get("MC33_BENCH_STREAMS", "2")) > 1:
+            self.side = torch.cuda.Stream(device=self.dev)
+            self.side_buf = self.ex.alloc(self.capV, self.capT, keys=keys)
+            self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     def step(self):
         """one pass over the workload's isovalues"""
@@ -269,7 +278,20 @@ class Rig:
         ex, W, n = self.ex, self.W, len(self.isos)
         if W.sweep:
             ex.classify_sweep(self.isos)
-        if self.world == 1:
+        if self.world == 1 and self.side is not None:
+            self.ev_fork.record(self.stream)
+            self.side.wait_event(self.ev_fork)
+            for j in range(n):
+                if j & 1:
+                    ex.use_stream(self.side)
+                    ex.extract_set_async(j, self.side_buf)
+                else:
+                    ex.use_stream(self.stream)
+                    ex.extract_set_async(j, self.buf)
+            self.ev_join.record(self.side)
+            self.stream.wait_event(self.ev_join)
+            ex.use_stream(self.stream)
+        elif self.world == 1:
             for j, iso in enumerate(self.isos):
                 if W.sweep:
                     ex.extract_set_async(j, self.buf)
@@ -397,6 +419,7 @@ class Rig:
     def close(self):
         self.ex.close()
         self.buf = None
+        self.side_buf = None
         self.grid = None
 
 
@@ -598,7 +621,8 @@ def measure(W, args, rank, world, local, with_extras=True):
                           "l2": f"inputs larger than L2 ({slab_bytes / 1e6:.0f} MB of samples per GPU vs 126 MB L2)"
                                 if slab_bytes > 126e6 else "inputs fit L2; every step rewrites > L2 of bitmaps / prefixes / mesh in between",
                           "step": ("one 8-isovalue sweep, grid resident in HBM: the samples are read once for the 8 isovalues "
-                                   "(mc33cu_classify_sweep), then count / scan / emit per isovalue") if W.sweep else
+                                   "(mc33cu_classify_sweep), then count / scan / emit per isovalue"
+                                   + (", the isovalues alternating between two CUDA streams of the context" if rig.side is not None else "")) if W.sweep else
                                   f"one pass over {n_iso} isovalue(s), grid resident in HBM: classify, count / scan, emit per isovalue"},
                "mtriangles_per_s": tri_step / (ms_step * 1e-3) * 1e-6,
                "ms_per_isosurface": ms_step / n_iso,

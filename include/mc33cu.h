@@ -107,7 +107,11 @@ void mc33cu_destroy(mc33cu_ctx *ctx);
  * MC33.O/D/ca/cb/_A/A_ and mult_Abf at store time, so the drop-in re-sends them
  * before every extraction */
 int  mc33cu_set_geometry(mc33cu_ctx *ctx, const mc33cu_desc *desc);
-/* cudaStream_t as void*; NULL = the context's own stream */
+/* cudaStream_t as void*; NULL = the context's own stream.  The stream may be changed between calls: the sets of an
+ * iso sweep (mc33cu_classify_sweep) are independent of each other, so mc33cu_extract_set_device for different sets
+ * may be issued on different streams and run side by side (the caller orders them after the sweep classify and keeps
+ * one set of output arrays per stream; the context keeps its per-extraction scratch per stream).  mc33cu_sync waits
+ * for the current stream and for every extraction issued on another one. */
 int  mc33cu_set_stream(mc33cu_ctx *ctx, void *cuda_stream);
 
 /* bind the samples.  *_device borrows a device pointer (no copy); the two upload

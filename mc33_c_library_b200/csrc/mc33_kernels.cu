@@ -1153,6 +1153,7 @@ static int fail(int code, const char *fmt, const char *a = "", const char *b = "
 		                                   "%s: %s", #call, cudaGetErrorString(e_));             \
 	} while (0)
 
+#define MC33CU_MAX_STREAMS 4
 struct mc33cu_ctx {
 	mc33cu_desc d;
 	int device;
@@ -1192,7 +1193,12 @@ struct mc33cu_ctx {
 	int vtx;                               // 2: vertices straight from the bitmaps (no vertex tasks); 1: the round-1 task form
 	uint32_t fine_pct, fine_rows;          // k_emit_cells: share of the rows handed out in small units at the end, unit size
 	bool fine_env;                         // ... set by the environment (A/B runs): no automatic choice for small grids
-	uint64_t *vtask; uint64_t vtask_cap;   // vertex tasks, grown to the largest output capacity seen
+	// vertex tasks (written by the cell kernel, read by the vertex kernel of the same extraction), grown to the largest
+	// output capacity seen; one buffer per stream the context has been used on, so that extractions of different sweep
+	// sets may run side by side on different streams
+	struct { cudaStream_t s; uint64_t *p; uint64_t cap; cudaEvent_t done; uint64_t stamp; } vt[MC33CU_MAX_STREAMS];
+	int n_vt, vt_cur;
+	uint64_t vt_clock;
 	// bitmaps of the single-isovalue path (P.S / P.Z / P.rowZ point here or into a sweep set)
 	uint32_t *S0, *Z0, *rowZ0, *D0;
 	size_t dwords;                         // words of one Z dirty-bit array
@@ -1283,7 +1289,7 @@ extern "C" void mc33cu_destroy(mc33cu_ctx *c)
 	cudaFree(c->swS); cudaFree(c->swZ); cudaFree(c->swRowZ); cudaFree(c->swAny); cudaFree(c->swD); cudaFree(c->D0);
 	cudaFree(c->rowBV0); cudaFree(c->totals0);
 	cudaFree(c->blk0);
-	cudaFree(c->vtask);
+	for (int i = 0; i < c->n_vt; i++) { cudaFree(c->vt[i].p); cudaEventDestroy(c->vt[i].done); }
 	cudaFree(c->lb0); cudaFree(c->lbt0); cudaFree(c->pcache0); cudaFree(c->swLb); cudaFree(c->swLbt); cudaFree(c->swPcache);
 	cudaFree(c->grid_owned);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -1902,6 +1908,7 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 		c->launches++;
 	}
 	if (c->timing) { CU(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
+	if (P.vtask) CU(cudaEventRecord(c->vt[c->vt_cur].done, s));     // (mc33cu_sync and a slot that changes hands wait for it)
 	CU(cudaGetLastError());
 	return MC33CU_OK;
 }
@@ -1960,16 +1967,36 @@ static int set_out(mc33cu_ctx *c, const mc33cu_out *o)
 {
 	Params &P = c->P;
 	const bool need_tasks = !(c->pipe == 2 && c->vtx == 2);
-	if (need_tasks && o->capV > c->vtask_cap) {
-		// (first extraction, or a larger output than any before: not on the steady-state path)
-		CU(cudaStreamSynchronize(c->stream));
-		cudaFree(c->vtask);
-		c->vtask = nullptr; c->vtask_cap = 0;
-		const uint64_t cap = (uint64_t)o->capV + o->capV / 8 + 1024;
-		CU(cudaMalloc((void **)&c->vtask, cap * sizeof(uint64_t)));
-		c->vtask_cap = cap;
+	P.vtask = nullptr;
+	if (need_tasks) {
+		int k = 0;
+		while (k < c->n_vt && c->vt[k].s != c->stream) k++;
+		if (k == c->n_vt) {
+			if (k < MC33CU_MAX_STREAMS) {
+				c->vt[k].p = nullptr; c->vt[k].cap = 0;
+				CU(cudaEventCreateWithFlags(&c->vt[k].done, cudaEventDisableTiming));
+				c->n_vt++;
+			} else {
+				// more streams than slots: the slot used longest ago changes hands once its last extraction is through
+				k = 0;
+				for (int i = 1; i < c->n_vt; i++) if (c->vt[i].stamp < c->vt[k].stamp) k = i;
+				CU(cudaEventSynchronize(c->vt[k].done));
+			}
+			c->vt[k].s = c->stream;
+		}
+		c->vt[k].stamp = ++c->vt_clock;
+		c->vt_cur = k;
+		if (o->capV > c->vt[k].cap) {
+			// (first extraction on this stream, or a larger output than any before: not on the steady-state path)
+			CU(cudaStreamSynchronize(c->stream));
+			cudaFree(c->vt[k].p);
+			c->vt[k].p = nullptr; c->vt[k].cap = 0;
+			const uint64_t cap = (uint64_t)o->capV + o->capV / 8 + 1024;
+			CU(cudaMalloc((void **)&c->vt[k].p, cap * sizeof(uint64_t)));
+			c->vt[k].cap = cap;
+		}
+		P.vtask = c->vt[k].p;
 	}
-	P.vtask = need_tasks ? c->vtask : nullptr;
 	P.V = o->V; P.N = o->N; P.color = o->color; P.T = o->T; P.vkey = o->vkey; P.tcell = o->tcell;
 	P.capV = o->capV; P.capT = o->capT;
 	P.vbase = o->vbase; P.vbase_next = o->vbase_next; P.dbases = o->dev_bases;
@@ -1987,6 +2014,9 @@ static int fetch_totals(mc33cu_ctx *c, uint32_t *flags = nullptr)
 	uint32_t want = c->pending_mask | (c->counted ? 1u << (c->counted_set + 1) : 0u);
 	if (!c->counted && !want) want = 1u;
 	want &= ~c->hvalid_mask | c->pending_mask;
+	// (extractions may have been issued on other streams of this context: their totals are read after them)
+	for (int i = 0; i < c->n_vt; i++)
+		if (c->vt[i].s != c->stream) CU(cudaEventSynchronize(c->vt[i].done));
 	for (int st = -1; st < SWEEP_MAX; st++)
 		if ((want >> (st + 1)) & 1u) {
 			if (st >= 0 && !c->swTotals) continue;

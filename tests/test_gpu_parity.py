@@ -457,6 +457,41 @@ def test_classify_sweep_matches_single_extractions(variant, shape, scale, isos):
     ex.close()
 
 
+@pytest.mark.parametrize("nstreams", [2, 6])
+def test_sweep_sets_on_several_streams(nstreams):
+    """the sets of one sweep extracted side by side on several CUDA streams of ONE context (bench.py's cfg2
+    schedule): the context keeps a vertex-task buffer per stream (four slots: with six streams slots change
+    hands), mc33cu_sync waits for all of them and reports every set's counts; meshes == the oracle's"""
+    import torch
+    from mc33_c_library_b200.device import Extractor
+    isos = [-0.6, -0.3, -0.1, 0.0, 0.1, 0.2, 0.4, 0.6]
+    a = gyroid_grid(128, periods=3)
+    ex = Extractor(make_desc(a.shape, "f32", None))
+    ex.upload(a)
+    wants = [oracle_extract(a, v, "f32") for v in isos]
+    capV, capT = max(w.nV for w in wants) + 8, max(w.nT for w in wants) + 8
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(nstreams)]
+    bufs = [ex.alloc(capV, capT, keys=True) for _ in isos]
+    for rep in range(2):
+        ex.use_stream(main)
+        ex.classify_sweep(isos)
+        ev = main.record_event()
+        for j in range(len(isos)):
+            s = streams[j % nstreams]
+            s.wait_event(ev)
+            ex.use_stream(s)
+            ex.extract_set_async(j, bufs[j])
+        ex.use_stream(main)
+        ex.sync()                       # waits for the extractions on the other streams too
+        for j, (want, b) in enumerate(zip(wants, bufs)):
+            nV, nT = want.nV, want.nT
+            g = Mesh(b["V"][:nV].cpu().numpy(), b["N"][:nV].cpu().numpy(), b["T"][:nT].cpu().numpy().view(np.uint32),
+                     color=b["color"][:nV].cpu().numpy(), vkey=b["vkey"][:nV].cpu().numpy(), tcell=b["tcell"][:nT].cpu().numpy())
+            _same(want, g)
+    ex.close()
+
+
 def test_sweep_sets_counted_first_then_emitted_across_slabs():
     """bench.py's multi-GPU sweep flow on one GPU: every slab classifies the sweep once and counts ALL its
     sets, the counts are 'all-gathered' as [slab][set][4], mc33cu_slab_bases_strided picks a set's column,
