@@ -860,15 +860,29 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
                             // as long as the busiest lane of the warp.  Kept for A/B.
 #endif
 #define EM_TW 96         // triangles per staging window
-#define EM_SCR (13 * 32 + 3 * EM_TW)      // per-warp scratch words: 13 ids x 32 lanes + the triangle window (or 8 (mask, base) pairs x 32 lanes)
+#if EMC_TRI_STAGED
+#define EM_SCR (13 * 32 + 3 * EM_TW)      // per-warp scratch words: 13 ids x 32 lanes + the triangle window
+#else
+#define EM_SCR (13 * 32 + 96)             // per-warp scratch words: 13 ids x 32 lanes + one owner byte per triangle of a round (<= 32 x 12)
+#endif
 #ifndef EMV_MINB
 #define EMV_MINB 5      // resident CTAs per SM the emit kernels are compiled for (register cap)
 #endif
 #ifndef EMC_MINB
 #define EMC_MINB 4
 #endif
-#define EM_ROWT 64      // per-warp row table words: (y, z) of the group's rows (G <= 32)
-#define EMC_SMEM (TBL_BYTES + EM_WARPS * (CQ + EM_SCR + EM_ROWT) * 4)
+#ifndef EMC_V2
+#define EMC_V2 1        // 1: per-row values of the cell kernel (row offsets, id bases, ownership) come from a table built once per
+                        // group, the pattern from the packed case table, the capacity check is hoisted out of the triangle loop
+#endif
+// per-warp row table words for groups of G rows (G <= 32): RowT / (y, z) of the group's rows.  Sized by the grid's G at
+// launch: shared memory the kernel does not take stays L1 cache -- for this kernel and for whatever runs next to it.
+#if EMC_V2
+#define EM_ROWT(G) (12u * (G))
+#else
+#define EM_ROWT(G) 64u
+#endif
+#define EMC_SMEM(G) (TBL_BYTES + EM_WARPS * (CQ + EM_SCR + EM_ROWT(G)) * 4)
 
 // K3, dense: thread id computes vertex id from the task the cell kernel left in the
 // vertex's own slot of N (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
@@ -892,6 +906,57 @@ __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_co
 	for (uint32_t id = blockIdx.x * 256u + threadIdx.x; id < n; id += gridDim.x * 256u) run_vertex_task<Sample, KEYS>(P, id);
 }
 
+// What a visited cell of row lr needs about its four point rows (suffix = dy dz), built once per row group: word
+// offsets of the rows in the bitmaps / prefixes, id of each row's first vertex as a GLOBAL id (the halo slice is
+// numbered by the next slab), and which of the row's points / cells this slab owns.  (A row that does not exist --
+// beyond the grid's high faces -- is replaced by the row itself, which empties the plane towards it.)
+struct RowT { uint32_t i00, i10, i01, i11, r00, r10, r01, r11, y, z, flags, g0; };
+
+__device__ __forceinline__ RowT make_rowt(const Params &P, uint32_t lr, uint32_t vb, uint32_t vbn)
+{
+	RowT t;
+	const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+	const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? P.NY : 0u;
+	const uint32_t l00 = lr, l10 = l00 + uy, l01 = l00 + uz, l11 = l01 + uy;
+	const uint32_t g0 = z == P.hz ? vbn : vb, g1 = z + 1 == P.hz ? vbn : vb;
+	t.i00 = l00 * P.WP; t.i10 = l10 * P.WP; t.i01 = l01 * P.WP; t.i11 = l11 * P.WP;
+	t.r00 = P.rowBV[l00] + g0; t.r10 = P.rowBV[l10] + g0; t.r01 = P.rowBV[l01] + g1; t.r11 = P.rowBV[l11] + g1;
+	t.y = y; t.z = z;
+	t.flags = (row_points_owned(P, z) ? 1u : 0u) | (row_cells_owned(P, z, y) ? 2u : 0u);
+	t.g0 = g0;
+	return t;
+}
+
+// cell_fast (mc33_core.cuh) with the per-row work taken from the row table: 12 loads, 8 popcounts.  (No mask for the
+// X plane's last point: a rank only counts bits below the cell's own, and the spurious bit of the row's last point
+// sits above every cell of its word; the caller clears it from `own`.)
+__device__ __forceinline__ unsigned cell_fast_rt(const Params &P, const RowT &t, uint32_t x, uint32_t *id, unsigned &own)
+{
+	const uint32_t w = x >> 5, b = x & 31u;
+	const uint32_t i00 = t.i00 + w, i10 = t.i10 + w, i01 = t.i01 + w, i11 = t.i11 + w;
+	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
+	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
+	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
+	const uint64_t p00 = P.wpreV[i00], p10 = P.wpreV[i10], p01 = P.wpreV[i01], p11 = P.wpreV[i11];
+	const uint32_t lo0 = (1u << b) - 1u;
+	const uint32_t mX00 = s00 ^ x00, mY00 = s00 ^ s10, mZ00 = s00 ^ s01;
+	const uint32_t mX10 = s10 ^ x10, mZ10 = s10 ^ s11;
+	const uint32_t mX01 = s01 ^ x01, mY01 = s01 ^ s11;
+	const uint32_t mX11 = s11 ^ x11;
+	const uint32_t bY = (mY00 >> b) & 1u, bZ = (mZ00 >> b) & 1u;
+	id[0] = t.r00 + fldV(p00, 1) + (uint32_t)popc32(mY00 & lo0);  id[4] = id[0] + bY;
+	id[1] = t.r10 + fldV(p10, 2) + (uint32_t)popc32(mZ10 & lo0);  id[5] = id[1] + ((mZ10 >> b) & 1u);
+	id[2] = t.r01 + fldV(p01, 1) + (uint32_t)popc32(mY01 & lo0);  id[6] = id[2] + ((mY01 >> b) & 1u);
+	id[3] = t.r00 + fldV(p00, 2) + (uint32_t)popc32(mZ00 & lo0);  id[7] = id[3] + bZ;
+	id[8] = t.r00 + fldV(p00, 0) + (uint32_t)popc32(mX00 & lo0);
+	id[9] = t.r10 + fldV(p10, 0) + (uint32_t)popc32(mX10 & lo0);
+	id[10] = t.r11 + fldV(p11, 0) + (uint32_t)popc32(mX11 & lo0);
+	id[11] = t.r01 + fldV(p01, 0) + (uint32_t)popc32(mX01 & lo0);
+	own = ((mX00 >> b) & 1u) | (bY << 1) | (bZ << 2);
+	return (((s00 >> b) & 1u) << 7) | (((s10 >> b) & 1u) << 6) | (((s11 >> b) & 1u) << 5) | (((s01 >> b) & 1u) << 4) |
+	       (((x00 >> b) & 1u) << 3) | (((x10 >> b) & 1u) << 2) | (((x11 >> b) & 1u) << 1) | ((x01 >> b) & 1u);
+}
+
 template <typename Sample, bool KEYS>
 __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_constant__ Params P, uint32_t row_begin, uint32_t row_end, uint32_t ngroups,
                                                                 uint32_t ncoarse, uint32_t gfine, uint32_t pick_nquads)
@@ -903,7 +968,12 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t *cq = (uint32_t *)(smem + TBL_BYTES) + wid * CQ;
 	uint32_t *scr = (uint32_t *)(smem + TBL_BYTES) + EM_WARPS * CQ + wid * EM_SCR;
-	uint2 *rowt = reinterpret_cast<uint2 *>((uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (CQ + EM_SCR) + wid * EM_ROWT);
+#if EMC_V2
+	RowT *rowt = reinterpret_cast<RowT *>((uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (CQ + EM_SCR) + wid * EM_ROWT(P.G));
+	const bool swap_all = P.geom.normal_neg != 0;
+#else
+	uint2 *rowt = reinterpret_cast<uint2 *>((uint32_t *)(smem + TBL_BYTES) + EM_WARPS * (CQ + EM_SCR) + wid * EM_ROWT(P.G));
+#endif
 	const bool anyz = *P.anyZp == P.zepoch;     // (tagged with the classify epoch: never has to be cleared)
 	const uint32_t nShared = P.totals->nShared;
 	const uint32_t vb = P.dbases ? P.dbases[0] : P.vbase;
@@ -924,10 +994,15 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 		const uint32_t lr0 = row_begin + (g < ncoarse ? g * P.G : ncoarse * P.G + (g - ncoarse) * gfine);
 		const uint32_t lrE = min(lr0 + (g < ncoarse ? P.G : gfine), row_end);
 		const bool gz = group_has_oniso(P, anyz, lr0, lane);
+#if EMC_V2
+		__syncwarp();                               // (the previous group's readers are done)
+		if (lane < P.G && lr0 + lane < lrE) rowt[lane] = make_rowt(P, lr0 + lane, vb, vbn);
+#else
 		if (lane < P.G) {
 			const uint32_t lr = lr0 + lane, zl = fastdiv(lr, P.NY, P.mNY);
 			rowt[lane] = make_uint2(lr - zl * P.NY, zl + P.zlo);
 		}
+#endif
 		__syncwarp();
 		// ======================= cells =======================
 		const uint32_t tbase = P.rowBT[lr0], cloc0 = nShared + P.rowBC[lr0];
@@ -973,6 +1048,52 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 				const uint32_t ncw = min((uint32_t)CQ, ncp - cw0);
 				for (uint32_t j0 = 0; j0 < ncw; j0 += 32) {
 					const bool on = j0 + lane < ncw;
+#if EMC_V2
+					// (scalars, not a CellPattern: the struct went through local memory)
+					unsigned zm = 0;
+					uint32_t x = 0, y = 0, z = 0, pstart = 0, pm = 0, pntri = 0, pcentre = 0;
+					if (on) {
+						const uint32_t e = cq[j0 + lane];
+						x = e & 0xFFFFu;
+						const RowT rt = rowt[e >> 16];
+						y = rt.y; z = rt.z;
+						const bool ownp = (rt.flags & 1u) != 0u, cellok = (rt.flags & 2u) != 0u && x < P.nx;
+						// groups near an on-iso sample: only the words it touches take the generic rules
+						if (!(gz && word_oniso(P, z, y, x >> 5))) {
+							uint32_t id[12];
+							unsigned own;
+							const unsigned idx = cell_fast_rt(P, rt, x, id, own);
+#pragma unroll
+							for (int k = 0; k < 12; k++) scr[k * 32 + lane] = id[k];
+							if (cellok && idx != 0u && idx != 255u) {
+								const uint32_t ci = tb.cinfo[idx];      // simple256 entry | winding flag << 16
+								pm = (ci >> 16) & 1u;
+								if ((ci & 0xFFFFu) != 0xFFFFu) {
+									pstart = ci & 0xFFFu; pntri = (ci >> 12) & 15u;
+								} else if (P.pcache) {
+									// complex cell: the count kernel of round 2 ran the MC33 tests and kept the pattern
+									pstart = P.pcache[(uint64_t)(lr0 + (e >> 16)) * (P.WP * 32u) + x];
+									const unsigned pi = tb.pat[pstart];
+									pntri = pi & 0x7Fu; pcentre = pi >> 7;
+								} else {
+									const CellPattern cp = cell_pattern_slow<Sample>(P, tb, x, y, z, idx, 0u);
+									pstart = cp.start; pm = cp.m; pntri = cp.ntri; pcentre = cp.centre;
+								}
+							}
+							if (ownp) {
+								const uint32_t lr = lr0 + (e >> 16);
+								if ((own & 1u) && x < P.nx) put_vertex_task(P, id[8] - rt.g0, lr, x, 0u, false);
+								if (own & 2u) put_vertex_task(P, id[0] - rt.g0, lr, x, 1u, false);
+								if (own & 4u) put_vertex_task(P, id[3] - rt.g0, lr, x, 2u, false);
+							}
+						} else {
+							const CellPattern cp = cell_slow<Sample>(P, tb, x, y, z, ownp, cellok, scr + lane, 32, zm);
+							pstart = cp.start; pm = cp.m; pntri = cp.ntri; pcentre = cp.centre;
+						}
+					}
+					CellPattern pat;
+					pat.start = pstart; pat.m = pm; pat.ntri = pntri; pat.centre = pcentre;
+#else
 					CellPattern pat;
 					pat.start = 0; pat.m = 0; pat.ntri = 0; pat.centre = 0;
 					unsigned zm = 0, b = 0;
@@ -1014,6 +1135,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							pat = cell_slow<Sample>(P, tb, x, y, z, ownp, cellok, scr + lane, 32, zm);
 						}
 					}
+#endif
 					// triangle / centre offsets: shuffle scan in sweep order
 					const uint32_t v = pat.ntri | (pat.centre << 16);
 					uint32_t iv = v;
@@ -1081,6 +1203,35 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							for (uint32_t j = 0; j < pat.ntri; j++) own[e0 + j] = (uint8_t)lane;
 						}
 						__syncwarp();
+#if EMC_V2
+						// bit 12: the triangle's first two corners change places (the pattern's winding flag against the grid's
+						// orientation, marching_cubes_33.c:1246-1250); the capacity is checked once for the round's triangles
+						const uint32_t sm = pat.start | (((pat.m != 0u) != swap_all ? 1u : 0u) << 12) | (zm ? 0x80000000u : 0u);
+						const uint32_t tfirst = tbase + runT;
+						const bool fits = (uint64_t)tfirst + ntot <= (uint64_t)P.capT;
+						uint32_t *const Tp = P.T + 3 * (uint64_t)tfirst;
+						for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
+							const uint32_t t = t0 + lane;
+							const bool act = t < ntot;
+							const int c = act ? (int)own[t] : 0;
+							const uint32_t csm = __shfl_sync(0xFFFFFFFFu, sm, c), ce0 = __shfl_sync(0xFFFFFFFFu, e0, c);
+							uint64_t ccell = 0;
+							if (KEYS && P.tcell) ccell = __shfl_sync(0xFFFFFFFFu, cell, c);
+							if (act && !(csm >> 31)) {
+								const unsigned tw = tb.tri[(csm & 0xFFFu) + (t - ce0)];
+								if (fits) {
+									const uint32_t *ids = scr + c;
+									const uint32_t i0 = ids[((tw >> 8) & 15u) * 32], i1 = ids[((tw >> 4) & 15u) * 32], i2 = ids[(tw & 15u) * 32];
+									const bool sw = ((csm >> 12) & 1u) != 0u;
+									uint32_t *T = Tp + 3 * t;
+									T[0] = sw ? i0 : i1; T[1] = sw ? i1 : i0; T[2] = i2;
+									if (KEYS && P.tcell) P.tcell[tfirst + t] = ccell;
+								} else {
+									emit_triangle_fast<KEYS>(P, tw, (((csm >> 12) & 1u) != 0u) != swap_all ? 1u : 0u, scr + c, 32, tfirst + t, ccell);
+								}
+							}
+						}
+#else
 						const uint32_t sm = pat.start | (pat.m << 12) | (zm ? 0x80000000u : 0u);
 						for (uint32_t t0 = 0; t0 < ntot; t0 += 32) {
 							const uint32_t t = t0 + lane;
@@ -1092,6 +1243,7 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 							if (act && !(csm >> 31))
 								emit_triangle_fast<KEYS>(P, tb.tri[(csm & 0xFFFu) + (t - ce0)], (csm >> 12) & 1u, scr + c, 32, tbase + runT + t, ccell);
 						}
+#endif
 						__syncwarp();
 						if (zm) cell_slow_triangles<Sample>(P, tb, x, y, z, pat, zm, vb + cl, tid, cell);
 					}
@@ -1315,8 +1467,8 @@ template <typename Sample> static int set_kernel_attrs(const ClsPlan &pl)
 	if ((size_t)pl.stage_bytes * CLS_STAGES > CLS_MAX_SMEM) return fail(MC33CU_ERR_ARG, "classify plan exceeds the shared memory ring");
 	CU(cudaFuncSetAttribute(k_classify<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
 	CU(cudaFuncSetAttribute(k_classify_vec<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
-	CU(cudaFuncSetAttribute(k_emit_cells<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
-	CU(cudaFuncSetAttribute(k_emit_cells<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM));
+	CU(cudaFuncSetAttribute(k_emit_cells<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM(32)));
+	CU(cudaFuncSetAttribute(k_emit_cells<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC_SMEM(32)));
 	CU(cudaFuncSetAttribute(k_emit_cells2<Sample, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC2_SMEM));
 	CU(cudaFuncSetAttribute(k_emit_cells2<Sample, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMC2_SMEM));
 	CU(cudaFuncSetAttribute(k_classify_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_MAX_SMEM));
@@ -1859,8 +2011,8 @@ template <typename Sample> static int launch_emit_phase(mc33cu_ctx *c)
 				if (c->pick_val[c->cur_state + 1][i] && c->pick_iso[c->cur_state + 1][i] == P.iso) which = c->pick_val[c->cur_state + 1][i];
 		if (which != 2) {
 			const uint32_t pk = which == 0 ? nquads : 0u;
-			if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine, pk);
-			else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM, s>>>(P, rb, re, ngroups, ncoarse, gfine, pk);
+			if (P.vkey || P.tcell) k_emit_cells<Sample, true><<<grid, 256, EMC_SMEM(P.G), s>>>(P, rb, re, ngroups, ncoarse, gfine, pk);
+			else k_emit_cells<Sample, false><<<grid, 256, EMC_SMEM(P.G), s>>>(P, rb, re, ngroups, ncoarse, gfine, pk);
 			if (which == 0) c->launches++;
 		}
 		if (which != 1) {
