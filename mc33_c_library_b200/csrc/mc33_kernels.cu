@@ -1224,7 +1224,11 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 									const uint32_t i0 = ids[((tw >> 8) & 15u) * 32], i1 = ids[((tw >> 4) & 15u) * 32], i2 = ids[(tw & 15u) * 32];
 									const bool sw = ((csm >> 12) & 1u) != 0u;
 									uint32_t *T = Tp + 3 * t;
+#if MC33_STREAM_STORES
+									__stcs(T, sw ? i0 : i1); __stcs(T + 1, sw ? i1 : i0); __stcs(T + 2, i2);     // (written once, read by nobody here)
+#else
 									T[0] = sw ? i0 : i1; T[1] = sw ? i1 : i0; T[2] = i2;
+#endif
 									if (KEYS && P.tcell) P.tcell[tfirst + t] = ccell;
 								} else {
 									emit_triangle_fast<KEYS>(P, tw, (((csm >> 12) & 1u) != 0u) != swap_all ? 1u : 0u, scr + c, 32, tfirst + t, ccell);

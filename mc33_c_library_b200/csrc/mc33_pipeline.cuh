@@ -867,7 +867,11 @@ SIMT_FN void emit_cells_body(const CX &cx, const Params &P, const Tables &tb, co
 										const uint32_t nw = 3u * (ntot - t0 < (uint32_t)P2_TW ? ntot - t0 : (uint32_t)P2_TW);
 										const uint64_t wbase = (uint64_t)(tbase + runT + t0) * 3u, wcap = (uint64_t)P.capT * 3u;
 										for (uint32_t w = lane; w < nw; w += 32) {
+#if defined(__CUDA_ARCH__) && MC33_STREAM_STORES
+											if (wbase + w < wcap) __stcs(P.T + (wbase + w), tst[w]);
+#else
 											if (wbase + w < wcap) P.T[wbase + w] = tst[w];
+#endif
 											else P.totals->overflow = 1;
 										}
 										cx.syncwarp();
