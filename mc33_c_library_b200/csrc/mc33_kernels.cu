@@ -871,6 +871,9 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
 #ifndef EMC_MINB
 #define EMC_MINB 4
 #endif
+#ifndef EMC_REVERSE
+#define EMC_REVERSE 1
+#endif
 #ifndef EMC_V2
 #define EMC_V2 1        // 1: per-row values of the cell kernel (row offsets, id bases, ownership) come from a table built once per
                         // group, the pattern from the packed case table, the capacity check is hoisted out of the triangle loop
@@ -991,7 +994,13 @@ __global__ void __launch_bounds__(256, EMC_MINB) k_emit_cells(const __grid_const
 	// find work and the last units are short (a warp takes ~20 us over a whole group).
 	for (; g < ngroups; g = __shfl_sync(0xFFFFFFFFu, gnext, 0)) {
 		if (lane == 0) gnext = nwarps + atomicAdd(&P.totals->ticket, 1u);
+#if EMC_REVERSE
+		// whole groups are taken from the high rows down: the count kernel wrote A / wpreV / row bases from the low rows
+		// up, so its last rows are the ones still in L2 when this kernel starts
+		const uint32_t lr0 = row_begin + (g < ncoarse ? (ncoarse - 1u - g) * P.G : ncoarse * P.G + (g - ncoarse) * gfine);
+#else
 		const uint32_t lr0 = row_begin + (g < ncoarse ? g * P.G : ncoarse * P.G + (g - ncoarse) * gfine);
+#endif
 		const uint32_t lrE = min(lr0 + (g < ncoarse ? P.G : gfine), row_end);
 		const bool gz = group_has_oniso(P, anyz, lr0, lane);
 #if EMC_V2
