@@ -1232,6 +1232,57 @@ MC_HDN unsigned cell_fast(const Params &P, uint32_t x, uint32_t y, uint32_t z, u
 	       (((x00 >> b) & 1u) << 3) | (((x10 >> b) & 1u) << 2) | (((x11 >> b) & 1u) << 1) | ((x01 >> b) & 1u);
 }
 
+// What a visited cell of row lr needs about its four point rows (suffix = dy dz), built once per row group: word
+// offsets of the rows in the bitmaps / prefixes, id of each row's first vertex as a GLOBAL id (the halo slice is
+// numbered by the next slab), and which of the row's points / cells this slab owns.  (A row that does not exist --
+// beyond the grid's high faces -- is replaced by the row itself, which empties the plane towards it.)
+struct RowT { uint32_t i00, i10, i01, i11, r00, r10, r01, r11, y, z, flags, g0; };
+
+MC_HD RowT make_rowt(const Params &P, uint32_t lr, uint32_t vb, uint32_t vbn)
+{
+	RowT t;
+	const uint32_t zl = fastdiv(lr, P.NY, P.mNY), y = lr - zl * P.NY, z = zl + P.zlo;
+	const uint32_t uy = y < P.ny ? 1u : 0u, uz = z < P.nz ? P.NY : 0u;
+	const uint32_t l00 = lr, l10 = l00 + uy, l01 = l00 + uz, l11 = l01 + uy;
+	const uint32_t g0 = z == P.hz ? vbn : vb, g1 = z + 1 == P.hz ? vbn : vb;
+	t.i00 = l00 * P.WP; t.i10 = l10 * P.WP; t.i01 = l01 * P.WP; t.i11 = l11 * P.WP;
+	t.r00 = P.rowBV[l00] + g0; t.r10 = P.rowBV[l10] + g0; t.r01 = P.rowBV[l01] + g1; t.r11 = P.rowBV[l11] + g1;
+	t.y = y; t.z = z;
+	t.flags = (row_points_owned(P, z) ? 1u : 0u) | (row_cells_owned(P, z, y) ? 2u : 0u);
+	t.g0 = g0;
+	return t;
+}
+
+// cell_fast (mc33_core.cuh) with the per-row work taken from the row table: 12 loads, 8 popcounts.  (No mask for the
+// X plane's last point: a rank only counts bits below the cell's own, and the spurious bit of the row's last point
+// sits above every cell of its word; the caller clears it from `own`.)
+MC_HD unsigned cell_fast_rt(const Params &P, const RowT &t, uint32_t x, uint32_t *id, unsigned &own)
+{
+	const uint32_t w = x >> 5, b = x & 31u;
+	const uint32_t i00 = t.i00 + w, i10 = t.i10 + w, i01 = t.i01 + w, i11 = t.i11 + w;
+	const uint32_t s00 = P.S[i00], s10 = P.S[i10], s01 = P.S[i01], s11 = P.S[i11];
+	const uint32_t x00 = shr1(s00, P.S[i00 + 1]), x10 = shr1(s10, P.S[i10 + 1]);
+	const uint32_t x01 = shr1(s01, P.S[i01 + 1]), x11 = shr1(s11, P.S[i11 + 1]);
+	const uint64_t p00 = P.wpreV[i00], p10 = P.wpreV[i10], p01 = P.wpreV[i01], p11 = P.wpreV[i11];
+	const uint32_t lo0 = (1u << b) - 1u;
+	const uint32_t mX00 = s00 ^ x00, mY00 = s00 ^ s10, mZ00 = s00 ^ s01;
+	const uint32_t mX10 = s10 ^ x10, mZ10 = s10 ^ s11;
+	const uint32_t mX01 = s01 ^ x01, mY01 = s01 ^ s11;
+	const uint32_t mX11 = s11 ^ x11;
+	const uint32_t bY = (mY00 >> b) & 1u, bZ = (mZ00 >> b) & 1u;
+	id[0] = t.r00 + fldV(p00, 1) + (uint32_t)popc32(mY00 & lo0);  id[4] = id[0] + bY;
+	id[1] = t.r10 + fldV(p10, 2) + (uint32_t)popc32(mZ10 & lo0);  id[5] = id[1] + ((mZ10 >> b) & 1u);
+	id[2] = t.r01 + fldV(p01, 1) + (uint32_t)popc32(mY01 & lo0);  id[6] = id[2] + ((mY01 >> b) & 1u);
+	id[3] = t.r00 + fldV(p00, 2) + (uint32_t)popc32(mZ00 & lo0);  id[7] = id[3] + bZ;
+	id[8] = t.r00 + fldV(p00, 0) + (uint32_t)popc32(mX00 & lo0);
+	id[9] = t.r10 + fldV(p10, 0) + (uint32_t)popc32(mX10 & lo0);
+	id[10] = t.r11 + fldV(p11, 0) + (uint32_t)popc32(mX11 & lo0);
+	id[11] = t.r01 + fldV(p01, 0) + (uint32_t)popc32(mX01 & lo0);
+	own = ((mX00 >> b) & 1u) | (bY << 1) | (bZ << 2);
+	return (((s00 >> b) & 1u) << 7) | (((s10 >> b) & 1u) << 6) | (((s11 >> b) & 1u) << 5) | (((s01 >> b) & 1u) << 4) |
+	       (((x00 >> b) & 1u) << 3) | (((x10 >> b) & 1u) << 2) | (((x11 >> b) & 1u) << 1) | ((x01 >> b) & 1u);
+}
+
 // triangle j of a cell whose 13 vertex ids (12 edges + centre) sit at ids[e * stride]
 template <bool KEYS = true>
 MC_HD void emit_triangle_fast(const Params &P, unsigned tw, unsigned m, const uint32_t *ids, uint32_t stride, uint32_t tid,

@@ -18,6 +18,8 @@
 
 using namespace mc33;
 
+static uint64_t g_rt_checked = 0, g_rt_mismatch = 0;      // MC33_EMU_CHECK_RT (see run())
+
 static const Tables &host_tables()
 {
 	static Tables tb;
@@ -87,6 +89,30 @@ static void run(Params &P, bool emit)
 		A.dbg_noprefix = getenv("MC33_EMU_LB_NOPREFIX") ? 1u : 0u;
 		mc33emu::launch(A.nblk, 256, P2_CNT_SMEM, [&](EmuCtx &cx) { count_body<Sample>(cx, P, tb, A); });
 	}
+	// The direct cell kernel (k_emit_cells in mc33_kernels.cu) is device-only; its per-cell arithmetic is not: with
+	// MC33_EMU_CHECK_RT the row-table form it uses (make_rowt + cell_fast_rt) is compared with cell_fast for every
+	// grid point of every row the kernel would visit, on the state the count kernel just left.
+	if (getenv("MC33_EMU_CHECK_RT") && !*P.anyZp) {
+		const uint32_t zend = P.pz1 > P.cz1 ? P.pz1 : P.cz1;
+		const uint32_t rb = (P.cz0 - P.zlo) * P.NY, re = (zend - P.zlo) * P.NY;
+		const uint32_t vb = P.vbase, vbn = P.vbase_next - P.totals->nShared;
+		for (uint32_t lr = rb; lr < re; lr++) {
+			const RowT rt = make_rowt(P, lr, vb, vbn);
+			const uint32_t z = lr / P.NY + P.zlo, y = lr % P.NY;
+			if (rt.y != y || rt.z != z) g_rt_mismatch++;
+			for (uint32_t x = 0; x <= P.nx; x++) {
+				uint32_t ia[12], ib[12];
+				unsigned oa, ob;
+				const unsigned xa = cell_fast(P, x, y, z, z == P.hz ? vbn : vb, z + 1 == P.hz ? vbn : vb, ia, oa);
+				const unsigned xb = cell_fast_rt(P, rt, x, ib, ob);
+				if (x >= P.nx) ob &= ~1u;               // (the kernel clears the X plane of the row's last point)
+				bool same = xa == xb && oa == ob;
+				for (int e = 0; e < 12; e++) same = same && ia[e] == ib[e];
+				g_rt_checked++;
+				if (!same) g_rt_mismatch++;
+			}
+		}
+	}
 	if (!emit) return;
 	// K4
 	{
@@ -116,6 +142,12 @@ static void run(Params &P, bool emit)
 			emit_vertices_body<Sample, true>(cx, P, A, cx.smem() + cx.warp() * P2_VX_WARP_BYTES);
 		});
 	}
+}
+
+extern "C" void mc33emu_rt_stats(uint64_t *checked, uint64_t *mismatch)
+{
+	*checked = g_rt_checked; *mismatch = g_rt_mismatch;
+	g_rt_checked = 0; g_rt_mismatch = 0;
 }
 
 extern "C" int mc33emu_run(const mc33cu_desc *d, const void *data, double iso, const mc33cu_out *o,

@@ -158,3 +158,34 @@ def test_kernel_bodies_task_free_vertex_kernel(monkeypatch):
     _same(oracle_extract(f, 0.0, "f32"), emu_extract(f, 0.0, "f32"))
     g = inclined_geom()
     _same(oracle_extract(f, 0.0, "f32", g), emu_extract(f, 0.0, "f32", g))
+
+
+@pytest.mark.parametrize("variant,shape,scale", [("f32", (9, 11, 70), 0), ("f32", (6, 5, 129), 0), ("u8", (7, 9, 97), 9)])
+def test_row_table_cell_arithmetic_matches_cell_fast(variant, shape, scale, monkeypatch):
+    """the direct cell kernel is device-only, its per-cell arithmetic is not: make_rowt + cell_fast_rt (what
+    k_emit_cells runs) against cell_fast on every grid point of every visited row, whole grid and z-slabs with halo
+    slices (ids of the seam slice in the next slab's space); grids without on-iso samples, as on the kernel's fast path"""
+    import ctypes as C
+    from support import hostemu_lib
+    emu = hostemu_lib()
+    emu.mc33emu_rt_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    monkeypatch.setenv("MC33_EMU_CHECK_RT", "1")
+    iso = 0.05 if variant == "f32" else 4.5
+    a = noise_grid(0, variant, scale=scale, shape=shape) if scale else noise_grid(0, variant, shape=shape)
+    n, bad = C.c_uint64(), C.c_uint64()
+    emu.mc33emu_rt_stats(C.byref(n), C.byref(bad))          # reset
+    whole = emu_extract(a, iso, variant)
+    emu.mc33emu_rt_stats(C.byref(n), C.byref(bad))
+    assert n.value >= (shape[0] - 1) * shape[1] * shape[2] and bad.value == 0
+    _same(oracle_extract(a, iso, variant), whole)
+    parts = [s for s in slabs.partition(a.shape[0] - 1, 3) if s is not None]
+    _, sdt, real = DTYPES[variant]
+    descs = [make_desc(a.shape, variant, None, s) for s in parts]
+    subs = [np.ascontiguousarray(a[s.z_lo:s.z_hi]) for s in parts]
+    counts = [emu_count(sub, iso, d) for sub, d in zip(subs, descs)]
+    b = slabs.bases([(int(k.nV), int(k.nT)) for k in counts])
+    emu.mc33emu_rt_stats(C.byref(n), C.byref(bad))          # (the count-only runs do not know the bases: reset)
+    for d, sub, k, (vb, vbn) in zip(descs, subs, counts, b):
+        emu_emit(sub, iso, d, k, real, vbase=vb, vbase_next=vbn)
+    emu.mc33emu_rt_stats(C.byref(n), C.byref(bad))
+    assert n.value > 0 and bad.value == 0
