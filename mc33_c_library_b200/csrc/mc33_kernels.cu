@@ -888,16 +888,16 @@ __global__ void __launch_bounds__(256) k_rowscan(const __grid_constant__ Params 
 #define EMC_SMEM(G) (TBL_BYTES + EM_WARPS * (CQ + EM_SCR + EM_ROWT(G)) * 4)
 
 // K3, dense: thread id computes vertex id from the task the cell kernel left in the
-// vertex's own slot of N (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
-// threads write consecutive V / N / color.
-// K3, dense: thread id computes vertex id from the task the cell kernel left in the
 // vertex's own slot (mc33_core.cuh "Vertex tasks"): no scan, no queue, consecutive
 // threads write consecutive V / N / color.
-// (Round 2 measured two alternatives and dropped both: 16-byte stores of four lanes' positions / normals after a
-// shuffle -- the kernel is bound by L1 wavefronts, ncu l1tex__throughput 87 %, and the twelve-byte stride touches every
-// sector three times -- ran 0.098 ms against 0.087: the warp-uniform loop it needs costs more than the stores save;
-// and a task-free form that rebuilds the plane masks per row group and stages the vertices in shared memory
-// ran 0.18 ms: the staging competes for the same L1 / shared-memory pipe.)
+// What bounds it (round 2, ncu): DRAM traffic in scattered 32-byte sectors -- the ten samples of a vertex arrive as
+// 8.6 sectors, the surface touches about half of the grid's sectors (275 MB read for 126 MB written at cfg2: 4.6 TB/s,
+// 70 % of the copy bandwidth).  Measured and dropped: 16-byte stores of four lanes' components after a shuffle (0.098
+// against 0.087 ms), V / N through a shared-memory transpose (0.093), aligned 4-sample loads instead of scalar gathers
+// (0.109: a 128-bit load of scattered lanes costs as many L1 wavefronts as the two loads it replaces, and the planes'
+// code paths diverge), a task-free form that rebuilds the plane masks per row group (0.18), a tile order of the ids for
+// large slices (slower).  Kept: streaming stores / loads for what is touched once (mc33_core.cuh, MC33_STREAM_STORES),
+// which keeps the sample lines of the next slice in L2 -- 36 % off on 2048 x 2048 slices.
 template <typename Sample, bool KEYS>
 __global__ void __launch_bounds__(256, EMV_MINB) k_emit_vertices(const __grid_constant__ Params P)
 {
