@@ -691,6 +691,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries ONE JSON line: whatever libraries print there while the job runs (NCCL announces its version on
+    # rank 0's stdout) goes to stderr instead; the descriptor comes back for the line itself
+    sys.stdout.flush()
+    keep_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = workloads.make(args.workload)
@@ -704,8 +709,11 @@ def run_ours(args):
             out["weak_cfg2"] = {k: w[k] for k in ("value", "unit", "ms_per_step", "ms_per_isosurface", "mtriangles_per_s", "gpu_launches")}
             out["weak_cfg2"]["scaling"] = "weak"
             out["weak_cfg2"]["workload"] = w["config"]["workload"]
+    sys.stdout.flush()
+    os.dup2(keep_stdout, 1)
+    os.close(keep_stdout)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
