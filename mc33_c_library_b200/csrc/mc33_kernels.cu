@@ -1501,9 +1501,24 @@ extern "C" int mc33cu_create(const mc33cu_desc *d, int device, mc33cu_ctx **out)
 	c->real_size = d->dtype == MC33CU_F64 ? 8 : 4;
 	c->n_samples = (uint64_t)P.Lrows * P.NX;
 	{
-		uint32_t rpw = 32;                               // rows per warp and k_count block
-		if (const char *e = getenv("MC33_B200_CNT_RPW")) { int v = atoi(e); if (v >= 1 && v <= 32) rpw = (uint32_t)v; }
-		c->cnt_gw = rpw / P.G ? rpw / P.G : 1;
+		// Rows per count block (8 warps x GW groups of G rows, at most 256).  The blocks of a wave finish together, so the
+		// kernel takes (number of waves) x (a block's rows + its fixed tail: ticket, barriers, look-back, about 300 quads'
+		// worth); the block size is chosen for the fewest row-times, larger blocks on a tie.  Measured: cfg5 (768^3, 2458
+		// blocks of 240 rows = 4.15 waves) 10.3 -> 8.9 ms with 200 rows (4.98 waves), a 258-slice slab of cfg4 0.454 ->
+		// 0.418 ms with 224 rows; cfg2 / cfg3 keep 256.  MC33_B200_CNT_RPW=<rows per warp> overrides.
+		const uint32_t gw_max = 32 / P.G ? 32 / P.G : 1;
+		const uint64_t slots = (uint64_t)c->n_sm * CNT2_MINB;
+		const uint32_t tail_rows = (300 + P.Q - 1) / P.Q;
+		uint32_t best = gw_max;
+		uint64_t best_cost = ~0ull;
+		for (uint32_t gw = gw_max; gw >= 1; gw--) {
+			const uint64_t rb = (uint64_t)CNT_WARPS * gw * P.G, nb = (P.Lrows + rb - 1) / rb;
+			const uint64_t cost = ((nb + slots - 1) / slots) * (rb + tail_rows);
+			if (cost < best_cost) { best_cost = cost; best = gw; }
+			if (gw == gw_max && nb <= slots) break;          // one wave of the largest blocks: smaller ones only add tails (cfg1)
+		}
+		c->cnt_gw = best;
+		if (const char *e = getenv("MC33_B200_CNT_RPW")) { int v = atoi(e); if (v >= 1 && v <= 32) c->cnt_gw = (uint32_t)v / P.G ? (uint32_t)v / P.G : 1; }
 		c->cnt_rb = CNT_WARPS * c->cnt_gw * P.G;
 		c->nblk = (P.Lrows + c->cnt_rb - 1) / c->cnt_rb;
 	}
